@@ -1,0 +1,14 @@
+"""B200-native SMPL body-model forward pass (drop-in for the reference's PyTorch SMPL layer).
+
+Public surface:
+    SMPL                 nn.Module, forward(betas, pose, cam=None, ...) -> (vertices, joints[, kp2d])
+    capi                 ctypes binding of include/smpl_b200.h (libsmpl_b200.so)
+    synthetic            seeded SMPL-shaped model tensors / parameters
+    sharding             batch sharding across ranks (+ optional NCCL gather of joints)
+"""
+from . import synthetic  # noqa: F401
+from . import capi  # noqa: F401
+from .smpl import SMPL  # noqa: F401
+from . import sharding  # noqa: F401
+
+__all__ = ["SMPL", "capi", "synthetic", "sharding"]

@@ -1,0 +1,41 @@
+// Shared definitions for the SMPL sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace smplb200 {
+
+constexpr int kJ = 24;             // joints (fixed by the kintree warp layout: lane j = joint j)
+constexpr int kP = 9 * (kJ - 1);   // 207 pose-feature terms
+constexpr int kCoefK = 224;        // padded contraction length (betas | pose_feature | 1 | 0...)
+constexpr int kMaxBetas = 16;
+constexpr int kVertTile = 128;     // vertices per tile == TMEM lanes == LBS CTA width
+
+// Device-resident packed model (all pointers are device pointers unless noted).
+struct DeviceModel {
+  int V, VP, NB, KB;               // verts, verts padded to 128, betas, basis rows (NB + 207 + 1)
+  int NC;                          // planar columns = 3 * VP
+  int max_nnz;                     // max skinning weights per vertex
+  int max_depth;                   // kinematic tree depth
+  int jreg_nnz;                    // total non-zeros of the joint regressor
+  const float* basis;              // [KB, NC] planar, row NB+207 = v_template
+  const float* j_template;         // [J*3]   folded J_regressor^T v_template
+  const float* j_shapedirs;        // [NB, J*3] folded J_regressor^T shapedirs
+  const int* parents;              // [J]
+  const int* depth;                // [J]
+  const float4* ell_w;             // [VP] up to 4 weights per vertex (zero padded)
+  const uint32_t* ell_j;           // [VP] 4 packed uint8 joint indices
+  const float* dense_w;            // [VP, J]
+  const int* jreg_ptr;             // [J+1] CSR over joints
+  const int* jreg_idx;             // [jreg_nnz] vertex index
+  const float* jreg_val;           // [jreg_nnz]
+  // tensor-core operand images (see k_blend_tc.cuh / k_lbs_tc.cuh)
+  const uint16_t* basis_bf16_hi;   // [NC/128 tiles][28 chunks][128 rows][8]   canonical K-major
+  const uint16_t* basis_bf16_lo;   // same, low part of the 2-term bf16 split
+  const uint32_t* basis_tf32;      // [NC/128 tiles][56 chunks][128 rows][4]
+  const uint32_t* w_tf32;          // [VP/128 tiles][12 chunks][128 rows][4]  (W_hi | W_lo)
+};
+
+__device__ __forceinline__ float ld_nc(const float* p) { return __ldg(p); }
+
+}  // namespace smplb200

@@ -1,0 +1,210 @@
+// k2: folded joint regression + Rodrigues + 24-joint kinematic chain, one warp per body.
+//
+// Lane j (< 24) owns joint j.  The chain is composed level-synchronously down the kintree: at
+// level L every lane fetches its parent's world transform with 12 warp shuffles and the lanes
+// whose depth == L compose  G_j = G_parent * [R_j | J_j - J_parent].  Joint regression is folded
+// at model-create time into  J = J_template + betas * J_shapedirs  (1,440 flop/body
+// instead of 992,160), so this kernel reads 340 B/body and never touches the vertex arrays.
+//
+// Rodrigues mirrors the eager idiom op for op with explicit round-to-nearest
+// mul/add so nvcc cannot contract what the eager layer rounds separately.
+#pragma once
+#include "common.cuh"
+
+namespace smplb200 {
+
+constexpr int kChainWarps = 8;
+
+struct ChainOut {
+  float* coef;            // [n, 224] fp32 or null
+  float* A;               // [n, 24, 12] or null
+  float* joints;          // [n, 24, 3] or null
+  uint16_t* coef_bf16_hi; // tensor-core operand images (null unless a tcgen05 path follows)
+  uint16_t* coef_bf16_lo;
+  uint32_t* coef_tf32;
+  uint32_t* a_tf32;       // [n/16 blocks][12 chunks][192 rows][4] tf32 hi|lo image of A (LBS blend)
+};
+
+__device__ __forceinline__ void rodrigues_hmr(float tx, float ty, float tz, float R[9]) {
+  const float eps = 1e-8f;
+  float ex = __fadd_rn(tx, eps), ey = __fadd_rn(ty, eps), ez = __fadd_rn(tz, eps);
+  float n2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+  float angle = __fsqrt_rn(n2);
+  float ax = __fdiv_rn(tx, angle), ay = __fdiv_rn(ty, angle), az = __fdiv_rn(tz, angle);
+  float half = __fmul_rn(angle, 0.5f);
+  float c = cosf(half), s = sinf(half);
+  float qw = c, qx = __fmul_rn(s, ax), qy = __fmul_rn(s, ay), qz = __fmul_rn(s, az);
+  float qn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qw, qw), __fmul_rn(qx, qx)),
+                                            __fmul_rn(qy, qy)), __fmul_rn(qz, qz)));
+  float w = __fdiv_rn(qw, qn), x = __fdiv_rn(qx, qn), y = __fdiv_rn(qy, qn), z = __fdiv_rn(qz, qn);
+  float w2 = __fmul_rn(w, w), x2 = __fmul_rn(x, x), y2 = __fmul_rn(y, y), z2 = __fmul_rn(z, z);
+  float wx = __fmul_rn(w, x), wy = __fmul_rn(w, y), wz = __fmul_rn(w, z);
+  float xy = __fmul_rn(x, y), xz = __fmul_rn(x, z), yz = __fmul_rn(y, z);
+  R[0] = __fsub_rn(__fsub_rn(__fadd_rn(w2, x2), y2), z2);
+  R[1] = __fsub_rn(__fmul_rn(2.f, xy), __fmul_rn(2.f, wz));
+  R[2] = __fadd_rn(__fmul_rn(2.f, wy), __fmul_rn(2.f, xz));
+  R[3] = __fadd_rn(__fmul_rn(2.f, wz), __fmul_rn(2.f, xy));
+  R[4] = __fsub_rn(__fadd_rn(__fsub_rn(w2, x2), y2), z2);
+  R[5] = __fsub_rn(__fmul_rn(2.f, yz), __fmul_rn(2.f, wx));
+  R[6] = __fsub_rn(__fmul_rn(2.f, xz), __fmul_rn(2.f, wy));
+  R[7] = __fadd_rn(__fmul_rn(2.f, wx), __fmul_rn(2.f, yz));
+  R[8] = __fadd_rn(__fsub_rn(__fsub_rn(w2, x2), y2), z2);
+}
+
+// Canonical K-major no-swizzle operand image offsets (in elements of the operand type):
+// an image is [chunks][rows][E] with E elements per 16-byte chunk; see k_blend_tc.cuh.
+__device__ __forceinline__ uint32_t f32_to_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
+  uint16_t r;
+  asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(uint32_t(h) << 16); }
+
+constexpr int kCoefBlock = 32;   // bodies per tensor-core coefficient image (MMA N)
+constexpr int kLbsBlock = 16;    // bodies per LBS blend image (MMA N = 12 * 16 = 192)
+constexpr int kLbsK = 48;        // blend contraction: [A_hi | A_lo] over 24 joints (tf32 split)
+
+__global__ void __launch_bounds__(kChainWarps * 32)
+k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __restrict__ pose,
+             long long n, ChainOut out, int rotate_base) {
+  __shared__ __align__(16) float s_coef[kChainWarps][kCoefK];
+  __shared__ __align__(16) float s_A[kChainWarps][kJ * 12];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * kChainWarps + warp;
+  if (b >= n) return;  // whole warp exits together; no block-level sync below
+  const int j = lane < kJ ? lane : 0;
+  const bool active = lane < kJ;
+  const int NB = m.NB;
+
+  // ---- inputs
+  float th0 = 0.f, th1 = 0.f, th2 = 0.f;
+  if (active) {
+    const float* p = pose + b * (3 * kJ) + 3 * j;
+    th0 = __ldg(p); th1 = __ldg(p + 1); th2 = __ldg(p + 2);
+  }
+  float R[9];
+  rodrigues_hmr(th0, th1, th2, R);
+
+  // ---- folded joint regression: Jrest = J_template + betas . J_shapedirs
+  float J0 = m.j_template[3 * j], J1 = m.j_template[3 * j + 1], J2 = m.j_template[3 * j + 2];
+  const float* bb = betas + b * NB;
+  for (int k = 0; k < NB; ++k) {
+    float bk = __ldg(bb + k);
+    const float* js = m.j_shapedirs + k * (3 * kJ) + 3 * j;
+    J0 = fmaf(bk, js[0], J0); J1 = fmaf(bk, js[1], J1); J2 = fmaf(bk, js[2], J2);
+  }
+
+  // ---- blendshape coefficients: betas | (R - I) of joints 1..23 | 1 | zeros
+  float* sc = s_coef[warp];
+  for (int k = lane; k < kCoefK; k += 32) sc[k] = 0.f;
+  __syncwarp();
+  if (lane < NB) sc[lane] = __ldg(bb + lane);
+  if (lane == 0) sc[NB + kP] = 1.0f;
+  if (active && j >= 1) {
+    float* pf = sc + NB + 9 * (j - 1);
+    pf[0] = __fsub_rn(R[0], 1.f); pf[1] = R[1]; pf[2] = R[2];
+    pf[3] = R[3]; pf[4] = __fsub_rn(R[4], 1.f); pf[5] = R[5];
+    pf[6] = R[6]; pf[7] = R[7]; pf[8] = __fsub_rn(R[8], 1.f);
+  }
+
+  // ---- kinematic chain
+  const int parent = active ? m.parents[j] : 0;
+  const int pj = parent < 0 ? 0 : parent;
+  const int depth = active ? m.depth[j] : -1;
+  float pJ0 = __shfl_sync(0xffffffffu, J0, pj), pJ1 = __shfl_sync(0xffffffffu, J1, pj),
+        pJ2 = __shfl_sync(0xffffffffu, J2, pj);
+  float tl0 = J0, tl1 = J1, tl2 = J2;
+  if (depth > 0) { tl0 = __fsub_rn(J0, pJ0); tl1 = __fsub_rn(J1, pJ1); tl2 = __fsub_rn(J2, pJ2); }
+  float G[12];  // [Rw | t] row-major 3x4
+  if (depth == 0 && rotate_base) {  // HMR: root * diag(1,-1,-1)
+    R[1] = -R[1]; R[2] = -R[2]; R[4] = -R[4]; R[5] = -R[5]; R[7] = -R[7]; R[8] = -R[8];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    G[4 * r + 0] = R[3 * r + 0]; G[4 * r + 1] = R[3 * r + 1]; G[4 * r + 2] = R[3 * r + 2];
+  }
+  G[3] = tl0; G[7] = tl1; G[11] = tl2;
+  for (int level = 1; level <= m.max_depth; ++level) {
+    float P[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) P[e] = __shfl_sync(0xffffffffu, G[e], pj);
+    if (depth == level) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float a0 = P[4 * r], a1 = P[4 * r + 1], a2 = P[4 * r + 2], a3 = P[4 * r + 3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          G[4 * r + c] = fmaf(a2, R[6 + c], fmaf(a1, R[3 + c], __fmul_rn(a0, R[c])));
+        G[4 * r + 3] = __fadd_rn(fmaf(a2, tl2, fmaf(a1, tl1, __fmul_rn(a0, tl0))), a3);
+      }
+    }
+  }
+
+  // ---- outputs
+  if (active && out.joints) {
+    float* jo = out.joints + (b * kJ + j) * 3;
+    jo[0] = G[3]; jo[1] = G[7]; jo[2] = G[11];
+  }
+  float* sa = s_A[warp];
+  if (active) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      float* a = sa + j * 12 + 4 * r;
+      a[0] = G[4 * r]; a[1] = G[4 * r + 1]; a[2] = G[4 * r + 2];
+      // rest-pose removal: t - Rw * Jrest
+      float rj = fmaf(G[4 * r + 2], J2, fmaf(G[4 * r + 1], J1, __fmul_rn(G[4 * r], J0)));
+      a[3] = __fsub_rn(G[4 * r + 3], rj);
+    }
+  }
+  __syncwarp();
+  if (out.coef) {
+    float* dst = out.coef + b * kCoefK;
+    for (int k = lane; k < kCoefK; k += 32) dst[k] = sc[k];
+  }
+  if (out.A) {
+    float4* dst = reinterpret_cast<float4*>(out.A + b * (kJ * 12));
+    const float4* src = reinterpret_cast<const float4*>(sa);
+    for (int k = lane; k < kJ * 3; k += 32) dst[k] = src[k];
+  }
+  // tensor-core operand images: row = body within its block, K-chunk-major (see k_blend_tc.cuh)
+  if (out.coef_bf16_hi) {
+    const long long blk = b / kCoefBlock; const int row = int(b % kCoefBlock);
+    uint16_t* hi = out.coef_bf16_hi + blk * (long long)(kCoefK * kCoefBlock);
+    uint16_t* lo = out.coef_bf16_lo ? out.coef_bf16_lo + blk * (long long)(kCoefK * kCoefBlock) : nullptr;
+    for (int k = lane; k < kCoefK; k += 32) {
+      const float v = sc[k];
+      const uint16_t h = f32_to_bf16_rn(v);
+      const size_t off = (size_t)(k >> 3) * (kCoefBlock * 8) + row * 8 + (k & 7);
+      hi[off] = h;
+      if (lo) lo[off] = f32_to_bf16_rn(__fsub_rn(v, bf16_to_f32(h)));
+    }
+  }
+  if (out.coef_tf32) {
+    const long long blk = b / kCoefBlock; const int row = int(b % kCoefBlock);
+    uint32_t* im = out.coef_tf32 + blk * (long long)(kCoefK * kCoefBlock);
+    for (int k = lane; k < kCoefK; k += 32)
+      im[(size_t)(k >> 2) * (kCoefBlock * 4) + row * 4 + (k & 3)] = f32_to_tf32_rn(sc[k]);
+  }
+  if (out.a_tf32) {
+    // B operand of the blend MMA: rows n = (body_in_block*12 + e), K = 48 = [A_hi | A_lo]
+    const long long blk = b / kLbsBlock; const int bi = int(b % kLbsBlock);
+    constexpr int rows = kLbsBlock * 12;
+    uint32_t* im = out.a_tf32 + blk * (long long)(kLbsK * rows);
+    for (int idx = lane; idx < kJ * 12; idx += 32) {
+      const int jj = idx / 12, e = idx % 12;
+      const float v = sa[idx];
+      const uint32_t hi = f32_to_tf32_rn(v);
+      const uint32_t lo = f32_to_tf32_rn(__fsub_rn(v, __uint_as_float(hi)));
+      const int row = bi * 12 + e;
+      auto at = [&](int k) { return (size_t)(k >> 2) * (rows * 4) + row * 4 + (k & 3); };
+      im[at(jj)] = hi; im[at(24 + jj)] = lo;
+    }
+  }
+}
+
+}  // namespace smplb200

@@ -1,0 +1,234 @@
+// k3 (+k4) tensor-core path: linear blend skinning with the 24-joint blend on tcgen05 / TMEM.
+//
+//   T[v, (b,e)] = sum_j W[v,j] * A[b,j,e]          e = 12 entries of the 3x4 joint transform
+//   verts[b,v,:] = T[v,(b,:)] (3x4) * [vposed[b,v,:]; 1]
+//
+// Why tensor cores for a "memory-bound" op: dense 24-joint fp32 blending is FMA-bound on the CUDA
+// cores (4.1 Mflop per body needs ~97 TFLOP/s at 60% of HBM), and even
+// the <=4-nnz form is bound by the shared-memory crossbar (48 gathered floats per vertex-body).
+// As an MMA the blend is M = 128 vertices (TMEM lanes), N = 12 * 16 bodies, K = 24 joints, and
+// costs ~0.42 clk per vertex-body per SM for ANY weight matrix -- no sparsity assumption.
+//
+// fp32 fidelity comes from the 3xTF32 split (both operands split exactly into tf32 hi + lo):
+//   W*A ~= W_hi*A_hi + W_hi*A_lo + W_lo*A_hi      (dropped lo*lo term ~2^-22 relative)
+// tf32 x tf32 products are exact in the fp32 accumulator, so the blend error is ~1e-7 relative,
+// the same order as an fp32 FMA chain.  Images: W' = [W_hi | W_lo] per 128-vertex tile (resident
+// in shared memory), A' = [A_hi | A_lo] per 16-body block (written by k2, streamed by bulk TMA).
+//
+// Epilogue thread = vertex: reads its 12 blended entries per body from TMEM, the planar vposed
+// coordinates (prefetched, coalesced), applies the 3x4 transform with FMAs, transposes through a
+// per-warp shared-memory row and emits coalesced stores.  k4 (weak-perspective projection,
+// SURVEY.md A.8) is computed by the CTAs of vertex tile 0 after their last block.
+#pragma once
+#include "common.cuh"
+#include "k_chain.cuh"
+#include "ptx.cuh"
+
+namespace smplb200 {
+
+constexpr int kLbsTcThreads = 320;                       // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kLbsTcStages = 3;
+constexpr int kLbsTcAcc = 2;
+constexpr int kLbsN = kLbsBlock * 12;                    // 192
+constexpr int kLbsTmemCols = 512;                        // 2 x 192 rounded to a power of two
+constexpr uint32_t kLbsWBytes = kLbsK * 128 * 4;         // 24,576
+constexpr uint32_t kLbsBStage = kLbsK * kLbsN * 4;       // 36,864
+constexpr uint32_t kLbsOutOff = kLbsWBytes + kLbsTcStages * kLbsBStage;
+constexpr uint32_t kLbsBarOff = kLbsOutOff + 8 * 96 * 4;
+constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;
+constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
+
+__global__ void __launch_bounds__(kLbsTcThreads, 1)
+k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
+         const float* __restrict__ vposed, long long n, int nblocks, int blocks_per_cta,
+         int V, int VP, float* __restrict__ verts, const float* __restrict__ joints_in,
+         const float* __restrict__ cam, float* __restrict__ kp2d) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sB = smem + kLbsWBytes;
+  float* sOut = reinterpret_cast<float*>(smem + kLbsOutOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLbsBarOff);
+  uint64_t* bar_w = bars;
+  uint64_t* bar_full = bars + 1;
+  uint64_t* bar_empty = bar_full + kLbsTcStages;
+  uint64_t* bar_tfull = bar_empty + kLbsTcStages;
+  uint64_t* bar_tempty = bar_tfull + kLbsTcAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + kLbsTcAcc);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int blk_begin = blockIdx.y * blocks_per_cta;
+  const int blk_end = min(nblocks, blk_begin + blocks_per_cta);
+  const int nblk = blk_end - blk_begin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::mbar_init(bar_w, 1);
+    for (int s = 0; s < kLbsTcStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 1); }
+    for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 8); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, kLbsTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nblk > 0) {
+      ptx::mbar_arrive_expect_tx(bar_w, kLbsWBytes);
+      ptx::bulk_g2s(sW, w_img + (size_t)tile * kLbsWBytes, kLbsWBytes, bar_w);
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % kLbsTcStages;
+        ptx::mbar_wait(bar_empty + s, ((i / kLbsTcStages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar_full + s, kLbsBStage);
+        ptx::bulk_g2s_split(sB + (size_t)s * kLbsBStage, a_img + (size_t)(blk_begin + i) * kLbsBStage,
+                            kLbsBStage, bar_full + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nblk > 0) {
+      ptx::mbar_wait(bar_w, 0);
+      const uint32_t w_addr = ptx::smem_u32(sW);
+      constexpr uint32_t kLboW = 128 * 16, kLboB = kLbsN * 16, kSbo = 128;
+      constexpr uint32_t kHalfW = 6 * kLboW, kHalfB = 6 * kLboB;  // byte offset of the "lo" K half
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % kLbsTcStages, a = i % kLbsTcAcc;
+        ptx::mbar_wait(bar_tempty + a, ((i / kLbsTcAcc) & 1) ^ 1);
+        ptx::mbar_wait(bar_full + s, (i / kLbsTcStages) & 1);
+        ptx::tc_fence_after();
+        const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * kLbsBStage);
+        const uint32_t d_tmem = tmem_base + a * kLbsN;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {  // (W_hi,A_hi), (W_hi,A_lo), (W_lo,A_hi)
+          const uint32_t wp = w_addr + (g == 2 ? kHalfW : 0);
+          const uint32_t bp = b_addr + (g == 1 ? kHalfB : 0);
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks) {  // 24 joints = 3 tf32 k-steps of 8
+            const uint64_t wd = ptx::make_smem_desc(wp + ks * 2 * kLboW, kLboW, kSbo);
+            const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * kLboB, kLboB, kSbo);
+            ptx::mma_tf32(d_tmem, wd, bd, kLbsIdesc, acc);
+            acc = 1;
+          }
+        }
+        ptx::tc_commit(bar_empty + s);
+        ptx::tc_commit(bar_tfull + a);
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int ew = warp - 2;              // 0..7
+    const int q = warp & 3;               // TMEM lane quarter
+    const int h = ew >> 2;                // which 8 of the block's 16 bodies
+    const int v_local = q * 32 + lane;
+    const int v = tile * 128 + v_local;
+    const int warp_v0 = tile * 128 + q * 32;
+    const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
+    float* so = sOut + ew * 96;
+    for (int i = 0; i < nblk; ++i) {
+      const int a = i % kLbsTcAcc;
+      const long long b0 = (long long)(blk_begin + i) * kLbsBlock + h * 8;
+      const int nb = (int)max(0LL, min(8LL, n - b0));
+      // prefetch this warp's vposed coordinates (planar, coalesced) before waiting on the MMA
+      float px[8], py[8], pz[8];
+#pragma unroll
+      for (int bi = 0; bi < 8; ++bi) {
+        if (bi < nb) {
+          const float* vp = vposed + (size_t)(b0 + bi) * 3 * VP + v;
+          px[bi] = __ldg(vp); py[bi] = __ldg(vp + VP); pz[bi] = __ldg(vp + 2 * VP);
+        } else {
+          px[bi] = py[bi] = pz[bi] = 0.f;
+        }
+      }
+      ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kLbsN + h * 96;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {   // 4 bodies = 48 TMEM columns per round
+        uint32_t r0[16], r1[16], r2[16];
+        ptx::tmem_ld16(t_addr + half * 48, r0);
+        ptx::tmem_ld16(t_addr + half * 48 + 16, r1);
+        ptx::tmem_ld16(t_addr + half * 48 + 32, r2);
+        ptx::tmem_ld_wait();
+        if (half == 1) {
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(bar_tempty + a);
+          __syncwarp();
+        }
+        float T[48];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          T[e] = __uint_as_float(r0[e]); T[16 + e] = __uint_as_float(r1[e]); T[32 + e] = __uint_as_float(r2[e]);
+        }
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int bi = half * 4 + bb;
+          const float* t = T + bb * 12;
+          const float x = px[bi], y = py[bi], z = pz[bi];
+          const float ox = fmaf(t[2], z, fmaf(t[1], y, fmaf(t[0], x, t[3])));
+          const float oy = fmaf(t[6], z, fmaf(t[5], y, fmaf(t[4], x, t[7])));
+          const float oz = fmaf(t[10], z, fmaf(t[9], y, fmaf(t[8], x, t[11])));
+          __syncwarp();
+          so[3 * lane] = ox; so[3 * lane + 1] = oy; so[3 * lane + 2] = oz;
+          __syncwarp();
+          if (bi < nb) {
+            float* dst = verts + ((size_t)(b0 + bi) * V + warp_v0) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              if (lane + 32 * k < nf) dst[lane + 32 * k] = so[lane + 32 * k];
+          }
+        }
+      }
+    }
+    // k4: weak-perspective projection for this CTA's bodies (vertex tile 0 only)
+    if (tile == 0 && kp2d != nullptr) {
+      const long long bb0 = (long long)blk_begin * kLbsBlock;
+      const long long bb1 = min(n, (long long)blk_end * kLbsBlock);
+      for (long long i = bb0 * (kJ * 2) + (threadIdx.x - 64); i < bb1 * (kJ * 2); i += 256) {
+        const long long b = i / (kJ * 2);
+        const int r = int(i - b * (kJ * 2)), j = r >> 1, c = r & 1;
+        const float s = __ldg(cam + b * 3), t = __ldg(cam + b * 3 + 1 + c);
+        kp2d[i] = __fmul_rn(s, __fadd_rn(__ldg(joints_in + (b * kJ + j) * 3 + c), t));
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kLbsTmemCols);
+}
+
+// fp32 A [n,24,12] -> tf32 hi|lo operand image (stand-alone k3 entry point only).
+__global__ void __launch_bounds__(256)
+k_pack_a(const float* __restrict__ A, long long n, uint32_t* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * (kJ * 12)) return;
+  const long long b = idx / (kJ * 12);
+  const int r = int(idx - b * (kJ * 12)), jj = r / 12, e = r % 12;
+  const float v = A[idx];
+  const uint32_t hi = f32_to_tf32_rn(v);
+  const uint32_t lo = f32_to_tf32_rn(__fsub_rn(v, __uint_as_float(hi)));
+  const long long blk = b / kLbsBlock;
+  const int row = int(b % kLbsBlock) * 12 + e;
+  uint32_t* im = img + blk * (long long)(kLbsK * kLbsN);
+  im[(size_t)(jj >> 2) * (kLbsN * 4) + row * 4 + (jj & 3)] = hi;
+  im[(size_t)((24 + jj) >> 2) * (kLbsN * 4) + row * 4 + ((24 + jj) & 3)] = lo;
+}
+
+inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float* vposed,
+                                 const uint32_t* a_img, long long n, float* verts,
+                                 const float* joints_in, const float* cam, float* kp2d,
+                                 cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const int vtiles = m.VP / 128;
+  const int nblocks = (int)((n + kLbsBlock - 1) / kLbsBlock);
+  int bpc = 8;
+  while (bpc < nblocks && (long long)vtiles * ((nblocks + bpc - 1) / bpc) > 8LL * num_sms) bpc *= 2;
+  if (bpc > nblocks) bpc = nblocks;
+  const dim3 grid((unsigned)vtiles, (unsigned)((nblocks + bpc - 1) / bpc));
+  k_lbs_tc<<<grid, kLbsTcThreads, kLbsSmemBytes, s>>>(
+      reinterpret_cast<const uint8_t*>(m.w_tf32), reinterpret_cast<const uint8_t*>(a_img), vposed, n,
+      nblocks, bpc, m.V, m.VP, verts, joints_in, cam, kp2d);
+  return cudaGetLastError();
+}
+
+}  // namespace smplb200

@@ -1,0 +1,682 @@
+// libsmpl_b200.so -- C ABI (include/smpl_b200.h) over the hand-written sm_100a SMPL kernels.
+//
+// Host side: model packing at create time, workspace carving, kernel selection and launch.
+// No per-call allocation, no host synchronisation, no mutable globals (only a thread_local
+// "last CUDA error" cell), no CPU compute fallback.
+#include "../../include/smpl_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "k_chain.cuh"
+#include "k_blend_fma.cuh"
+#include "k_lbs_fma.cuh"
+#include "k_blend_tc.cuh"
+#include "k_lbs_tc.cuh"
+
+using namespace smplb200;
+
+struct SmplB200Model {
+  DeviceModel d;
+  int device = 0;
+  int num_sms = 0;
+  void* blob = nullptr;
+  size_t blob_bytes = 0;
+};
+
+namespace {
+
+thread_local int tl_last_cuda_error = 0;
+
+inline int cuda_fail(cudaError_t e) {
+  tl_last_cuda_error = (int)e;
+  return SMPLB200_ERR_CUDA;
+}
+#define CU_TRY(expr)                                   \
+  do {                                                 \
+    cudaError_t _e = (expr);                           \
+    if (_e != cudaSuccess) return cuda_fail(_e);       \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// RAII device switch: the library always runs on the model's device and restores the caller's.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) {
+      err = cudaSetDevice(dev);
+      switched = (err == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// ---- host-side bf16 / tf32 rounding (round-to-nearest-even), used only at model create ----
+inline uint16_t host_bf16(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float host_bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline uint32_t host_tf32(float x) {  // keep 10 mantissa bits, low 13 bits zero
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u & 0xffffe000u;
+  u += 0xfffu + ((u >> 13) & 1u);
+  return u & 0xffffe000u;
+}
+inline float bits_to_f32(uint32_t u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+struct BlobBuilder {
+  std::vector<uint8_t> bytes;
+  size_t add(const void* src, size_t n) {
+    size_t off = align_up(bytes.size(), 256);
+    bytes.resize(off + n);
+    if (src) std::memcpy(bytes.data() + off, src, n);
+    return off;
+  }
+};
+
+// ---- workspace carving -----------------------------------------------------------------
+struct Workspace {
+  size_t coef = 0, A = 0, vposed = 0, joints = 0;
+  size_t coef_hi = 0, coef_lo = 0, coef_tf32 = 0, a_tf32 = 0;
+  size_t total = 0;
+};
+
+struct Plan {
+  uint32_t prec;      // resolved SMPLB200_PREC_*
+  uint32_t lbs;       // resolved SMPLB200_LBS_*
+  bool regressed;
+  bool rotate_base;
+};
+
+bool resolve_plan(const SmplB200Model* m, long long n, uint32_t flags, Plan* p) {
+  uint32_t prec = flags & SMPLB200_PREC_MASK;
+  if (prec > SMPLB200_PREC_BF16X3) return false;
+  if (prec == SMPLB200_PREC_AUTO)
+    prec = n >= SMPLB200_TC_MIN_BATCH ? SMPLB200_PREC_BF16X3 : SMPLB200_PREC_FP32;
+  uint32_t lbs = flags & SMPLB200_LBS_MASK;
+  if (lbs == SMPLB200_LBS_AUTO)
+    lbs = n >= SMPLB200_TC_MIN_BATCH ? SMPLB200_LBS_TC : SMPLB200_LBS_FMA;
+  if (lbs == SMPLB200_LBS_FMA && m->d.max_nnz > 4) lbs = SMPLB200_LBS_DENSE;
+  if (flags & ~(SMPLB200_PREC_MASK | SMPLB200_JOINTS_REGRESSED | SMPLB200_ROTATE_BASE |
+                SMPLB200_LBS_MASK))
+    return false;
+  p->prec = prec;
+  p->lbs = lbs;
+  p->regressed = (flags & SMPLB200_JOINTS_REGRESSED) != 0;
+  p->rotate_base = (flags & SMPLB200_ROTATE_BASE) != 0;
+  return true;
+}
+
+Workspace carve(const SmplB200Model* m, long long n, const Plan& p) {
+  Workspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t nn = (size_t)std::max<long long>(n, 1);
+  w.coef = take(nn * kCoefK * sizeof(float));
+  w.A = take(nn * kJ * 12 * sizeof(float));
+  w.vposed = take(nn * 3 * (size_t)m->d.VP * sizeof(float));
+  w.joints = take(nn * kJ * 3 * sizeof(float));
+  const size_t coef_blocks = (nn + kCoefBlock - 1) / kCoefBlock;
+  const size_t lbs_blocks = (nn + kLbsBlock - 1) / kLbsBlock;
+  if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
+    w.coef_hi = take(coef_blocks * kCoefBlock * kCoefK * 2);
+  if (p.prec == SMPLB200_PREC_BF16X3) w.coef_lo = take(coef_blocks * kCoefBlock * kCoefK * 2);
+  if (p.prec == SMPLB200_PREC_TF32) w.coef_tf32 = take(coef_blocks * kCoefBlock * kCoefK * 4);
+  if (p.lbs == SMPLB200_LBS_TC) w.a_tf32 = take(lbs_blocks * kLbsBlock * 12 * kLbsK * 4);
+  w.total = off;
+  return w;
+}
+
+// ---- launches ----------------------------------------------------------------------------
+int launch_chain(const SmplB200Model* m, const float* betas, const float* pose, long long n,
+                 const ChainOut& out, bool rotate_base, cudaStream_t s) {
+  if (n == 0) return SMPLB200_OK;
+  const unsigned grid = (unsigned)((n + kChainWarps - 1) / kChainWarps);
+  k_pose_chain<<<grid, kChainWarps * 32, 0, s>>>(m->d, betas, pose, n, out, rotate_base ? 1 : 0);
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+int launch_blend_fma(const SmplB200Model* m, const float* coef, long long n, float* vposed,
+                     cudaStream_t s) {
+  if (n == 0) return SMPLB200_OK;
+  const unsigned gx = (unsigned)((m->d.NC + kFmaColsPerCta - 1) / kFmaColsPerCta);
+  if (n <= 8) {
+    k_blend_fma<8><<<dim3(gx, (unsigned)((n + 7) / 8)), kFmaThreads, 0, s>>>(m->d, coef, n, vposed);
+  } else if (n <= 128) {
+    k_blend_fma<16><<<dim3(gx, (unsigned)((n + 15) / 16)), kFmaThreads, 0, s>>>(m->d, coef, n, vposed);
+  } else {
+    k_blend_fma<32><<<dim3(gx, (unsigned)((n + 31) / 32)), kFmaThreads, 0, s>>>(m->d, coef, n, vposed);
+  }
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+int launch_lbs_fma(const SmplB200Model* m, bool dense, const float* vposed, const float* A,
+                   long long n, float* verts, const float* joints_in, const float* cam,
+                   float* kp2d, cudaStream_t s) {
+  if (n == 0) return SMPLB200_OK;
+  const int bodies_per_cta = 16;
+  dim3 grid((unsigned)(m->d.VP / kVertTile), (unsigned)((n + bodies_per_cta - 1) / bodies_per_cta));
+  if (dense)
+    k_lbs_fma<true><<<grid, kLbsThreads, 0, s>>>(m->d, vposed, A, n, bodies_per_cta, verts,
+                                                 joints_in, cam, kp2d);
+  else
+    k_lbs_fma<false><<<grid, kLbsThreads, 0, s>>>(m->d, vposed, A, n, bodies_per_cta, verts,
+                                                  joints_in, cam, kp2d);
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+int launch_regress(const SmplB200Model* m, const float* verts, long long n, float* joints,
+                   const float* cam, float* kp2d, cudaStream_t s) {
+  if (n == 0) return SMPLB200_OK;
+  const long long warps = n * kJ;
+  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+  k_regress_joints<<<grid, 256, 0, s>>>(m->d, verts, n, joints, cam, kp2d);
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// opt-in dynamic shared memory for the tcgen05 kernels (per device, idempotent)
+cudaError_t configure_tc_kernels() {
+  cudaError_t e;
+  if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
+  if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
+  if ((e = blend_tc_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_lbs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)kLbsSmemBytes);
+}
+
+size_t coef_image_bytes(long long n, uint32_t prec) {
+  const size_t blocks = ((size_t)std::max<long long>(n, 1) + kCoefBlock - 1) / kCoefBlock;
+  const size_t one = blocks * kCoefBlock * kCoefK;
+  if (prec == SMPLB200_PREC_BF16) return align_up(one * 2, 256);
+  if (prec == SMPLB200_PREC_BF16X3) return 2 * align_up(one * 2, 256);
+  if (prec == SMPLB200_PREC_TF32) return align_up(one * 4, 256);
+  return 0;
+}
+size_t a_image_bytes(long long n) {
+  const size_t blocks = ((size_t)std::max<long long>(n, 1) + kLbsBlock - 1) / kLbsBlock;
+  return align_up(blocks * kLbsBlock * 12 * kLbsK * 4, 256);
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int smplb200_version(void) { return SMPLB200_VERSION; }
+int smplb200_last_cuda_error(void) { return tl_last_cuda_error; }
+
+const char* smplb200_strerror(int status) {
+  switch (status) {
+    case SMPLB200_OK: return "ok";
+    case SMPLB200_ERR_INVALID_ARG: return "invalid argument";
+    case SMPLB200_ERR_UNSUPPORTED: return "unsupported model shape or flag combination";
+    case SMPLB200_ERR_WORKSPACE: return "workspace missing, too small or misaligned";
+    case SMPLB200_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
+    case SMPLB200_ERR_CUDA: return "CUDA runtime or launch error (see smplb200_last_cuda_error)";
+    case SMPLB200_ERR_NO_DEVICE: return "no usable CUDA device (need compute capability 10.x)";
+    case SMPLB200_ERR_ALLOC: return "allocation failed";
+    default: return "unknown status";
+  }
+}
+
+int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_model) {
+  if (!desc || !out_model) return SMPLB200_ERR_INVALID_ARG;
+  *out_model = nullptr;
+  if (desc->struct_size != sizeof(SmplB200ModelDesc)) return SMPLB200_ERR_INVALID_ARG;
+  if (!desc->v_template || !desc->shapedirs || !desc->posedirs || !desc->j_regressor ||
+      !desc->weights || !desc->parents)
+    return SMPLB200_ERR_INVALID_ARG;
+  if (desc->num_joints != kJ) return SMPLB200_ERR_UNSUPPORTED;
+  if (desc->num_betas < 1 || desc->num_betas > kMaxBetas) return SMPLB200_ERR_UNSUPPORTED;
+  if (desc->num_verts < 1 || desc->num_verts > (1 << 24)) return SMPLB200_ERR_UNSUPPORTED;
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    return SMPLB200_ERR_NO_DEVICE;
+  }
+  if (desc->device < 0 || desc->device >= ndev) return SMPLB200_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10) return SMPLB200_ERR_NO_DEVICE;  // sm_100a cubin only
+
+  const int V = desc->num_verts, NB = desc->num_betas;
+  const int VP = (int)align_up((size_t)V, kVertTile), NC = 3 * VP, KB = NB + kP + 1;
+
+  // ---- kinematic tree
+  std::vector<int> parents(kJ), depth(kJ, 0);
+  int max_depth = 0;
+  for (int j = 0; j < kJ; ++j) {
+    int p = desc->parents[j];
+    if (j == 0) {
+      parents[j] = -1;  // root, whatever sentinel the file used (-1 or 0xFFFFFFFF)
+    } else {
+      if (p < 0 || p >= j) return SMPLB200_ERR_UNSUPPORTED;  // parents must precede children
+      parents[j] = p;
+      depth[j] = depth[p] + 1;
+      max_depth = std::max(max_depth, depth[j]);
+    }
+  }
+
+  BlobBuilder bb;
+  try {
+    // ---- planar fp32 basis [KB, NC]: shapedirs | posedirs | v_template
+    std::vector<float> basis((size_t)KB * NC, 0.f);
+    auto src_row = [&](int k) -> const float* {
+      if (k < NB) return desc->shapedirs + (size_t)k * 3 * V;
+      if (k < NB + kP) return desc->posedirs + (size_t)(k - NB) * 3 * V;
+      return desc->v_template;
+    };
+    for (int k = 0; k < KB; ++k) {
+      const float* s = src_row(k);
+      float* d = basis.data() + (size_t)k * NC;
+      for (int v = 0; v < V; ++v)
+        for (int c = 0; c < 3; ++c) d[c * VP + v] = s[3 * v + c];
+    }
+    // ---- folded joint regressor (fp64 accumulation on the host)
+    std::vector<float> jt(kJ * 3), jsd((size_t)NB * kJ * 3);
+    {
+      std::vector<double> acc((size_t)(NB + 1) * kJ * 3, 0.0);
+      for (int v = 0; v < V; ++v) {
+        const float* r = desc->j_regressor + (size_t)v * kJ;
+        for (int j = 0; j < kJ; ++j) {
+          const double rj = r[j];
+          if (rj == 0.0) continue;
+          for (int c = 0; c < 3; ++c) {
+            acc[(size_t)NB * kJ * 3 + j * 3 + c] += rj * desc->v_template[3 * v + c];
+            for (int k = 0; k < NB; ++k)
+              acc[(size_t)k * kJ * 3 + j * 3 + c] += rj * desc->shapedirs[(size_t)k * 3 * V + 3 * v + c];
+          }
+        }
+      }
+      for (int i = 0; i < kJ * 3; ++i) jt[i] = (float)acc[(size_t)NB * kJ * 3 + i];
+      for (size_t i = 0; i < jsd.size(); ++i) jsd[i] = (float)acc[i];
+    }
+    // ---- skinning weights: ELL (<=4) + dense, padded to VP rows
+    std::vector<float> dense_w((size_t)VP * kJ, 0.f);
+    std::vector<float> ell_w((size_t)VP * 4, 0.f);
+    std::vector<uint32_t> ell_j((size_t)VP, 0u);
+    int max_nnz = 0;
+    for (int v = 0; v < V; ++v) {
+      int cnt = 0;
+      uint32_t packed = 0;
+      for (int j = 0; j < kJ; ++j) {
+        const float wv = desc->weights[(size_t)v * kJ + j];
+        dense_w[(size_t)v * kJ + j] = wv;
+        if (wv != 0.f) {
+          if (cnt < 4) {
+            ell_w[(size_t)v * 4 + cnt] = wv;
+            packed |= (uint32_t)j << (8 * cnt);
+          }
+          ++cnt;
+        }
+      }
+      ell_j[v] = packed;
+      max_nnz = std::max(max_nnz, cnt);
+    }
+    // ---- joint regressor CSR over joints (for SMPLB200_JOINTS_REGRESSED)
+    std::vector<int> jptr(kJ + 1, 0), jidx;
+    std::vector<float> jval;
+    for (int j = 0; j < kJ; ++j) {
+      for (int v = 0; v < V; ++v) {
+        const float r = desc->j_regressor[(size_t)v * kJ + j];
+        if (r != 0.f) { jidx.push_back(v); jval.push_back(r); }
+      }
+      jptr[j + 1] = (int)jidx.size();
+    }
+    if (jidx.empty()) { jidx.push_back(0); jval.push_back(0.f); }
+
+    // ---- tensor-core operand images (canonical K-major, no swizzle; k_blend_tc.cuh)
+    // basis^T tiles: tile t = 128 planar columns; image[chunk][row][E]
+    const int ntile = NC / 128;
+    std::vector<uint16_t> bhi((size_t)ntile * kCoefK * 128, 0), blo((size_t)ntile * kCoefK * 128, 0);
+    std::vector<uint32_t> btf((size_t)ntile * kCoefK * 128, 0);
+    for (int t = 0; t < ntile; ++t)
+      for (int k = 0; k < kCoefK; ++k)
+        for (int r = 0; r < 128; ++r) {
+          const float x = k < KB ? basis[(size_t)k * NC + t * 128 + r] : 0.f;
+          const uint16_t h = host_bf16(x);
+          const size_t o16 = (size_t)t * kCoefK * 128 + (size_t)(k >> 3) * (128 * 8) + r * 8 + (k & 7);
+          bhi[o16] = h;
+          blo[o16] = host_bf16(x - host_bf16_to_f32(h));
+          const size_t o32 = (size_t)t * kCoefK * 128 + (size_t)(k >> 2) * (128 * 4) + r * 4 + (k & 3);
+          btf[o32] = host_tf32(x);
+        }
+    // skinning weights W' = [W_hi | W_lo] per 128-vertex tile, K = 48 tf32 (3xTF32 split blend)
+    const int vtile = VP / 128;
+    std::vector<uint32_t> wtf((size_t)vtile * kLbsK * 128, 0);
+    for (int t = 0; t < vtile; ++t)
+      for (int r = 0; r < 128; ++r)
+        for (int j = 0; j < kJ; ++j) {
+          const float x = dense_w[(size_t)(t * 128 + r) * kJ + j];
+          const uint32_t hi = host_tf32(x);
+          const uint32_t lo = host_tf32(x - bits_to_f32(hi));
+          auto at = [&](int k) { return (size_t)t * kLbsK * 128 + (size_t)(k >> 2) * (128 * 4) + r * 4 + (k & 3); };
+          wtf[at(j)] = hi; wtf[at(24 + j)] = lo;
+        }
+
+    SmplB200Model* m = new (std::nothrow) SmplB200Model();
+    if (!m) return SMPLB200_ERR_ALLOC;
+    const size_t o_basis = bb.add(basis.data(), basis.size() * 4);
+    const size_t o_jt = bb.add(jt.data(), jt.size() * 4);
+    const size_t o_jsd = bb.add(jsd.data(), jsd.size() * 4);
+    const size_t o_par = bb.add(parents.data(), kJ * 4);
+    const size_t o_dep = bb.add(depth.data(), kJ * 4);
+    const size_t o_ew = bb.add(ell_w.data(), ell_w.size() * 4);
+    const size_t o_ej = bb.add(ell_j.data(), ell_j.size() * 4);
+    const size_t o_dw = bb.add(dense_w.data(), dense_w.size() * 4);
+    const size_t o_jp = bb.add(jptr.data(), jptr.size() * 4);
+    const size_t o_ji = bb.add(jidx.data(), jidx.size() * 4);
+    const size_t o_jv = bb.add(jval.data(), jval.size() * 4);
+    const size_t o_bhi = bb.add(bhi.data(), bhi.size() * 2);
+    const size_t o_blo = bb.add(blo.data(), blo.size() * 2);
+    const size_t o_btf = bb.add(btf.data(), btf.size() * 4);
+    const size_t o_wtf = bb.add(wtf.data(), wtf.size() * 4);
+
+    DeviceGuard guard(desc->device);
+    if (guard.err != cudaSuccess) { delete m; return cuda_fail(guard.err); }
+    cudaError_t e = cudaMalloc(&m->blob, bb.bytes.size());
+    if (e != cudaSuccess) { delete m; tl_last_cuda_error = (int)e; cudaGetLastError(); return SMPLB200_ERR_ALLOC; }
+    e = cudaMemcpy(m->blob, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
+    // opt-in shared memory sizes for the tensor-core kernels
+    e = configure_tc_kernels();
+    if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
+
+    m->blob_bytes = bb.bytes.size();
+    m->device = desc->device;
+    m->num_sms = prop.multiProcessorCount;
+    uint8_t* base = static_cast<uint8_t*>(m->blob);
+    DeviceModel& d = m->d;
+    d.V = V; d.VP = VP; d.NB = NB; d.KB = KB; d.NC = NC;
+    d.max_nnz = max_nnz; d.max_depth = max_depth; d.jreg_nnz = (int)jval.size();
+    d.basis = reinterpret_cast<const float*>(base + o_basis);
+    d.j_template = reinterpret_cast<const float*>(base + o_jt);
+    d.j_shapedirs = reinterpret_cast<const float*>(base + o_jsd);
+    d.parents = reinterpret_cast<const int*>(base + o_par);
+    d.depth = reinterpret_cast<const int*>(base + o_dep);
+    d.ell_w = reinterpret_cast<const float4*>(base + o_ew);
+    d.ell_j = reinterpret_cast<const uint32_t*>(base + o_ej);
+    d.dense_w = reinterpret_cast<const float*>(base + o_dw);
+    d.jreg_ptr = reinterpret_cast<const int*>(base + o_jp);
+    d.jreg_idx = reinterpret_cast<const int*>(base + o_ji);
+    d.jreg_val = reinterpret_cast<const float*>(base + o_jv);
+    d.basis_bf16_hi = reinterpret_cast<const uint16_t*>(base + o_bhi);
+    d.basis_bf16_lo = reinterpret_cast<const uint16_t*>(base + o_blo);
+    d.basis_tf32 = reinterpret_cast<const uint32_t*>(base + o_btf);
+    d.w_tf32 = reinterpret_cast<const uint32_t*>(base + o_wtf);
+    *out_model = m;
+    return SMPLB200_OK;
+  } catch (const std::bad_alloc&) {
+    return SMPLB200_ERR_ALLOC;
+  }
+}
+
+void smplb200_model_destroy(SmplB200Model* model) {
+  if (!model) return;
+  {
+    DeviceGuard guard(model->device);
+    if (model->blob) cudaFree(model->blob);
+  }
+  delete model;
+}
+
+int32_t smplb200_model_num_verts(const SmplB200Model* m) { return m ? m->d.V : 0; }
+int32_t smplb200_model_num_joints(const SmplB200Model* m) { return m ? kJ : 0; }
+int32_t smplb200_model_num_betas(const SmplB200Model* m) { return m ? m->d.NB : 0; }
+int32_t smplb200_model_device(const SmplB200Model* m) { return m ? m->device : -1; }
+int32_t smplb200_model_max_weight_nnz(const SmplB200Model* m) { return m ? m->d.max_nnz : 0; }
+size_t smplb200_model_device_bytes(const SmplB200Model* m) { return m ? m->blob_bytes : 0; }
+int64_t smplb200_padded_verts(const SmplB200Model* m) { return m ? m->d.VP : 0; }
+
+size_t smplb200_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags) {
+  Plan p;
+  if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  return carve(model, n, p).total;
+}
+
+int smplb200_forward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags,
+                                  int with_projection) {
+  Plan p;
+  if (!model || n <= 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  (void)with_projection;
+  return 3 + (p.regressed ? 1 : 0);
+}
+
+int smplb200_pose_chain(const SmplB200Model* model, const float* betas, const float* pose,
+                        int64_t n, float* coef, float* A, float* joints, uint32_t flags,
+                        void* stream) {
+  if (!model || n < 0 || (n > 0 && (!betas || !pose))) return SMPLB200_ERR_INVALID_ARG;
+  if (A && !aligned16(A)) return SMPLB200_ERR_ALIGNMENT;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  ChainOut out{};
+  out.coef = coef; out.A = A; out.joints = joints;
+  return launch_chain(model, betas, pose, n, out, (flags & SMPLB200_ROTATE_BASE) != 0,
+                      static_cast<cudaStream_t>(stream));
+}
+
+size_t smplb200_blendshapes_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags) {
+  Plan p;
+  if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  return coef_image_bytes(n, p.prec);
+}
+
+int smplb200_blendshapes(const SmplB200Model* model, const float* coef, int64_t n, float* vposed,
+                         void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!model || n < 0 || (n > 0 && (!coef || !vposed))) return SMPLB200_ERR_INVALID_ARG;
+  if (!aligned16(vposed) || !aligned16(coef)) return SMPLB200_ERR_ALIGNMENT;
+  Plan p;
+  if (!resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
+  if (n == 0) return SMPLB200_OK;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p.prec == SMPLB200_PREC_FP32) return launch_blend_fma(model, coef, n, vposed, s);
+  // stand-alone tensor-core entry: operand images are built from the fp32 coefficients first
+  const size_t need = coef_image_bytes(n, p.prec);
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return SMPLB200_ERR_WORKSPACE;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint16_t* hi = nullptr; uint16_t* lo = nullptr; uint32_t* tf = nullptr;
+  if (p.prec == SMPLB200_PREC_TF32) tf = reinterpret_cast<uint32_t*>(ws);
+  else hi = reinterpret_cast<uint16_t*>(ws);
+  if (p.prec == SMPLB200_PREC_BF16X3) lo = reinterpret_cast<uint16_t*>(ws + need / 2);
+  const long long total = n * kCoefK;
+  k_pack_coef<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(coef, n, hi, lo, tf);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_blend_tc(model->d, model->num_sms, p.prec, hi, lo, tf, n, vposed, s));
+  return SMPLB200_OK;
+}
+
+size_t smplb200_lbs_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags) {
+  Plan p;
+  if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  return p.lbs == SMPLB200_LBS_TC ? a_image_bytes(n) : 0;
+}
+
+int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A, int64_t n,
+                 float* vertices, const float* joints_in, const float* cam, float* kp2d,
+                 void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!model || n < 0 || (n > 0 && (!vposed || !A || !vertices))) return SMPLB200_ERR_INVALID_ARG;
+  if ((kp2d != nullptr) && (!cam || !joints_in)) return SMPLB200_ERR_INVALID_ARG;
+  if (!aligned16(A) || !aligned16(vposed)) return SMPLB200_ERR_ALIGNMENT;
+  Plan p;
+  if (!resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
+  if (n == 0) return SMPLB200_OK;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p.lbs == SMPLB200_LBS_TC) {
+    const size_t need = a_image_bytes(n);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+      return SMPLB200_ERR_WORKSPACE;
+    uint32_t* img = static_cast<uint32_t*>(workspace);
+    const long long total = n * (kJ * 12);
+    k_pack_a<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, n, img);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, img, n, vertices, joints_in, cam, kp2d, s));
+    return SMPLB200_OK;
+  }
+  return launch_lbs_fma(model, p.lbs == SMPLB200_LBS_DENSE, vposed, A, n, vertices, joints_in, cam,
+                        kp2d, s);
+}
+
+int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, int64_t n,
+                            float* joints, const float* cam, float* kp2d, void* stream) {
+  if (!model || n < 0 || (n > 0 && (!vertices || !joints))) return SMPLB200_ERR_INVALID_ARG;
+  if (kp2d && !cam) return SMPLB200_ERR_INVALID_ARG;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  return launch_regress(model, vertices, n, joints, cam, kp2d, static_cast<cudaStream_t>(stream));
+}
+
+int smplb200_forward(const SmplB200Model* model, const float* betas, const float* pose,
+                     const float* cam, int64_t n, float* vertices, float* joints, float* kp2d,
+                     void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!model || n < 0) return SMPLB200_ERR_INVALID_ARG;
+  if (n == 0) return SMPLB200_OK;
+  if (!betas || !pose || !vertices) return SMPLB200_ERR_INVALID_ARG;
+  if ((kp2d != nullptr) != (cam != nullptr)) return SMPLB200_ERR_INVALID_ARG;
+  Plan p;
+  if (!resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
+  const Workspace w = carve(model, n, p);
+  if (!workspace || workspace_bytes < w.total || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return SMPLB200_ERR_WORKSPACE;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  float* coef = reinterpret_cast<float*>(ws + w.coef);
+  float* A = reinterpret_cast<float*>(ws + w.A);
+  float* vposed = reinterpret_cast<float*>(ws + w.vposed);
+  float* jbuf = joints ? joints : reinterpret_cast<float*>(ws + w.joints);
+
+  // k2
+  ChainOut out{};
+  out.A = A;
+  out.joints = p.regressed ? nullptr : jbuf;
+  if (p.prec == SMPLB200_PREC_FP32) out.coef = coef;
+  if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
+    out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.coef_hi);
+  if (p.prec == SMPLB200_PREC_BF16X3) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.coef_lo);
+  if (p.prec == SMPLB200_PREC_TF32) out.coef_tf32 = reinterpret_cast<uint32_t*>(ws + w.coef_tf32);
+  if (p.lbs == SMPLB200_LBS_TC) out.a_tf32 = reinterpret_cast<uint32_t*>(ws + w.a_tf32);
+  int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
+  if (st) return st;
+
+  // k1
+  if (p.prec == SMPLB200_PREC_FP32)
+    st = launch_blend_fma(model, coef, n, vposed, s);
+  else
+    CU_TRY(launch_blend_tc(model->d, model->num_sms, p.prec, out.coef_bf16_hi, out.coef_bf16_lo,
+                           out.coef_tf32, n, vposed, s));
+  if (st) return st;
+
+  // k3 (+k4 when joints are kinematic)
+  const bool proj_in_lbs = (kp2d != nullptr) && !p.regressed;
+  if (p.lbs == SMPLB200_LBS_TC)
+    CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, out.a_tf32, n, vertices,
+                         proj_in_lbs ? jbuf : nullptr, proj_in_lbs ? cam : nullptr,
+                         proj_in_lbs ? kp2d : nullptr, s));
+  else
+    st = launch_lbs_fma(model, p.lbs == SMPLB200_LBS_DENSE, vposed, A, n, vertices,
+                        proj_in_lbs ? jbuf : nullptr, proj_in_lbs ? cam : nullptr,
+                        proj_in_lbs ? kp2d : nullptr, s);
+  if (st) return st;
+
+  if (p.regressed && (joints || kp2d)) st = launch_regress(model, vertices, n, jbuf, cam, kp2d, s);
+  return st;
+}
+
+size_t smplb200_host_staging_bytes(const SmplB200Model* model, int64_t n, uint32_t flags) {
+  Plan p;
+  if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  const size_t nn = (size_t)std::max<int64_t>(n, 1);
+  size_t off = 0;
+  auto take = [&](size_t b) { off = align_up(off + b, 256); };
+  take(nn * model->d.NB * 4); take(nn * 3 * kJ * 4); take(nn * 3 * 4);
+  take(nn * (size_t)model->d.V * 3 * 4); take(nn * kJ * 3 * 4); take(nn * kJ * 2 * 4);
+  return off + carve(model, n, p).total;
+}
+
+int smplb200_forward_host(const SmplB200Model* model, const float* betas_host,
+                          const float* pose_host, const float* cam_host, int64_t n,
+                          float* vertices_host, float* joints_host, float* kp2d_host,
+                          void* staging, size_t staging_bytes, uint32_t flags, void* stream) {
+  if (!model || n < 0) return SMPLB200_ERR_INVALID_ARG;
+  if (n == 0) return SMPLB200_OK;
+  if (!betas_host || !pose_host) return SMPLB200_ERR_INVALID_ARG;
+  if (kp2d_host && !cam_host) return SMPLB200_ERR_INVALID_ARG;
+  const size_t need = smplb200_host_staging_bytes(model, n, flags);
+  if (need == 0) return SMPLB200_ERR_INVALID_ARG;
+  if (!staging || staging_bytes < need || (reinterpret_cast<uintptr_t>(staging) & 255u))
+    return SMPLB200_ERR_WORKSPACE;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t nn = (size_t)n;
+  uint8_t* base = static_cast<uint8_t*>(staging);
+  size_t off = 0;
+  auto take = [&](size_t b) { uint8_t* p = base + off; off = align_up(off + b, 256); return p; };
+  float* d_betas = reinterpret_cast<float*>(take(nn * model->d.NB * 4));
+  float* d_pose = reinterpret_cast<float*>(take(nn * 3 * kJ * 4));
+  float* d_cam = reinterpret_cast<float*>(take(nn * 3 * 4));
+  float* d_verts = reinterpret_cast<float*>(take(nn * (size_t)model->d.V * 3 * 4));
+  float* d_joints = reinterpret_cast<float*>(take(nn * kJ * 3 * 4));
+  float* d_kp = reinterpret_cast<float*>(take(nn * kJ * 2 * 4));
+  void* ws = base + off;
+  CU_TRY(cudaMemcpyAsync(d_betas, betas_host, nn * model->d.NB * 4, cudaMemcpyHostToDevice, s));
+  CU_TRY(cudaMemcpyAsync(d_pose, pose_host, nn * 3 * kJ * 4, cudaMemcpyHostToDevice, s));
+  if (cam_host) CU_TRY(cudaMemcpyAsync(d_cam, cam_host, nn * 3 * 4, cudaMemcpyHostToDevice, s));
+  const bool proj = cam_host != nullptr;
+  int st = smplb200_forward(model, d_betas, d_pose, proj ? d_cam : nullptr, n, d_verts, d_joints,
+                            proj ? d_kp : nullptr, ws, staging_bytes - off, flags, stream);
+  if (st) return st;
+  if (vertices_host)
+    CU_TRY(cudaMemcpyAsync(vertices_host, d_verts, nn * (size_t)model->d.V * 3 * 4, cudaMemcpyDeviceToHost, s));
+  if (joints_host)
+    CU_TRY(cudaMemcpyAsync(joints_host, d_joints, nn * kJ * 3 * 4, cudaMemcpyDeviceToHost, s));
+  if (kp2d_host && proj)
+    CU_TRY(cudaMemcpyAsync(kp2d_host, d_kp, nn * kJ * 2 * 4, cudaMemcpyDeviceToHost, s));
+  return SMPLB200_OK;
+}
+
+}  // extern "C"

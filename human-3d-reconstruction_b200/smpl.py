@@ -1,0 +1,244 @@
+"""Drop-in SMPL layer: ``forward(betas, pose, cam=None) -> (vertices, joints[, kp2d])``.
+
+The reference snapshot names an HMR trainer but ships no SMPL module; this class
+is the layer BASELINE.json's north_star asks for, shaped like the reference's one native-op
+module (nn.Module over an autograd-free native call, reference
+src/lib/models/DCNv2/dcn_v2.py:57-128) and fed the way its decode stage would feed it: per-person
+vectors gathered by ``_transpose_and_gather_feat`` (reference src/lib/models/utils.py:23-27) from
+heads ``{'pose': 72, 'shape': 10, 'cam': 3}`` (reference src/lib/opts.py:248-258).
+
+Model tensors are registered buffers so ``nn.DataParallel`` (reference
+src/lib/trains/trainer.py:176) replicates them; the packed device-side model (one
+``SmplB200Model*`` per device) is created lazily from the buffers on first use.
+
+Forward-only (SURVEY.md §8b "Autograd"): requesting gradients raises.  CUDA-only: a CPU tensor
+raises -- there is no CPU path in the product.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import capi, synthetic
+
+_BUFFERS = ("v_template", "shapedirs", "posedirs", "J_regressor", "weights")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _check_in(name, t, n, width, device):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if t.device != device:
+        raise RuntimeError(f"{name} is on {t.device}, expected {device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 2 or t.shape[0] != n or t.shape[1] != width:
+        raise ValueError(f"{name} must have shape [{n}, {width}], got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+class SMPL(nn.Module):
+    """SMPL body model on B200.
+
+    Args:
+      model: dict (or path to an .npz) with ``v_template[V,3]``, ``shapedirs[NB,3V]``,
+             ``posedirs[207,3V]``, ``J_regressor[V,24]``, ``weights[V,24]``, ``parents[24]``
+             in the eager layer's layouts.
+      precision: 'auto' | 'fp32' | 'bf16' | 'tf32' | 'bf16x3'  (blendshape operands)
+      joints: 'kinematic' (J_posed of the chain, default) | 'regressed' (HMR-style, from vertices)
+      rotate_base: HMR's root pre-rotation by diag(1,-1,-1); default False
+      lbs: 'auto' | 'fma' | 'tc' | 'dense'  (skinning kernel)
+    """
+
+    def __init__(self, model, precision="auto", joints="kinematic", rotate_base=False, lbs="auto"):
+        super().__init__()
+        if isinstance(model, (str, bytes)):
+            with np.load(model) as z:
+                model = {k: z[k] for k in z.files}
+        for k in _BUFFERS:
+            self.register_buffer(k, torch.as_tensor(np.asarray(model[k], dtype=np.float32)).clone())
+        self.register_buffer(
+            "parents", torch.as_tensor(np.asarray(model["parents"]).astype(np.int64)).clone())
+        self.num_verts = int(self.v_template.shape[0])
+        self.num_joints = int(self.weights.shape[1])
+        self.num_betas = int(self.shapedirs.shape[0])
+        self.flags = capi.make_flags(precision, joints, rotate_base, lbs)
+        self.precision, self.joints_from, self.rotate_base, self.lbs = precision, joints, rotate_base, lbs
+        # shared by DataParallel replicas (replicate() shallow-copies __dict__): device index -> handle
+        self._handles = {}
+        self._handles_lock = threading.Lock()
+
+    # -- construction helpers ------------------------------------------------------------------
+    @classmethod
+    def synthetic(cls, seed: int = 0, weights: str = "sparse", regressor: str = "sparse", **kw):
+        """Seeded SMPL-shaped random model (the licensed model file is not available offline)."""
+        return cls(synthetic.make_model(seed, weights=weights, regressor=regressor), **kw)
+
+    def model_dict(self) -> dict:
+        d = {k: getattr(self, k).detach().cpu().numpy() for k in _BUFFERS}
+        d["parents"] = self.parents.detach().cpu().numpy().astype(np.int32)
+        return d
+
+    def handle(self, device) -> capi.ModelHandle:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("SMPL (B200) runs on CUDA devices only; there is no CPU fallback")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            with self._handles_lock:
+                h = self._handles.get(idx)
+                if h is None:
+                    h = capi.ModelHandle(self.model_dict(), idx)
+                    self._handles[idx] = h
+        return h
+
+    # -- the forward pass ------------------------------------------------------------------------
+    def forward(self, betas, pose, cam=None, *, flags=None):
+        """betas[N,NB], pose[N,72] (axis-angle), cam[N,3]=(s,tx,ty) or None.
+
+        Returns (vertices[N,V,3], joints[N,24,3]) and, when ``cam`` is given, kp2d[N,24,2].
+        """
+        if not isinstance(betas, torch.Tensor) or betas.device.type != "cuda":
+            raise RuntimeError("SMPL (B200) needs CUDA tensors; there is no CPU fallback")
+        if torch.is_grad_enabled() and any(
+                isinstance(t, torch.Tensor) and t.requires_grad for t in (betas, pose, cam)):
+            raise RuntimeError("SMPL (B200) is forward-only: wrap the call in torch.no_grad() "
+                               "or detach the inputs (backward is out of scope, SURVEY.md §8f)")
+        device = betas.device
+        n = int(betas.shape[0])
+        betas = _check_in("betas", betas, n, self.num_betas, device)
+        pose = _check_in("pose", pose, n, 3 * self.num_joints, device)
+        if cam is not None:
+            cam = _check_in("cam", cam, n, 3, device)
+        flags = self.flags if flags is None else int(flags)
+        h = self.handle(device)
+        with torch.cuda.device(device):
+            verts = torch.empty((n, self.num_verts, 3), dtype=torch.float32, device=device)
+            joints = torch.empty((n, self.num_joints, 3), dtype=torch.float32, device=device)
+            kp2d = None if cam is None else torch.empty((n, self.num_joints, 2), dtype=torch.float32, device=device)
+            if n > 0:
+                ws_bytes = h.workspace_bytes(n, flags)
+                if ws_bytes == 0:
+                    raise RuntimeError("smplb200_workspace_bytes rejected the flag combination")
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+                capi.check(capi.lib().smplb200_forward(
+                    h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(verts), _ptr(joints), _ptr(kp2d),
+                    _ptr(ws), ws_bytes, flags, _stream_ptr(device)), "smplb200_forward")
+        return (verts, joints) if cam is None else (verts, joints, kp2d)
+
+    def launch_count(self, n: int, with_projection: bool, device=None) -> int:
+        h = self.handle(device if device is not None else self.v_template.device)
+        return h.launch_count(n, self.flags, with_projection)
+
+
+class HostRunner:
+    """End-to-end runner over HOST buffers through ``smplb200_forward_host``.
+
+    Owns pinned host input/output buffers and one device staging arena sized for ``n`` bodies;
+    each ``run()`` copies the inputs host->device, runs the forward and copies the requested
+    outputs device->host on the given stream (no synchronisation inside).
+    """
+
+    def __init__(self, smpl: SMPL, n: int, device, with_vertices: bool = False, with_cam: bool = True):
+        self.smpl, self.n = smpl, int(n)
+        self.device = torch.device(device)
+        self.h = smpl.handle(self.device)
+        pin = dict(dtype=torch.float32, pin_memory=True)
+        self.betas = torch.empty((n, smpl.num_betas), **pin)
+        self.pose = torch.empty((n, 3 * smpl.num_joints), **pin)
+        self.cam = torch.empty((n, 3), **pin) if with_cam else None
+        self.vertices = torch.empty((n, smpl.num_verts, 3), **pin) if with_vertices else None
+        self.joints = torch.empty((n, smpl.num_joints, 3), **pin)
+        self.kp2d = torch.empty((n, smpl.num_joints, 2), **pin) if with_cam else None
+        self.staging_bytes = self.h.host_staging_bytes(n, smpl.flags)
+        with torch.cuda.device(self.device):
+            self.staging = torch.empty(self.staging_bytes, dtype=torch.uint8, device=self.device)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * 4 for t in (self.betas, self.pose, self.cam) if t is not None)
+
+    @property
+    def d2h_bytes(self) -> int:
+        return sum(t.numel() * 4 for t in (self.vertices, self.joints, self.kp2d) if t is not None)
+
+    def run(self, stream=None):
+        s = _stream_ptr(self.device) if stream is None else stream.cuda_stream
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib().smplb200_forward_host(
+                self.h.ptr, _ptr(self.betas), _ptr(self.pose), _ptr(self.cam), self.n,
+                _ptr(self.vertices), _ptr(self.joints), _ptr(self.kp2d),
+                _ptr(self.staging), self.staging_bytes, self.smpl.flags, s), "smplb200_forward_host")
+
+
+# ---- per-kernel entry points (unit parity, ncu) --------------------------------------------------
+def pose_chain(smpl: SMPL, betas, pose, flags=None):
+    """k2 -> (coef[N,224], A[N,24,12], joints[N,24,3])."""
+    device, n = betas.device, int(betas.shape[0])
+    h = smpl.handle(device)
+    flags = smpl.flags if flags is None else flags
+    with torch.cuda.device(device):
+        coef = torch.empty((n, capi.COEF_K), dtype=torch.float32, device=device)
+        A = torch.empty((n, smpl.num_joints, 12), dtype=torch.float32, device=device)
+        joints = torch.empty((n, smpl.num_joints, 3), dtype=torch.float32, device=device)
+        capi.check(capi.lib().smplb200_pose_chain(
+            h.ptr, _ptr(betas.contiguous()), _ptr(pose.contiguous()), n, _ptr(coef), _ptr(A), _ptr(joints),
+            flags, _stream_ptr(device)), "smplb200_pose_chain")
+    return coef, A, joints
+
+
+def blendshapes(smpl: SMPL, coef, flags=None):
+    """k1 -> vposed planar [N,3,VP]."""
+    device, n = coef.device, int(coef.shape[0])
+    h = smpl.handle(device)
+    flags = smpl.flags if flags is None else flags
+    with torch.cuda.device(device):
+        vposed = torch.empty((n, 3, h.padded_verts), dtype=torch.float32, device=device)
+        wsb = int(capi.lib().smplb200_blendshapes_workspace_bytes(h.ptr, n, flags))
+        ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=device)
+        capi.check(capi.lib().smplb200_blendshapes(
+            h.ptr, _ptr(coef.contiguous()), n, _ptr(vposed), _ptr(ws), wsb, flags,
+            _stream_ptr(device)), "smplb200_blendshapes")
+    return vposed
+
+
+def lbs(smpl: SMPL, vposed, A, joints=None, cam=None, flags=None):
+    """k3 (+k4) -> vertices[N,V,3] (and kp2d when joints and cam are given)."""
+    device, n = vposed.device, int(vposed.shape[0])
+    h = smpl.handle(device)
+    flags = smpl.flags if flags is None else flags
+    with torch.cuda.device(device):
+        verts = torch.empty((n, smpl.num_verts, 3), dtype=torch.float32, device=device)
+        kp2d = None
+        if cam is not None and joints is not None:
+            kp2d = torch.empty((n, smpl.num_joints, 2), dtype=torch.float32, device=device)
+        wsb = int(capi.lib().smplb200_lbs_workspace_bytes(h.ptr, n, flags))
+        ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=device)
+        capi.check(capi.lib().smplb200_lbs(
+            h.ptr, _ptr(vposed.contiguous()), _ptr(A.contiguous()), n, _ptr(verts),
+            _ptr(joints), _ptr(cam), _ptr(kp2d), _ptr(ws), wsb, flags, _stream_ptr(device)),
+            "smplb200_lbs")
+    return verts if kp2d is None else (verts, kp2d)
+
+
+def regress_joints(smpl: SMPL, vertices, cam=None):
+    device, n = vertices.device, int(vertices.shape[0])
+    h = smpl.handle(device)
+    with torch.cuda.device(device):
+        joints = torch.empty((n, smpl.num_joints, 3), dtype=torch.float32, device=device)
+        kp2d = None if cam is None else torch.empty((n, smpl.num_joints, 2), dtype=torch.float32, device=device)
+        capi.check(capi.lib().smplb200_regress_joints(
+            h.ptr, _ptr(vertices.contiguous()), n, _ptr(joints), _ptr(cam), _ptr(kp2d),
+            _stream_ptr(device)), "smplb200_regress_joints")
+    return joints if kp2d is None else (joints, kp2d)

@@ -1,0 +1,177 @@
+/*
+ * smpl_b200.h -- C ABI of the B200-native SMPL body-model forward pass (libsmpl_b200.so).
+ *
+ * Drop-in boundary for the PyTorch SMPL layer that BASELINE.json's north_star names
+ * (`forward(betas, pose, ...) -> (vertices, joints)`).  The mounted reference snapshot has no
+ * SMPL layer, so the boundary follows the one native-op convention the reference
+ * does have -- the DCNv2 extension:
+ *   - `extern "C"` launchers taking raw `const float*` + sizes + `cudaStream_t`
+ *       reference src/lib/models/DCNv2/src/cuda/dcn_v2_im2col_cuda.h:67-99
+ *   - a thin tensor shim over them        reference src/lib/models/DCNv2/src/dcn_v2.h:9-39,
+ *                                                   src/lib/models/DCNv2/src/vision.cpp:4-9
+ *   - an nn.Module on top                 reference src/lib/models/DCNv2/dcn_v2.py:57-128
+ * and deliberately departs from it where SURVEY.md §8(b) says so: the callee never allocates per
+ * call (caller owns outputs and workspace), never prints, never throws, keeps no mutable globals
+ * (contrast reference src/lib/models/DCNv2/src/cuda/dcn_v2_cuda.cu:12) and reports errors as an
+ * `int` status.
+ *
+ * Conventions
+ *   - all tensors are fp32, C-contiguous; "device" pointers live on the model's CUDA device;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host sync;
+ *   - thread-safe and re-entrant: one model handle per device, calls may come from any thread.
+ *   - N = bodies, V = vertices (6890), J = joints (24), NB = betas (<=16), P = 9*(J-1) = 207.
+ *
+ * There is NO CPU fallback: every entry point below launches hand-written sm_100a kernels.
+ */
+#ifndef SMPL_B200_H
+#define SMPL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMPLB200_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ---------------------------------------------------------------------- */
+enum {
+  SMPLB200_OK = 0,
+  SMPLB200_ERR_INVALID_ARG = 1,   /* null pointer, bad size, unknown flag               */
+  SMPLB200_ERR_UNSUPPORTED = 2,   /* model shape outside what the kernels are built for  */
+  SMPLB200_ERR_WORKSPACE = 3,     /* workspace null/too small/misaligned                 */
+  SMPLB200_ERR_ALIGNMENT = 4,     /* an output pointer is not 16-byte aligned            */
+  SMPLB200_ERR_CUDA = 5,          /* a CUDA runtime call or kernel launch failed         */
+  SMPLB200_ERR_NO_DEVICE = 6,     /* no sm_100 device / device index out of range        */
+  SMPLB200_ERR_ALLOC = 7          /* host or device allocation failed at model create    */
+};
+
+/* ---- forward flags --------------------------------------------------------------------- */
+/* blendshape operand precision (accumulate and output are always fp32)                      */
+#define SMPLB200_PREC_AUTO   0u  /* FP32 FMA below SMPLB200_TC_MIN_BATCH bodies, BF16X3 above */
+#define SMPLB200_PREC_FP32   1u  /* vectorised FMA kernel, k-ascending single accumulator     */
+#define SMPLB200_PREC_BF16   2u  /* tcgen05 kind::f16, bf16 operands                          */
+#define SMPLB200_PREC_TF32   3u  /* tcgen05 kind::tf32                                        */
+#define SMPLB200_PREC_BF16X3 4u  /* tcgen05, 3-term split bf16 (hi*hi + hi*lo + lo*hi)        */
+#define SMPLB200_PREC_MASK   0x7u
+/* joint output: kinematic J_posed (default) or HMR-style regression from skinned vertices   */
+#define SMPLB200_JOINTS_KINEMATIC 0u
+#define SMPLB200_JOINTS_REGRESSED (1u << 3)
+/* HMR's root pre-rotation by diag(1,-1,-1); default off                      */
+#define SMPLB200_ROTATE_BASE      (1u << 4)
+/* skinning path                                                                              */
+#define SMPLB200_LBS_AUTO   0u          /* tcgen05 blend at large N, FMA below               */
+#define SMPLB200_LBS_FMA    (1u << 5)   /* CUDA-core kernel (ELL-sparse weights if <=4 nnz)  */
+#define SMPLB200_LBS_TC     (2u << 5)   /* 3xTF32 tcgen05 blend of the 24 joint transforms   */
+#define SMPLB200_LBS_DENSE  (3u << 5)   /* CUDA-core kernel, all 24 weights (debug/fallback) */
+#define SMPLB200_LBS_MASK   (3u << 5)
+
+#define SMPLB200_TC_MIN_BATCH 256
+
+/* ---- model ----------------------------------------------------------------------------- */
+typedef struct SmplB200Model SmplB200Model;
+
+/* Host-side description of the model tensors in the layout the eager layer keeps them
+ * (SURVEY.md App. A.1).  All pointers are HOST pointers; they are read during create only.   */
+typedef struct SmplB200ModelDesc {
+  uint32_t struct_size;      /* = sizeof(SmplB200ModelDesc)                                  */
+  int32_t device;            /* CUDA device ordinal the handle lives on                      */
+  int32_t num_verts;         /* V  (>= 1)                                                    */
+  int32_t num_joints;        /* J  (must be 24)                                              */
+  int32_t num_betas;         /* NB (1..16)                                                   */
+  const float* v_template;   /* [V,3]                                                        */
+  const float* shapedirs;    /* [NB, 3V]   column = 3*v + c                                  */
+  const float* posedirs;     /* [9*(J-1), 3V]                                                */
+  const float* j_regressor;  /* [V, J]     (the model's [J,V] transposed, HMR idiom)         */
+  const float* weights;      /* [V, J]     skinning weights                                  */
+  const int32_t* parents;    /* [J]        kintree_table[0]; root = -1 (or 0xFFFFFFFF)       */
+} SmplB200ModelDesc;
+
+/* Packs the model for the device (folded joint regressor, planar K-padded blendshape basis,
+ * pre-tiled bf16/tf32 tensor-core operand images, ELL skinning weights) and uploads it.
+ * Synchronous; the only entry point that allocates device memory.                            */
+int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_model);
+void smplb200_model_destroy(SmplB200Model* model);
+
+/* Introspection (pure host, no CUDA calls).                                                  */
+int32_t smplb200_model_num_verts(const SmplB200Model* model);
+int32_t smplb200_model_num_joints(const SmplB200Model* model);
+int32_t smplb200_model_num_betas(const SmplB200Model* model);
+int32_t smplb200_model_device(const SmplB200Model* model);
+int32_t smplb200_model_max_weight_nnz(const SmplB200Model* model); /* max non-zeros per vertex */
+size_t smplb200_model_device_bytes(const SmplB200Model* model);
+
+/* ---- the forward pass ------------------------------------------------------------------ */
+/* Bytes of device scratch `smplb200_forward` needs for `n` bodies with `flags`.              */
+size_t smplb200_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags);
+
+/* vertices[N,V,3], joints[N,J,3], kp2d[N,J,2] <- betas[N,NB], pose[N,3J], cam[N,3].
+ * DEVICE pointers.  `cam`/`kp2d` may both be NULL (no projection); `joints` may be NULL.
+ * `workspace` must be 256-byte aligned and >= smplb200_workspace_bytes(...).
+ * Replaces: the forward() of the eager SMPL nn.Module.            */
+int smplb200_forward(const SmplB200Model* model,
+                     const float* betas, const float* pose, const float* cam, int64_t n,
+                     float* vertices, float* joints, float* kp2d,
+                     void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* Same pass with HOST buffers (pinned recommended): copies betas/pose/cam host->device,
+ * runs the forward, copies the requested outputs device->host, all ordered on `stream`.
+ * `vertices_host`/`joints_host`/`kp2d_host` may each be NULL to skip that copy.
+ * `staging` is device scratch of >= smplb200_host_staging_bytes(model, n, flags) bytes
+ * (inputs + outputs + workspace).  Returns without synchronising.                            */
+size_t smplb200_host_staging_bytes(const SmplB200Model* model, int64_t n, uint32_t flags);
+int smplb200_forward_host(const SmplB200Model* model,
+                          const float* betas_host, const float* pose_host, const float* cam_host,
+                          int64_t n, float* vertices_host, float* joints_host, float* kp2d_host,
+                          void* staging, size_t staging_bytes, uint32_t flags, void* stream);
+
+/* ---- per-kernel entry points (unit parity + ncu) ---------------------------------------- */
+/* Internal intermediate layouts (owned by this library, stable within a version):
+ *   coef   [N, 224] fp32   k<NB: betas; NB..NB+206: pose_feature (R[1:]-I); NB+207: 1.0; rest 0
+ *   A      [N, J, 12] fp32 rows 0..2 of the rest-pose-removed joint transforms, row-major 3x4
+ *   vposed [N, 3, VP] fp32 planar (x-plane, y-plane, z-plane), VP = V rounded up to 128
+ */
+int64_t smplb200_padded_verts(const SmplB200Model* model);          /* VP                    */
+#define SMPLB200_COEF_K 224
+
+/* k2: folded joint regression + Rodrigues + kinematic chain (one warp per body).
+ * Writes coef, A, and optionally joints (kinematic J_posed).  Any output may be NULL.       */
+int smplb200_pose_chain(const SmplB200Model* model, const float* betas, const float* pose,
+                        int64_t n, float* coef, float* A, float* joints,
+                        uint32_t flags, void* stream);
+
+/* k1: shape + pose blendshapes, coef[N,224] x basis -> vposed (planar).  `flags` selects the
+ * FMA or a tcgen05 path via SMPLB200_PREC_*.  The tcgen05 paths need device scratch for the
+ * bf16/tf32 operand images (`smplb200_blendshapes_workspace_bytes`, 256-byte aligned); the FMA
+ * path needs none (workspace may be NULL).                                                   */
+size_t smplb200_blendshapes_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags);
+int smplb200_blendshapes(const SmplB200Model* model, const float* coef, int64_t n,
+                         float* vposed, void* workspace, size_t workspace_bytes,
+                         uint32_t flags, void* stream);
+
+/* k3 (+k4): linear blend skinning with the weak-perspective projection in its epilogue.
+ * `joints_in`/`cam`/`kp2d` may be NULL together (no projection).  SMPLB200_LBS_TC needs
+ * `smplb200_lbs_workspace_bytes` of scratch for the tf32 hi|lo image of A.                   */
+size_t smplb200_lbs_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags);
+int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A, int64_t n,
+                 float* vertices, const float* joints_in, const float* cam, float* kp2d,
+                 void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* joints regressed from skinned vertices (SMPLB200_JOINTS_REGRESSED) + optional projection. */
+int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, int64_t n,
+                            float* joints, const float* cam, float* kp2d, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------- */
+const char* smplb200_strerror(int status);
+int smplb200_version(void);
+/* Last CUDA error code seen by this thread inside the library (cudaError_t), 0 if none.      */
+int smplb200_last_cuda_error(void);
+/* Number of kernel launches the given forward configuration issues (for bench accounting).  */
+int smplb200_forward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags,
+                                  int with_projection);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMPL_B200_H */
