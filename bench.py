@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""SMPL forward benchmark (BASELINE.json metric: SMPL forward bodies/sec; LBS % HBM, GEMM % TC).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one SMPL forward (k2 chain -> k1 blendshapes -> k3 LBS + k4 projection) over one
+batch of synthetic per-person parameters; the workload is BASELINE.json configs[2]
+("batch 4096 ... tcgen05 GEMM regime ... fp32 LBS") per GPU.  With N > 1 (torchrun, one process
+per GPU) every rank runs its own 4096-body shard (weak scaling, no data-path collective) and the
+step ends with the optional NCCL all-gather of joints + kp2d (480 B/body, configs[3]).
+
+Printed JSON (rank 0, one line):
+  value      bodies/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the C-ABI host entry (smplb200_forward_host): pinned host inputs
+             H2D + forward + D2H of joints and kp2d every step (vertices stay on the device, as
+             they do for the reference's GPU module; a variant that also copies the vertices to
+             the host is reported as e2e_vertices_d2h)
+  roofline   dominant kernel (k3 LBS) against the measured HBM peak; roofline_kernels lists all
+  cpu_baseline  the CPU oracle (oracle/smpl_ref.py, fp32 eager PyTorch) timed on the host cores
+
+`--impl reference` times the reference arm.  The reference snapshot contains no SMPL layer and
+no compilable source for this path, so the arm runs the oracle restatement of the
+eager PyTorch layer on the host cores ("kind": "port"), on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BODIES_PER_GPU = 4096
+BYTES_E2E = 83_500          # per body: 340 in + 83,160 out
+BYTES_K1 = 83_020           # write vposed 82,680 + read coefficients 340
+BYTES_K2 = 2_100
+BYTES_K3 = 166_992          # read vposed 82,680 + A 1,152; write verts 82,680 + joints/kp2d 480
+FLOPS_K1 = 8_970_780        # 2 * 217 * 20670 (algorithmic; the MMA executes K = 224)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled in the background with host timestamps."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int, period_ms: int = 20):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", str(period_ms), "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append((time.time(), parts))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        inside = [p for (t, p) in self.samples if t0 <= t <= t1]
+        note = "sampled inside the timed region"
+        if len(inside) < 3:
+            inside = [p for (_, p) in self.samples]
+            note = "timed region shorter than 3 sampling periods: samples span warm-up + timed + kernel loops"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        mhz, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for p in inside:
+            try:
+                mhz.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, p[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(mhz) if mhz else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(inside), "note": note}
+
+
+def cpu_oracle_throughput(model, bodies: int, warm: int, timed: int, seed: int = 1):
+    """bodies/s of the CPU oracle (fp32, all host threads) on `bodies` bodies per call."""
+    import torch
+    from human_3d_reconstruction_b200 import synthetic
+    from oracle.smpl_ref import smpl_forward
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    torch.set_num_threads(cores)
+    betas, pose, cam = synthetic.make_inputs(bodies, seed)
+    tm = {k: torch.as_tensor(v) for k, v in model.items()}
+    times = []
+    with torch.no_grad():
+        for i in range(warm + timed):
+            t0 = time.perf_counter()
+            smpl_forward(tm, betas, pose, cam, dtype=torch.float32)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+    med = statistics.median(times)
+    return bodies / med, cores, times
+
+
+def run_reference(args):
+    """Reference arm: the oracle port of the eager PyTorch SMPL layer on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from human_3d_reconstruction_b200 import synthetic
+    model = synthetic.make_model(0)
+    # calibrate so that warmup + steps stay within ~2.5 minutes
+    bps, cores, _ = cpu_oracle_throughput(model, 32, 1, 2)
+    budget_s = 150.0
+    bodies = int(max(1, min(BODIES_PER_GPU, bps * budget_s / max(1, args.steps + args.warmup))))
+    bodies = min(bodies, 512)  # bound the eager T[N,V,4,4] intermediate (441 KB/body)
+    t0 = time.perf_counter()
+    bps, cores, times = cpu_oracle_throughput(model, bodies, args.warmup, args.steps)
+    total = sum(times)
+    value = bodies * len(times) / total
+    line = {
+        "impl": "reference", "metric": "smpl_forward_bodies_per_sec", "value": value, "unit": "bodies/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SMPL forward batch {BODIES_PER_GPU} (+2D keypoint projection), synthetic "
+                               "SMPL-shaped model seed 0 (6890 verts, 24 joints, 10 betas, 207 posedirs)",
+                   "note": "reference snapshot has no SMPL layer (SURVEY.md F1): arm = CPU oracle port of "
+                           "the eager PyTorch layer; each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": "bodies/s", "cores": cores, "kind": "port",
+                         "sample": f"{bodies} bodies per step, {len(times)} timed steps, torch "
+                                   f"{torch.__version__} fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def time_loop(fn, iters: int, torch):
+    """CUDA-event time of `iters` back-to-back calls on the current stream, in seconds."""
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(iters):
+        fn()
+    end.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bodies-per-gpu", type=int, default=BODIES_PER_GPU)
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16", "tf32", "bf16x3", "auto"])
+    ap.add_argument("--lbs", default="tc", choices=["fma", "tc", "dense", "auto"])
+    ap.add_argument("--weights", default="sparse", choices=["sparse", "dense"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-iters", type=int, default=50)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from human_3d_reconstruction_b200 import SMPL, capi, synthetic, sharding
+    from human_3d_reconstruction_b200 import smpl as ops
+    from human_3d_reconstruction_b200.smpl import HostRunner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.bodies_per_gpu
+    peaks = load_peaks()
+
+    model = synthetic.make_model(0, weights=args.weights)
+    layer = SMPL(model, precision=args.precision, lbs=args.lbs).to(dev)
+    betas, pose, cam = synthetic.make_inputs(n, 1 + rank)
+    tb, tp, tc = (torch.from_numpy(x).to(dev) for x in (betas, pose, cam))
+    n_total = n * world
+
+    def step():
+        v, j, k = layer(tb, tp, tc)
+        if world > 1:  # optional gather of the small outputs (configs[3]); vertices stay sharded
+            j = sharding.all_gather_rows(j, n_total)
+            k = sharding.all_gather_rows(k, n_total)
+        return v, j, k
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        t_wall0 = time.time()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(args.steps):
+            step()
+        end.record()
+        barrier()
+        t_wall1 = time.time()
+        elapsed = start.elapsed_time(end) * 1e-3
+        if world > 1:
+            t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            elapsed = float(t.item())
+        value = n_total * args.steps / elapsed
+
+        # ---- e2e through the C-ABI host entry point (pinned host buffers) -----------------
+        def e2e_rate(with_vertices: bool, iters: int):
+            runner = HostRunner(layer, n, dev, with_vertices=with_vertices, with_cam=True)
+            runner.betas.copy_(torch.from_numpy(betas)); runner.pose.copy_(torch.from_numpy(pose))
+            runner.cam.copy_(torch.from_numpy(cam))
+            for _ in range(3):
+                runner.run()
+            barrier()
+            dt = time_loop(runner.run, iters, torch)
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return n_total * iters / dt, runner.h2d_bytes, runner.d2h_bytes
+
+        e2e_iters = max(10, min(args.steps, 200))
+        e2e_val, h2d, d2h = e2e_rate(False, e2e_iters)
+        e2e_v_val, h2d_v, d2h_v = e2e_rate(True, max(3, min(args.steps, 10)))
+
+        # ---- per-kernel timing (rank 0) for the roofline ------------------------------------
+        kernels = {}
+        if rank == 0:
+            flags = layer.flags
+            coef, A, joints = ops.pose_chain(layer, tb, tp)
+            vposed = ops.blendshapes(layer, coef, flags=flags)
+            it = args.kernel_iters
+            h = layer.handle(dev)
+            lib = capi.lib()
+            s = torch.cuda.current_stream(dev).cuda_stream
+            verts = torch.empty((n, layer.num_verts, 3), device=dev)
+            kp = torch.empty((n, 24, 2), device=dev)
+            ws = torch.empty(h.workspace_bytes(n, flags), dtype=torch.uint8, device=dev)
+            wsb = int(lib.smplb200_blendshapes_workspace_bytes(h.ptr, n, flags))
+            wsl = int(lib.smplb200_lbs_workspace_bytes(h.ptr, n, flags))
+
+            def k2():
+                capi.check(lib.smplb200_pose_chain(h.ptr, tb.data_ptr(), tp.data_ptr(), n, coef.data_ptr(),
+                                                   A.data_ptr(), joints.data_ptr(), flags, s), "k2")
+
+            def k1():  # note: the stand-alone entry also runs the small operand pack kernel
+                capi.check(lib.smplb200_blendshapes(h.ptr, coef.data_ptr(), n, vposed.data_ptr(), ws.data_ptr(),
+                                                    wsb, flags, s), "k1")
+
+            def k3():
+                capi.check(lib.smplb200_lbs(h.ptr, vposed.data_ptr(), A.data_ptr(), n, verts.data_ptr(),
+                                            joints.data_ptr(), tc.data_ptr(), kp.data_ptr(), ws.data_ptr(),
+                                            wsl, flags, s), "k3")
+
+            for name, fn, byts in (("k2_pose_chain", k2, BYTES_K2), ("k1_blendshapes", k1, BYTES_K1),
+                                   ("k3_lbs", k3, BYTES_K3)):
+                for _ in range(3):
+                    fn()
+                dt = time_loop(fn, it, torch) / it
+                kernels[name] = {"us": dt * 1e6, "gbs": byts * n / dt * 1e-9}
+        t_kern_end = time.time()
+
+    clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
+    if sampler:
+        sampler.stop()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        bps, cores, times = cpu_oracle_throughput(model, 256, 2, 8)
+        cpu = {"value": bps, "unit": "bodies/s", "cores": cores, "kind": "port",
+               "sample": f"oracle/smpl_ref.py fp32, 256-body calls, 2 warm-up + 8 timed (median), "
+                         f"{sum(times):.1f} s of CPU work"}
+
+    if rank == 0:
+        k3 = kernels["k3_lbs"]; k1 = kernels["k1_blendshapes"]
+        hbm = peaks["hbm_gbs"]
+        tf_k1 = FLOPS_K1 * n / (k1["us"] * 1e-6) * 1e-12
+        roof_k = {
+            "k3_lbs": {"bound": "hbm", "achieved": k3["gbs"], "peak": hbm, "unit": "GB/s",
+                       "frac": k3["gbs"] / hbm, "us": k3["us"], "bytes_per_body": BYTES_K3},
+            "k1_blendshapes": {"bound": "hbm", "achieved": k1["gbs"], "peak": hbm, "unit": "GB/s",
+                               "frac": k1["gbs"] / hbm, "us": k1["us"], "bytes_per_body": BYTES_K1,
+                               "tensor_tflops": tf_k1, "tensor_frac_of_bf16_burst": tf_k1 / peaks["bf16_tflops"],
+                               "note": "K=217: write-bound, tensor frac capped at ~0.42 of bf16 burst (SURVEY B.2)"},
+            "k2_pose_chain": {"bound": "latency", "us": kernels["k2_pose_chain"]["us"],
+                              "achieved": kernels["k2_pose_chain"]["gbs"], "unit": "GB/s"},
+            "whole_step": {"bound": "hbm", "achieved": BYTES_E2E * value / world * 1e-9, "peak": hbm,
+                           "unit": "GB/s", "frac": BYTES_E2E * value / world * 1e-9 / hbm,
+                           "bytes_per_body": BYTES_E2E},
+        }
+        launches_per_step = layer.launch_count(n, True, dev)
+        line = {
+            "metric": "smpl_forward_bodies_per_sec", "value": value, "unit": "bodies/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"SMPL forward + 2D keypoint projection, batch {n} per GPU "
+                            f"(BASELINE.json configs[2]), synthetic SMPL-shaped model seed 0 "
+                            f"(6890 verts, 24 joints, 10 betas, 207 posedirs, {args.weights} weights)",
+                "blendshape_operands": args.precision, "lbs": args.lbs, "accumulate": "fp32",
+                "parallelism": f"batch-sharded x{world}, no data-path collective"
+                               + ("; NCCL all-gather of joints+kp2d in the step" if world > 1 else ""),
+                "l2": "per step ~1.0 GB streams through HBM (vposed 340 MB w+r, vertices 340 MB w) >> 126 MB L2; "
+                      "model tensors (19 MB) are L2-resident by design and excluded from algorithmic bytes",
+            },
+            "e2e": {"value": e2e_val, "unit": "bodies/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "smplb200_forward_host: pinned host betas/pose/cam H2D, forward, joints+kp2d D2H; "
+                            "vertices remain device-resident"},
+            "e2e_vertices_d2h": {"value": e2e_v_val, "unit": "bodies/s", "h2d_bytes_per_step": h2d_v,
+                                 "d2h_bytes_per_step": d2h_v, "note": "same call also copying all vertices to the host"},
+            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": {**roof_k["k3_lbs"], "kernel": "k_lbs_tc" if args.lbs in ("tc", "auto") else "k_lbs_fma",
+                         "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": None},
+            "roofline_kernels": roof_k,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -8,7 +8,7 @@ namespace smplb200 {
 constexpr int kJ = 24;             // joints (fixed by the kintree warp layout: lane j = joint j)
 constexpr int kP = 9 * (kJ - 1);   // 207 pose-feature terms
 constexpr int kCoefK = 224;        // padded contraction length (betas | pose_feature | 1 | 0...)
-constexpr int kMaxBetas = 16;
+constexpr int kMaxBetas = 14;       // NB + 207 pose terms + 3 template rows <= 224
 constexpr int kVertTile = 128;     // vertices per tile == TMEM lanes == LBS CTA width
 
 // Device-resident packed model (all pointers are device pointers unless noted).

@@ -99,12 +99,12 @@ k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __rest
     J0 = fmaf(bk, js[0], J0); J1 = fmaf(bk, js[1], J1); J2 = fmaf(bk, js[2], J2);
   }
 
-  // ---- blendshape coefficients: betas | (R - I) of joints 1..23 | 1 | zeros
+  // ---- blendshape coefficients: betas | (R - I) of joints 1..23 | 1 1 1 | zeros
   float* sc = s_coef[warp];
   for (int k = lane; k < kCoefK; k += 32) sc[k] = 0.f;
   __syncwarp();
   if (lane < NB) sc[lane] = __ldg(bb + lane);
-  if (lane == 0) sc[NB + kP] = 1.0f;
+  if (lane < 3) sc[NB + kP + lane] = 1.0f;   // v_template rows (split in 3 exact pieces for tcgen05)
   if (active && j >= 1) {
     float* pf = sc + NB + 9 * (j - 1);
     pf[0] = __fsub_rn(R[0], 1.f); pf[1] = R[1]; pf[2] = R[2];

@@ -368,16 +368,31 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     const int ntile = NC / 128;
     std::vector<uint16_t> bhi((size_t)ntile * kCoefK * 128, 0), blo((size_t)ntile * kCoefK * 128, 0);
     std::vector<uint32_t> btf((size_t)ntile * kCoefK * 128, 0);
+    // The v_template row is O(1 m) while blendshape terms are O(1 mm): it is split EXACTLY over
+    // three of the spare K rows (coefficient 1.0 each): bf16 hi+mid+lo / tf32 hi+lo(+rest).
+    auto tmpl_piece = [&](float x, int piece, bool tf) -> float {
+      float rem = x;
+      for (int p = 0; p <= piece; ++p) {
+        const float h = tf ? bits_to_f32(host_tf32(rem)) : host_bf16_to_f32(host_bf16(rem));
+        if (p == piece) return h;
+        rem -= h;
+      }
+      return 0.f;
+    };
     for (int t = 0; t < ntile; ++t)
       for (int k = 0; k < kCoefK; ++k)
         for (int r = 0; r < 128; ++r) {
-          const float x = k < KB ? basis[(size_t)k * NC + t * 128 + r] : 0.f;
+          const int tp = k - (NB + kP);  // 0,1,2 -> template pieces
+          const float raw = k < NB + kP ? basis[(size_t)k * NC + t * 128 + r] : 0.f;
+          const float tv = (tp >= 0 && tp < 3) ? basis[(size_t)(NB + kP) * NC + t * 128 + r] : 0.f;
+          const float x = (tp >= 0 && tp < 3) ? tmpl_piece(tv, tp, false) : raw;
+          const float xt = (tp >= 0 && tp < 3) ? tmpl_piece(tv, tp, true) : raw;
           const uint16_t h = host_bf16(x);
           const size_t o16 = (size_t)t * kCoefK * 128 + (size_t)(k >> 3) * (128 * 8) + r * 8 + (k & 7);
           bhi[o16] = h;
           blo[o16] = host_bf16(x - host_bf16_to_f32(h));
           const size_t o32 = (size_t)t * kCoefK * 128 + (size_t)(k >> 2) * (128 * 4) + r * 4 + (k & 3);
-          btf[o32] = host_tf32(x);
+          btf[o32] = host_tf32(xt);
         }
     // skinning weights W' = [W_hi | W_lo] per 128-vertex tile, K = 48 tf32 (3xTF32 split blend)
     const int vtile = VP / 128;

@@ -19,7 +19,7 @@
  *   - all tensors are fp32, C-contiguous; "device" pointers live on the model's CUDA device;
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host sync;
  *   - thread-safe and re-entrant: one model handle per device, calls may come from any thread.
- *   - N = bodies, V = vertices (6890), J = joints (24), NB = betas (<=16), P = 9*(J-1) = 207.
+ *   - N = bodies, V = vertices (6890), J = joints (24), NB = betas (<=14), P = 9*(J-1) = 207.
  *
  * There is NO CPU fallback: every entry point below launches hand-written sm_100a kernels.
  */
@@ -79,7 +79,7 @@ typedef struct SmplB200ModelDesc {
   int32_t device;            /* CUDA device ordinal the handle lives on                      */
   int32_t num_verts;         /* V  (>= 1)                                                    */
   int32_t num_joints;        /* J  (must be 24)                                              */
-  int32_t num_betas;         /* NB (1..16)                                                   */
+  int32_t num_betas;         /* NB (1..14)                                                   */
   const float* v_template;   /* [V,3]                                                        */
   const float* shapedirs;    /* [NB, 3V]   column = 3*v + c                                  */
   const float* posedirs;     /* [9*(J-1), 3V]                                                */
@@ -128,7 +128,8 @@ int smplb200_forward_host(const SmplB200Model* model,
 
 /* ---- per-kernel entry points (unit parity + ncu) ---------------------------------------- */
 /* Internal intermediate layouts (owned by this library, stable within a version):
- *   coef   [N, 224] fp32   k<NB: betas; NB..NB+206: pose_feature (R[1:]-I); NB+207: 1.0; rest 0
+ *   coef   [N, 224] fp32   k<NB: betas; NB..NB+206: pose_feature (R[1:]-I); NB+207..209: 1.0
+ *                          (v_template, split exactly over 3 rows for the tcgen05 paths); rest 0
  *   A      [N, J, 12] fp32 rows 0..2 of the rest-pose-removed joint transforms, row-major 3x4
  *   vposed [N, 3, VP] fp32 planar (x-plane, y-plane, z-plane), VP = V rounded up to 128
  */

@@ -40,7 +40,7 @@ def main():
         NB = layer.num_betas
         print("coef betas", err(coef[:, :NB], torch.from_numpy(betas)))
         print("coef pf", err(coef[:, NB:NB + 207], inter["pose_feature"]))
-        print("coef one/pad", coef[:, NB + 207].min().item(), coef[:, NB + 208:].abs().max().item())
+        print("coef one/pad", coef[:, NB + 207:NB + 210].min().item(), coef[:, NB + 210:].abs().max().item())
         print("A", err(A.view(n, 24, 3, 4), inter["A"][:, :, :3, :]))
         print("joints", err(joints, ref_j))
     elif case.startswith("blend_"):

@@ -1,0 +1,93 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/smpl_b200.h declares; host-side validation works without a GPU; nothing falls back to CPU
+compute."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from human_3d_reconstruction_b200 import SMPL, capi, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    entry.build()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "smpl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(smplb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    names = declared_symbols()
+    assert len(names) >= 20
+    handle = ctypes.CDLL(capi.LIB_PATH)
+    for name in names:
+        assert hasattr(handle, name), f"{name} declared in smpl_b200.h but not exported"
+    assert set(names) == set(capi.SYMBOLS), "capi.SYMBOLS must bind exactly the header's entry points"
+
+
+def test_version_and_strerror():
+    lib = capi.lib()
+    assert lib.smplb200_version() == 100
+    assert capi.strerror(0) == "ok"
+    assert "workspace" in capi.strerror(3)
+    assert capi.strerror(12345) == "unknown status"
+
+
+def test_null_and_bad_args_rejected_without_gpu():
+    lib = capi.lib()
+    out = ctypes.c_void_p()
+    assert lib.smplb200_model_create(None, ctypes.byref(out)) == 1
+    desc = capi.ModelDesc()
+    desc.struct_size = 4  # wrong size
+    assert lib.smplb200_model_create(ctypes.byref(desc), ctypes.byref(out)) == 1
+    assert lib.smplb200_workspace_bytes(None, 10, 0) == 0
+    assert lib.smplb200_forward(None, None, None, None, 1, None, None, None, None, 0, 0, None) == 1
+    assert lib.smplb200_model_num_verts(None) == 0
+    lib.smplb200_model_destroy(None)  # no-op
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_model_create_reports_no_device_on_cpu_box():
+    m = synthetic.make_model(0, num_verts=256)
+    with pytest.raises(RuntimeError, match="no usable CUDA device|CUDA"):
+        capi.ModelHandle(m, 0)
+
+
+def test_module_is_cuda_only_and_forward_only():
+    layer = SMPL.synthetic(0)
+    assert layer.num_verts == 6890 and layer.num_joints == 24 and layer.num_betas == 10
+    # buffers (not parameters): replicated by DataParallel, harmless in state_dict
+    assert len(list(layer.parameters())) == 0
+    assert {"v_template", "shapedirs", "posedirs", "J_regressor", "weights", "parents"} <= set(
+        dict(layer.named_buffers()))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        layer(torch.zeros(2, 10), torch.zeros(2, 72))
+
+
+def test_flags():
+    assert capi.make_flags() == 0
+    f = capi.make_flags("bf16x3", "regressed", True, "tc")
+    assert f & capi.PREC_MASK == capi.PREC_BF16X3 and f & capi.JOINTS_REGRESSED and f & capi.ROTATE_BASE
+    assert f & (3 << 5) == capi.LBS_TC
+    with pytest.raises(ValueError):
+        capi.make_flags("fp64")
+
+
+def test_product_never_imports_oracle():
+    """The product path may not route through the oracle (or any CPU compute fallback)."""
+    pkg = os.path.join(ROOT, "human-3d-reconstruction_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("oracle/", ""), f"{fn} mentions the oracle module"
+            assert "import oracle" not in src and "from oracle" not in src

@@ -1,0 +1,57 @@
+"""Host-side multi-GPU logic on CPU: shard bounds and the optional all-gather of joints, run
+with the gloo backend at world_size 2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from human_3d_reconstruction_b200 import sharding
+
+
+@pytest.mark.parametrize("n,world", [(0, 2), (1, 2), (7, 2), (8, 2), (65536, 8), (10, 4), (3, 8)])
+def test_shard_bounds_partition(n, world):
+    spans = [sharding.shard_bounds(n, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    for (a, b), (c, d) in zip(spans, spans[1:]):
+        assert b == c and a <= b and c <= d
+    assert max(b - a for a, b in spans) <= sharding.shard_size(n, world)
+
+
+def _worker(rank, world, port, n, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        betas = torch.randn(n, 10, generator=g)
+        pose = torch.randn(n, 72, generator=g)
+        cam = torch.randn(n, 3, generator=g)
+
+        def fake_forward(b, p, c):  # stands in for the CUDA layer: per-body independent maps
+            verts = (b.sum(1, keepdim=True) + p[:, :3]).unsqueeze(1).expand(-1, 5, -1).contiguous()
+            joints = p.view(-1, 24, 3) * 2.0
+            kp = c[:, None, 0:1] * (joints[:, :, :2] + c[:, None, 1:3])
+            return verts, joints, kp
+
+        sh = sharding.ShardedSMPL(fake_forward)
+        verts, joints, kp2d, (lo, hi) = sh.forward(betas, pose, cam, gather=True)
+        ref_v, ref_j, ref_k = fake_forward(betas, pose, cam)
+        assert (lo, hi) == sharding.shard_bounds(n, world, rank)
+        assert torch.equal(verts, ref_v[lo:hi])          # vertices stay sharded
+        assert torch.equal(joints, ref_j) and torch.equal(kp2d, ref_k)  # small outputs gathered
+        v2, j2, k2, _ = sh.forward(betas, pose, cam, gather=False)
+        assert torch.equal(j2, ref_j[lo:hi]) and torch.equal(k2, ref_k[lo:hi])
+        with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
+            f.write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [7, 8, 1])
+def test_sharded_forward_and_gather_gloo_world2(tmp_path, n):
+    port = 29500 + (os.getpid() % 500) + n
+    mp.spawn(_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(2))
