@@ -29,11 +29,11 @@ struct DeviceModel {
   const int* jreg_ptr;             // [J+1] CSR over joints
   const int* jreg_idx;             // [jreg_nnz] vertex index
   const float* jreg_val;           // [jreg_nnz]
-  // tensor-core operand images (see k_blend_tc.cuh / k_lbs_tc.cuh)
-  const uint16_t* basis_bf16_hi;   // [NC/128 tiles][28 chunks][128 rows][8]   canonical K-major
-  const uint16_t* basis_bf16_lo;   // same, low part of the 2-term bf16 split
-  const uint32_t* basis_tf32;      // [NC/128 tiles][56 chunks][128 rows][4]
-  const uint32_t* w_tf32;          // [VP/128 tiles][12 chunks][128 rows][4]  (W_hi | W_lo)
+  // tensor-core operands (see k_blend_tc.cuh / k_lbs_tc.cuh)
+  const uint32_t* basis_rows_bf16_hi;  // [NC][112] basis^T rows, 2 bf16 per word (TMEM A operand)
+  const uint32_t* basis_rows_bf16_lo;  // same, low part of the 2-term bf16 split
+  const uint32_t* basis_rows_tf32;     // [NC][224] tf32
+  const uint32_t* w_tf32;              // [VP][48] skinning-weight rows, tf32 W_hi(24) | W_lo(24)
 };
 
 __device__ __forceinline__ float ld_nc(const float* p) { return __ldg(p); }

@@ -2,20 +2,26 @@
 //
 //   vposed^T[col, b] = sum_{k<224} basis^T[col, k] * coef[b, k]          (col = planar column)
 //
-// with coef = [betas | pose_feature | 1 | 0...] so the v_template add is a row of the contraction
-// (K = 10 + 207 + 1 padded to 224 = 14 bf16 / 28 tf32 MMA k-steps).
+// with coef = [betas | pose_feature | 1 1 1 | 0...] so the v_template add is part of the
+// contraction (K = 10 + 207 + 3 padded to 224 = 14 bf16 / 28 tf32 MMA k-steps).
 //
-// Orientation: the BASIS tile is the MMA "A" operand (M = 128 planar columns = 128 TMEM lanes)
-// and a block of 32 bodies is the "B" operand (N = 32 TMEM columns).  Reasons:
-//   * the basis tile (57 KB bf16 / 115 KB split-bf16 or tf32) is loaded ONCE per CTA and stays
-//     resident in shared memory while body blocks stream through a TMA/mbarrier ring;
-//   * an epilogue thread owns one planar column for 32 bodies, so each of its stores is a fully
-//     coalesced 128-byte row segment of the planar vposed[b, plane, v] layout -- no shared-memory
-//     transpose and no TMA-store alignment constraints in the epilogue.
+// Orientation and operand placement
+//   * the BASIS tile is the MMA "A" operand: M = 128 planar columns = the 128 TMEM lanes.  It is
+//     kept RESIDENT IN TENSOR MEMORY (tcgen05.mma with A in TMEM): with A in shared memory every
+//     MMA re-reads 128 x 32 B of A, which at N <= 64 exceeds the 128 B/clk shared-memory port
+//     (round-1a ncu: tc pipe 65% busy for 21% math).  From TMEM the only shared-memory traffic
+//     per MMA is the B operand (64 B/clk).
+//   * a block of 64 bodies is the "B" operand (N = 64), streamed through a bulk-TMA/mbarrier
+//     ring from the K-major operand images that k2 writes.
+//   * an epilogue thread owns one planar column for 64 bodies, so each store instruction of a
+//     warp is one fully coalesced 128-byte segment of the planar vposed[b, plane, v] layout.
+//
+// Scheduling: persistent CTAs (one per SM); the (tile, body-block) units are split into equal
+// contiguous ranges, tile-major, so every CTA does the same amount of work (no wave
+// quantisation) and switches basis tile at most a few times.
 //
 // Warp roles (192 threads): warp 0 = bulk-TMA producer, warp 1 = single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp % 4).  Three mbarrier pipelines: smem
-// full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue), and one barrier for the basis.
+// warps 2..5 = epilogue + basis loader (TMEM lane quarter = warp % 4).
 //
 // Precisions (operands; accumulation is always fp32 in TMEM):
 //   BF16    1 MMA group   hi*hi
@@ -29,40 +35,39 @@
 namespace smplb200 {
 
 constexpr int kTcThreads = 192;
-constexpr int kTcAccBufs = 4;                  // TMEM accumulator ring (4 x 32 columns)
-constexpr int kTcTmemCols = kTcAccBufs * kCoefBlock;  // 128
+constexpr int kTcAccBufs = 4;                           // TMEM accumulator ring (4 x 64 columns)
+constexpr int kTcAccCols = kTcAccBufs * kCoefBlock;     // 256
+constexpr int kTcTmemCols = 512;
 
 template <uint32_t PREC>
 struct BlendTcCfg {
   static constexpr bool kTf32 = PREC == SMPLB200_PREC_TF32;
   static constexpr int kElem = kTf32 ? 4 : 2;
-  static constexpr int kParts = PREC == SMPLB200_PREC_BF16X3 ? 2 : 1;   // hi (+ lo) images
-  static constexpr int kStages = PREC == SMPLB200_PREC_BF16 ? 4 : 3;
-  static constexpr int kChunkElems = 16 / kElem;                         // K elements per 16 B
-  static constexpr int kChunks = kCoefK / kChunkElems;                   // 28 or 56
-  static constexpr int kKSteps = kChunks / 2;                            // 14 or 28
-  static constexpr uint32_t kABytesPart = kCoefK * 128 * kElem;          // one basis image
+  static constexpr int kParts = PREC == SMPLB200_PREC_BF16X3 ? 2 : 1;   // hi (+ lo) operands
+  static constexpr int kStages = 3;
+  static constexpr int kKSteps = kCoefK * kElem / 32;                    // 14 (bf16) or 28 (tf32)
+  static constexpr int kAColsPart = kCoefK * kElem / 4;                  // TMEM columns: 112 / 224
+  static constexpr int kAWords = kAColsPart;                             // 32-bit words per basis row
   static constexpr uint32_t kBBytesPart = kCoefK * kCoefBlock * kElem;   // one coef image
-  static constexpr uint32_t kABytes = kABytesPart * kParts;
   static constexpr uint32_t kBStage = kBBytesPart * kParts;
-  static constexpr uint32_t kBarOffset = kABytes + kStages * kBStage;
+  static constexpr uint32_t kBarOffset = kStages * kBStage;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256;
-  static constexpr uint32_t kLboA = 128 * 16, kLboB = kCoefBlock * 16, kSbo = 128;
+  static constexpr uint32_t kLboB = kCoefBlock * 16, kSbo = 128;
   static constexpr uint32_t kIdesc =
       ptx::make_idesc(kTf32 ? ptx::kFmtTF32 : ptx::kFmtBF16, 128, kCoefBlock);
+  static_assert(kTcAccCols + kAColsPart * kParts <= kTcTmemCols, "TMEM budget");
 };
 
 template <uint32_t PREC>
 __global__ void __launch_bounds__(kTcThreads, 1)
-k_blend_tc(const uint8_t* __restrict__ basis_hi, const uint8_t* __restrict__ basis_lo,
+k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ basis_lo,
            const uint8_t* __restrict__ coef_hi, const uint8_t* __restrict__ coef_lo,
-           long long n, int nblocks, int blocks_per_cta, int NC, float* __restrict__ vposed) {
+           long long n, int nblocks, long long total_units, int NC, float* __restrict__ vposed) {
   using C = BlendTcCfg<PREC>;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + C::kABytes;
+  uint8_t* sB = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOffset);
-  uint64_t* bar_a = bars;                        // basis tile landed
+  uint64_t* bar_a = bars;                        // basis tile resident in TMEM (4 warp arrivals)
   uint64_t* bar_full = bars + 1;                 // [kStages] coef block landed
   uint64_t* bar_empty = bar_full + C::kStages;   // [kStages] MMAs reading the stage retired
   uint64_t* bar_tfull = bar_empty + C::kStages;  // [kTcAccBufs] accumulator ready
@@ -70,13 +75,13 @@ k_blend_tc(const uint8_t* __restrict__ basis_hi, const uint8_t* __restrict__ bas
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + kTcAccBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int blk_begin = blockIdx.y * blocks_per_cta;
-  const int blk_end = min(nblocks, blk_begin + blocks_per_cta);
-  const int nblk = blk_end - blk_begin;
+  // equal contiguous share of the tile-major unit list
+  const long long u0 = total_units * blockIdx.x / gridDim.x;
+  const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
+  const int nunits = (int)(u1 - u0);
 
   if (warp == 0 && lane == 0) {
-    ptx::mbar_init(bar_a, 1);
+    ptx::mbar_init(bar_a, 4);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 1); }
     for (int a = 0; a < kTcAccBufs; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4); }
     ptx::fence_barrier_init();
@@ -86,50 +91,51 @@ k_blend_tc(const uint8_t* __restrict__ basis_hi, const uint8_t* __restrict__ bas
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + kTcAccCols;   // A operand columns follow the accumulators
 
   if (warp == 0) {
-    // ===== bulk-TMA producer =====
-    if (lane == 0 && nblk > 0) {
-      ptx::mbar_arrive_expect_tx(bar_a, C::kABytes);
-      ptx::bulk_g2s_split(sA, basis_hi + (size_t)tile * C::kABytesPart, C::kABytesPart, bar_a);
-      if (C::kParts == 2)
-        ptx::bulk_g2s_split(sA + C::kABytesPart, basis_lo + (size_t)tile * C::kABytesPart,
-                            C::kABytesPart, bar_a);
-      for (int i = 0; i < nblk; ++i) {
+    // ===== bulk-TMA producer: coef images of the body blocks =====
+    if (lane == 0) {
+      for (int i = 0; i < nunits; ++i) {
         const int s = i % C::kStages;
+        const int blk = (int)((u0 + i) % nblocks);
         ptx::mbar_wait(bar_empty + s, ((i / C::kStages) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(bar_full + s, C::kBStage);
         uint8_t* dst = sB + (size_t)s * C::kBStage;
-        const size_t src = (size_t)(blk_begin + i) * C::kBBytesPart;
+        const size_t src = (size_t)blk * C::kBBytesPart;
         ptx::bulk_g2s(dst, coef_hi + src, C::kBBytesPart, bar_full + s);
         if (C::kParts == 2) ptx::bulk_g2s(dst + C::kBBytesPart, coef_lo + src, C::kBBytesPart, bar_full + s);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    if (lane == 0 && nblk > 0) {
-      ptx::mbar_wait(bar_a, 0);
-      const uint32_t a_addr = ptx::smem_u32(sA);
-      for (int i = 0; i < nblk; ++i) {
+    if (lane == 0) {
+      long long cur_tile = -1;
+      uint32_t a_phase = 0;
+      for (int i = 0; i < nunits; ++i) {
         const int s = i % C::kStages, a = i % kTcAccBufs;
+        const long long tile = (u0 + i) / nblocks;
+        if (tile != cur_tile) {            // wait until the epilogue warps have (re)loaded A
+          ptx::mbar_wait(bar_a, a_phase);
+          a_phase ^= 1;
+          cur_tile = tile;
+        }
         ptx::mbar_wait(bar_tempty + a, ((i / kTcAccBufs) & 1) ^ 1);
         ptx::mbar_wait(bar_full + s, (i / C::kStages) & 1);
         ptx::tc_fence_after();
         const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * C::kBStage);
         const uint32_t d_tmem = tmem_base + a * kCoefBlock;
         uint32_t acc = 0;
-        // MMA groups: (A part, B part) = (hi,hi) [, (hi,lo), (lo,hi)]
-        constexpr int kGroups = C::kParts == 2 ? 3 : 1;
+        constexpr int kGroups = C::kParts == 2 ? 3 : 1;   // (hi,hi) [, (hi,lo), (lo,hi)]
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
-          const uint32_t ap = a_addr + (g == 2 ? C::kABytesPart : 0);
+          const uint32_t ap = tmem_a + (g == 2 ? C::kAColsPart : 0);
           const uint32_t bp = b_addr + (g == 1 ? C::kBBytesPart : 0);
 #pragma unroll
           for (int ks = 0; ks < C::kKSteps; ++ks) {
-            const uint64_t ad = ptx::make_smem_desc(ap + ks * 2 * C::kLboA, C::kLboA, C::kSbo);
             const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * C::kLboB, C::kLboB, C::kSbo);
-            if (C::kTf32) ptx::mma_tf32(d_tmem, ad, bd, C::kIdesc, acc);
-            else ptx::mma_bf16(d_tmem, ad, bd, C::kIdesc, acc);
+            if (C::kTf32) ptx::mma_tf32_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
+            else ptx::mma_bf16_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
             acc = 1;
           }
         }
@@ -138,25 +144,58 @@ k_blend_tc(const uint8_t* __restrict__ basis_hi, const uint8_t* __restrict__ bas
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> coalesced planar stores =====
+    // ===== epilogue + basis loader =====
     const int q = warp & 3;                               // TMEM lane quarter of this warp
-    const int col = tile * 128 + q * 32 + lane;           // planar column owned by this thread
-    for (int i = 0; i < nblk; ++i) {
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    long long cur_tile = -1;
+    for (int i = 0; i < nunits; ++i) {
       const int a = i % kTcAccBufs;
+      const long long tile = (u0 + i) / nblocks;
+      const int blk = (int)((u0 + i) % nblocks);
+      if (tile != cur_tile) {
+        // Every earlier unit's accumulator was waited on below, so all MMAs that read the old
+        // basis tile have retired: overwrite the A operand columns with the new tile's rows.
+        cur_tile = tile;
+        const size_t row = (size_t)tile * 128 + q * 32 + lane;
+#pragma unroll
+        for (int part = 0; part < C::kParts; ++part) {
+          const uint4* src = reinterpret_cast<const uint4*>((part ? basis_lo : basis_hi) + row * C::kAWords);
+#pragma unroll 7
+          for (int c = 0; c < C::kAWords / 16; ++c) {
+            uint32_t w[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint4 x = __ldg(src + c * 4 + v);
+              w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+            ptx::tmem_st16(tmem_a + lane_addr + part * C::kAColsPart + c * 16, w);
+          }
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_a);
+        __syncwarp();
+      }
       ptx::mbar_wait(bar_tfull + a, (i / kTcAccBufs) & 1);
       ptx::tc_fence_after();
-      uint32_t r[32];
-      ptx::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * kCoefBlock, r);
+      uint32_t r0[32], r1[32];
+      ptx::tmem_ld32(tmem_base + lane_addr + a * kCoefBlock, r0);
+      ptx::tmem_ld32(tmem_base + lane_addr + a * kCoefBlock + 32, r1);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       if (lane == 0) ptx::mbar_arrive(bar_tempty + a);
       __syncwarp();
-      const long long b0 = (long long)(blk_begin + i) * kCoefBlock;
+      const long long b0 = (long long)blk * kCoefBlock;
+      const int col = (int)tile * 128 + q * 32 + lane;    // planar column owned by this thread
       float* dst = vposed + (size_t)b0 * NC + col;
       const int nb = (int)min((long long)kCoefBlock, n - b0);
 #pragma unroll
-      for (int j = 0; j < kCoefBlock; ++j)
-        if (j < nb) dst[(size_t)j * NC] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j)
+        if (j < nb) dst[(size_t)j * NC] = __uint_as_float(r0[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j + 32 < nb) dst[(size_t)(j + 32) * NC] = __uint_as_float(r1[j]);
     }
   }
   ptx::tc_fence_before();
@@ -199,16 +238,12 @@ inline void blend_tc_launch(const DeviceModel& m, int num_sms, const void* chi, 
   using C = BlendTcCfg<PREC>;
   const int ntile = m.NC / 128;
   const int nblocks = (int)((n + kCoefBlock - 1) / kCoefBlock);
-  // amortise the resident basis tile over >= 8 body blocks while keeping >= ~4 CTAs per SM queued
-  int bpc = 8;
-  while (bpc < nblocks && (long long)ntile * ((nblocks + bpc - 1) / bpc) > 8LL * num_sms) bpc *= 2;
-  if (bpc > nblocks) bpc = nblocks;
-  const dim3 grid((unsigned)ntile, (unsigned)((nblocks + bpc - 1) / bpc));
-  const uint8_t* bh = reinterpret_cast<const uint8_t*>(C::kTf32 ? (const void*)m.basis_tf32 : (const void*)m.basis_bf16_hi);
-  const uint8_t* bl = reinterpret_cast<const uint8_t*>(m.basis_bf16_lo);
+  const long long total = (long long)ntile * nblocks;
+  const unsigned grid = (unsigned)std::min<long long>(num_sms, total);
+  const uint32_t* bh = C::kTf32 ? m.basis_rows_tf32 : m.basis_rows_bf16_hi;
   k_blend_tc<PREC><<<grid, kTcThreads, C::kSmemBytes, s>>>(
-      bh, bl, static_cast<const uint8_t*>(chi), static_cast<const uint8_t*>(clo), n, nblocks, bpc,
-      m.NC, vposed);
+      bh, m.basis_rows_bf16_lo, static_cast<const uint8_t*>(chi), static_cast<const uint8_t*>(clo), n,
+      nblocks, total, m.NC, vposed);
 }
 
 inline cudaError_t launch_blend_tc(const DeviceModel& m, int num_sms, uint32_t prec,

@@ -12,13 +12,15 @@
 // fp32 fidelity comes from the 3xTF32 split (both operands split exactly into tf32 hi + lo):
 //   W*A ~= W_hi*A_hi + W_hi*A_lo + W_lo*A_hi      (dropped lo*lo term ~2^-22 relative)
 // tf32 x tf32 products are exact in the fp32 accumulator, so the blend error is ~1e-7 relative,
-// the same order as an fp32 FMA chain.  Images: W' = [W_hi | W_lo] per 128-vertex tile (resident
-// in shared memory), A' = [A_hi | A_lo] per 16-body block (written by k2, streamed by bulk TMA).
+// the same order as an fp32 FMA chain.  W' = [W_hi | W_lo] rows of a 128-vertex tile are RESIDENT
+// IN TENSOR MEMORY as the MMA A operand (no shared-memory re-reads); A' = [A_hi | A_lo] per
+// 16-body block (written by k2) is the B operand, streamed through a bulk-TMA / mbarrier ring.
+// Persistent CTAs own equal contiguous ranges of the tile-major (vertex tile, body block) units.
 //
 // Epilogue thread = vertex: reads its 12 blended entries per body from TMEM, the planar vposed
 // coordinates (prefetched, coalesced), applies the 3x4 transform with FMAs, transposes through a
 // per-warp shared-memory row and emits coalesced stores.  k4 (weak-perspective projection,
-// SURVEY.md A.8) is computed by the CTAs of vertex tile 0 after their last block.
+// SURVEY.md A.8) rides in the epilogue of the CTAs that own vertex tile 0.
 #pragma once
 #include "common.cuh"
 #include "k_chain.cuh"
@@ -30,25 +32,24 @@ constexpr int kLbsTcThreads = 320;                       // TMA warp, MMA warp, 
 constexpr int kLbsTcStages = 3;
 constexpr int kLbsTcAcc = 2;
 constexpr int kLbsN = kLbsBlock * 12;                    // 192
-constexpr int kLbsTmemCols = 512;                        // 2 x 192 rounded to a power of two
-constexpr uint32_t kLbsWBytes = kLbsK * 128 * 4;         // 24,576
+constexpr int kLbsTmemCols = 512;                        // 2 x 192 accumulators + 48 columns of W'
+constexpr int kLbsAccCols = kLbsTcAcc * kLbsN;           // 384
 constexpr uint32_t kLbsBStage = kLbsK * kLbsN * 4;       // 36,864
-constexpr uint32_t kLbsOutOff = kLbsWBytes + kLbsTcStages * kLbsBStage;
+constexpr uint32_t kLbsOutOff = kLbsTcStages * kLbsBStage;
 constexpr uint32_t kLbsBarOff = kLbsOutOff + 8 * 96 * 4;
 constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
 __global__ void __launch_bounds__(kLbsTcThreads, 1)
-k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
-         const float* __restrict__ vposed, long long n, int nblocks, int blocks_per_cta,
+k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
+         const float* __restrict__ vposed, long long n, int nblocks, long long total_units,
          int V, int VP, float* __restrict__ verts, const float* __restrict__ joints_in,
          const float* __restrict__ cam, float* __restrict__ kp2d) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sW = smem;
-  uint8_t* sB = smem + kLbsWBytes;
+  uint8_t* sB = smem;
   float* sOut = reinterpret_cast<float*>(smem + kLbsOutOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLbsBarOff);
-  uint64_t* bar_w = bars;
+  uint64_t* bar_w = bars;                          // W' rows resident in TMEM (4 warp arrivals)
   uint64_t* bar_full = bars + 1;
   uint64_t* bar_empty = bar_full + kLbsTcStages;
   uint64_t* bar_tfull = bar_empty + kLbsTcStages;
@@ -56,13 +57,13 @@ k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + kLbsTcAcc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
-  const int blk_begin = blockIdx.y * blocks_per_cta;
-  const int blk_end = min(nblocks, blk_begin + blocks_per_cta);
-  const int nblk = blk_end - blk_begin;
+  // equal contiguous share of the tile-major (vertex tile, body block) unit list
+  const long long u0 = total_units * blockIdx.x / gridDim.x;
+  const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
+  const int nunits = (int)(u1 - u0);
 
   if (warp == 0 && lane == 0) {
-    ptx::mbar_init(bar_w, 1);
+    ptx::mbar_init(bar_w, 4);
     for (int s = 0; s < kLbsTcStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 1); }
     for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 8); }
     ptx::fence_barrier_init();
@@ -72,27 +73,31 @@ k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_w = tmem_base + kLbsAccCols;
 
   if (warp == 0) {
-    if (lane == 0 && nblk > 0) {
-      ptx::mbar_arrive_expect_tx(bar_w, kLbsWBytes);
-      ptx::bulk_g2s(sW, w_img + (size_t)tile * kLbsWBytes, kLbsWBytes, bar_w);
-      for (int i = 0; i < nblk; ++i) {
+    // ===== bulk-TMA producer: tf32 hi|lo images of the joint transforms =====
+    if (lane == 0) {
+      for (int i = 0; i < nunits; ++i) {
         const int s = i % kLbsTcStages;
+        const int blk = (int)((u0 + i) % nblocks);
         ptx::mbar_wait(bar_empty + s, ((i / kLbsTcStages) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(bar_full + s, kLbsBStage);
-        ptx::bulk_g2s_split(sB + (size_t)s * kLbsBStage, a_img + (size_t)(blk_begin + i) * kLbsBStage,
-                            kLbsBStage, bar_full + s);
+        ptx::bulk_g2s_split(sB + (size_t)s * kLbsBStage, a_img + (size_t)blk * kLbsBStage, kLbsBStage,
+                            bar_full + s);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nblk > 0) {
-      ptx::mbar_wait(bar_w, 0);
-      const uint32_t w_addr = ptx::smem_u32(sW);
-      constexpr uint32_t kLboW = 128 * 16, kLboB = kLbsN * 16, kSbo = 128;
-      constexpr uint32_t kHalfW = 6 * kLboW, kHalfB = 6 * kLboB;  // byte offset of the "lo" K half
-      for (int i = 0; i < nblk; ++i) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t kLboB = kLbsN * 16, kSbo = 128;
+      constexpr uint32_t kHalfB = 6 * kLboB;     // byte offset of the A_lo K half in the image
+      long long cur_tile = -1;
+      uint32_t w_phase = 0;
+      for (int i = 0; i < nunits; ++i) {
         const int s = i % kLbsTcStages, a = i % kLbsTcAcc;
+        const long long tile = (u0 + i) / nblocks;
+        if (tile != cur_tile) { ptx::mbar_wait(bar_w, w_phase); w_phase ^= 1; cur_tile = tile; }
         ptx::mbar_wait(bar_tempty + a, ((i / kLbsTcAcc) & 1) ^ 1);
         ptx::mbar_wait(bar_full + s, (i / kLbsTcStages) & 1);
         ptx::tc_fence_after();
@@ -101,13 +106,12 @@ k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
         uint32_t acc = 0;
 #pragma unroll
         for (int g = 0; g < 3; ++g) {  // (W_hi,A_hi), (W_hi,A_lo), (W_lo,A_hi)
-          const uint32_t wp = w_addr + (g == 2 ? kHalfW : 0);
+          const uint32_t wp = tmem_w + (g == 2 ? 24 : 0);
           const uint32_t bp = b_addr + (g == 1 ? kHalfB : 0);
 #pragma unroll
           for (int ks = 0; ks < 3; ++ks) {  // 24 joints = 3 tf32 k-steps of 8
-            const uint64_t wd = ptx::make_smem_desc(wp + ks * 2 * kLboW, kLboW, kSbo);
             const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * kLboB, kLboB, kSbo);
-            ptx::mma_tf32(d_tmem, wd, bd, kLbsIdesc, acc);
+            ptx::mma_tf32_ts(d_tmem, wp + ks * 8, bd, kLbsIdesc, acc);
             acc = 1;
           }
         }
@@ -120,29 +124,65 @@ k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
     const int ew = warp - 2;              // 0..7
     const int q = warp & 3;               // TMEM lane quarter
     const int h = ew >> 2;                // which 8 of the block's 16 bodies
-    const int v_local = q * 32 + lane;
-    const int v = tile * 128 + v_local;
-    const int warp_v0 = tile * 128 + q * 32;
-    const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float* so = sOut + ew * 96;
-    for (int i = 0; i < nblk; ++i) {
-      const int a = i % kLbsTcAcc;
-      const long long b0 = (long long)(blk_begin + i) * kLbsBlock + h * 8;
+    long long cur_tile = -1;
+
+    // vposed of this warp's 8 bodies of unit i, prefetched one unit ahead (planar, coalesced)
+    float cx[8], cy[8], cz[8], nx[8], ny[8], nz[8];
+    auto prefetch = [&](int i, float (&px)[8], float (&py)[8], float (&pz)[8]) {
+      const long long tile = (u0 + i) / nblocks;
+      const int blk = (int)((u0 + i) % nblocks);
+      const long long b0 = (long long)blk * kLbsBlock + h * 8;
       const int nb = (int)max(0LL, min(8LL, n - b0));
-      // prefetch this warp's vposed coordinates (planar, coalesced) before waiting on the MMA
-      float px[8], py[8], pz[8];
+      const float* vp = vposed + (size_t)b0 * 3 * VP + tile * 128 + q * 32 + lane;
 #pragma unroll
       for (int bi = 0; bi < 8; ++bi) {
         if (bi < nb) {
-          const float* vp = vposed + (size_t)(b0 + bi) * 3 * VP + v;
           px[bi] = __ldg(vp); py[bi] = __ldg(vp + VP); pz[bi] = __ldg(vp + 2 * VP);
         } else {
           px[bi] = py[bi] = pz[bi] = 0.f;
         }
+        vp += 3 * (size_t)VP;
       }
+    };
+    if (nunits > 0) prefetch(0, cx, cy, cz);
+
+    for (int i = 0; i < nunits; ++i) {
+      const int a = i % kLbsTcAcc;
+      const long long tile = (u0 + i) / nblocks;
+      const int blk = (int)((u0 + i) % nblocks);
+      if (tile != cur_tile) {
+        // all MMAs that read the old W' have retired (their accumulators were waited on below)
+        cur_tile = tile;
+        if (h == 0) {
+          const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + q * 32 + lane) * kLbsK);
+#pragma unroll
+          for (int c = 0; c < kLbsK / 16; ++c) {
+            uint32_t w[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint4 x = __ldg(src + c * 4 + v);
+              w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+            ptx::tmem_st16(tmem_w + lane_addr + c * 16, w);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_w);
+          __syncwarp();
+        }
+      }
+      if (i + 1 < nunits) prefetch(i + 1, nx, ny, nz);   // in flight while unit i is processed
+
+      const long long b0 = (long long)blk * kLbsBlock + h * 8;
+      const int nb = (int)max(0LL, min(8LL, n - b0));
+      const int warp_v0 = (int)tile * 128 + q * 32;
+      const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
       ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kLbsN + h * 96;
+      const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN + h * 96;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {   // 4 bodies = 48 TMEM columns per round
         uint32_t r0[16], r1[16], r2[16];
@@ -164,7 +204,7 @@ k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
         for (int bb = 0; bb < 4; ++bb) {
           const int bi = half * 4 + bb;
           const float* t = T + bb * 12;
-          const float x = px[bi], y = py[bi], z = pz[bi];
+          const float x = cx[bi], y = cy[bi], z = cz[bi];
           const float ox = fmaf(t[2], z, fmaf(t[1], y, fmaf(t[0], x, t[3])));
           const float oy = fmaf(t[6], z, fmaf(t[5], y, fmaf(t[4], x, t[7])));
           const float oz = fmaf(t[10], z, fmaf(t[9], y, fmaf(t[8], x, t[11])));
@@ -179,17 +219,21 @@ k_lbs_tc(const uint8_t* __restrict__ w_img, const uint8_t* __restrict__ a_img,
           }
         }
       }
-    }
-    // k4: weak-perspective projection for this CTA's bodies (vertex tile 0 only)
-    if (tile == 0 && kp2d != nullptr) {
-      const long long bb0 = (long long)blk_begin * kLbsBlock;
-      const long long bb1 = min(n, (long long)blk_end * kLbsBlock);
-      for (long long i = bb0 * (kJ * 2) + (threadIdx.x - 64); i < bb1 * (kJ * 2); i += 256) {
-        const long long b = i / (kJ * 2);
-        const int r = int(i - b * (kJ * 2)), j = r >> 1, c = r & 1;
-        const float s = __ldg(cam + b * 3), t = __ldg(cam + b * 3 + 1 + c);
-        kp2d[i] = __fmul_rn(s, __fadd_rn(__ldg(joints_in + (b * kJ + j) * 3 + c), t));
+      // k4: weak-perspective projection of this block's bodies, by the CTA that owns tile 0
+      if (tile == 0 && kp2d != nullptr) {
+        const int t = (int)threadIdx.x - 64;                       // 0..255
+        const long long bb0 = (long long)blk * kLbsBlock;
+        for (int r = t; r < kLbsBlock * kJ * 2; r += 256) {
+          const long long b = bb0 + r / (kJ * 2);
+          if (b < n) {
+            const int rr = r % (kJ * 2), j = rr >> 1, c = rr & 1;
+            const float sc = __ldg(cam + b * 3), tt = __ldg(cam + b * 3 + 1 + c);
+            kp2d[b * (kJ * 2) + rr] = __fmul_rn(sc, __fadd_rn(__ldg(joints_in + (b * kJ + j) * 3 + c), tt));
+          }
+        }
       }
+#pragma unroll
+      for (int bi = 0; bi < 8; ++bi) { cx[bi] = nx[bi]; cy[bi] = ny[bi]; cz[bi] = nz[bi]; }
     }
   }
   ptx::tc_fence_before();
@@ -221,13 +265,11 @@ inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float*
   if (n == 0) return cudaSuccess;
   const int vtiles = m.VP / 128;
   const int nblocks = (int)((n + kLbsBlock - 1) / kLbsBlock);
-  int bpc = 8;
-  while (bpc < nblocks && (long long)vtiles * ((nblocks + bpc - 1) / bpc) > 8LL * num_sms) bpc *= 2;
-  if (bpc > nblocks) bpc = nblocks;
-  const dim3 grid((unsigned)vtiles, (unsigned)((nblocks + bpc - 1) / bpc));
+  const long long total = (long long)vtiles * nblocks;
+  const unsigned grid = (unsigned)std::min<long long>(num_sms, total);
   k_lbs_tc<<<grid, kLbsTcThreads, kLbsSmemBytes, s>>>(
-      reinterpret_cast<const uint8_t*>(m.w_tf32), reinterpret_cast<const uint8_t*>(a_img), vposed, n,
-      nblocks, bpc, m.V, m.VP, verts, joints_in, cam, kp2d);
+      m.w_tf32, reinterpret_cast<const uint8_t*>(a_img), vposed, n, nblocks, total, m.V, m.VP, verts,
+      joints_in, cam, kp2d);
   return cudaGetLastError();
 }
 

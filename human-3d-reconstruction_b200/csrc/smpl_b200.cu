@@ -363,11 +363,9 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     }
     if (jidx.empty()) { jidx.push_back(0); jval.push_back(0.f); }
 
-    // ---- tensor-core operand images (canonical K-major, no swizzle; k_blend_tc.cuh)
-    // basis^T tiles: tile t = 128 planar columns; image[chunk][row][E]
-    const int ntile = NC / 128;
-    std::vector<uint16_t> bhi((size_t)ntile * kCoefK * 128, 0), blo((size_t)ntile * kCoefK * 128, 0);
-    std::vector<uint32_t> btf((size_t)ntile * kCoefK * 128, 0);
+    // ---- tensor-core A operand of k1: basis^T rows [planar column][K], resident in TMEM
+    std::vector<uint16_t> bhi((size_t)NC * kCoefK, 0), blo((size_t)NC * kCoefK, 0);
+    std::vector<uint32_t> btf((size_t)NC * kCoefK, 0);
     // The v_template row is O(1 m) while blendshape terms are O(1 mm): it is split EXACTLY over
     // three of the spare K rows (coefficient 1.0 each): bf16 hi+mid+lo / tf32 hi+lo(+rest).
     auto tmpl_piece = [&](float x, int piece, bool tf) -> float {
@@ -379,33 +377,28 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
       }
       return 0.f;
     };
-    for (int t = 0; t < ntile; ++t)
-      for (int k = 0; k < kCoefK; ++k)
-        for (int r = 0; r < 128; ++r) {
-          const int tp = k - (NB + kP);  // 0,1,2 -> template pieces
-          const float raw = k < NB + kP ? basis[(size_t)k * NC + t * 128 + r] : 0.f;
-          const float tv = (tp >= 0 && tp < 3) ? basis[(size_t)(NB + kP) * NC + t * 128 + r] : 0.f;
-          const float x = (tp >= 0 && tp < 3) ? tmpl_piece(tv, tp, false) : raw;
-          const float xt = (tp >= 0 && tp < 3) ? tmpl_piece(tv, tp, true) : raw;
-          const uint16_t h = host_bf16(x);
-          const size_t o16 = (size_t)t * kCoefK * 128 + (size_t)(k >> 3) * (128 * 8) + r * 8 + (k & 7);
-          bhi[o16] = h;
-          blo[o16] = host_bf16(x - host_bf16_to_f32(h));
-          const size_t o32 = (size_t)t * kCoefK * 128 + (size_t)(k >> 2) * (128 * 4) + r * 4 + (k & 3);
-          btf[o32] = host_tf32(xt);
-        }
-    // skinning weights W' = [W_hi | W_lo] per 128-vertex tile, K = 48 tf32 (3xTF32 split blend)
-    const int vtile = VP / 128;
-    std::vector<uint32_t> wtf((size_t)vtile * kLbsK * 128, 0);
-    for (int t = 0; t < vtile; ++t)
-      for (int r = 0; r < 128; ++r)
-        for (int j = 0; j < kJ; ++j) {
-          const float x = dense_w[(size_t)(t * 128 + r) * kJ + j];
-          const uint32_t hi = host_tf32(x);
-          const uint32_t lo = host_tf32(x - bits_to_f32(hi));
-          auto at = [&](int k) { return (size_t)t * kLbsK * 128 + (size_t)(k >> 2) * (128 * 4) + r * 4 + (k & 3); };
-          wtf[at(j)] = hi; wtf[at(24 + j)] = lo;
-        }
+    for (int col = 0; col < NC; ++col)
+      for (int k = 0; k < kCoefK; ++k) {
+        const int tp = k - (NB + kP);  // 0,1,2 -> template pieces
+        const float raw = k < NB + kP ? basis[(size_t)k * NC + col] : 0.f;
+        const float tv = (tp >= 0 && tp < 3) ? basis[(size_t)(NB + kP) * NC + col] : 0.f;
+        const float x = (tp >= 0 && tp < 3) ? tmpl_piece(tv, tp, false) : raw;
+        const float xt = (tp >= 0 && tp < 3) ? tmpl_piece(tv, tp, true) : raw;
+        const uint16_t h = host_bf16(x);
+        bhi[(size_t)col * kCoefK + k] = h;
+        blo[(size_t)col * kCoefK + k] = host_bf16(x - host_bf16_to_f32(h));
+        btf[(size_t)col * kCoefK + k] = host_tf32(xt);
+      }
+    // skinning weights as the TMEM A operand of the LBS blend: rows [VP][48] = W_hi(24) | W_lo(24)
+    std::vector<uint32_t> wtf((size_t)VP * kLbsK, 0);
+    for (int v = 0; v < VP; ++v)
+      for (int j = 0; j < kJ; ++j) {
+        const float x = dense_w[(size_t)v * kJ + j];
+        const uint32_t hi = host_tf32(x);
+        const uint32_t lo = host_tf32(x - bits_to_f32(hi));
+        wtf[(size_t)v * kLbsK + j] = hi;
+        wtf[(size_t)v * kLbsK + 24 + j] = lo;
+      }
 
     SmplB200Model* m = new (std::nothrow) SmplB200Model();
     if (!m) return SMPLB200_ERR_ALLOC;
@@ -453,9 +446,9 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     d.jreg_ptr = reinterpret_cast<const int*>(base + o_jp);
     d.jreg_idx = reinterpret_cast<const int*>(base + o_ji);
     d.jreg_val = reinterpret_cast<const float*>(base + o_jv);
-    d.basis_bf16_hi = reinterpret_cast<const uint16_t*>(base + o_bhi);
-    d.basis_bf16_lo = reinterpret_cast<const uint16_t*>(base + o_blo);
-    d.basis_tf32 = reinterpret_cast<const uint32_t*>(base + o_btf);
+    d.basis_rows_bf16_hi = reinterpret_cast<const uint32_t*>(base + o_bhi);
+    d.basis_rows_bf16_lo = reinterpret_cast<const uint32_t*>(base + o_blo);
+    d.basis_rows_tf32 = reinterpret_cast<const uint32_t*>(base + o_btf);
     d.w_tf32 = reinterpret_cast<const uint32_t*>(base + o_wtf);
     *out_model = m;
     return SMPLB200_OK;
