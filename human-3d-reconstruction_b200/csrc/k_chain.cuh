@@ -22,7 +22,7 @@ struct ChainOut {
   uint16_t* coef_bf16_hi; // tensor-core operand images (null unless a tcgen05 path follows)
   uint16_t* coef_bf16_lo;
   uint32_t* coef_tf32;
-  uint32_t* a_tf32;       // [n/16 blocks][12 chunks][192 rows][4] tf32 hi|lo image of A (LBS blend)
+  uint32_t* a_tf32;       // [n/8 blocks][12 chunks][96 rows][4] tf32 hi|lo image of A (LBS blend)
 };
 
 __device__ __forceinline__ void rodrigues_hmr(float tx, float ty, float tz, float R[9]) {
@@ -66,7 +66,7 @@ __device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(uint32_t(h) << 16); }
 
 constexpr int kCoefBlock = 64;   // bodies per tensor-core coefficient image (MMA N)
-constexpr int kLbsBlock = 16;    // bodies per LBS blend image (MMA N = 12 * 16 = 192)
+constexpr int kLbsBlock = 8;     // bodies per LBS blend image (MMA N = 12 * 8 = 96)
 constexpr int kLbsK = 48;        // blend contraction: [A_hi | A_lo] over 24 joints (tf32 split)
 
 __global__ void __launch_bounds__(kChainWarps * 32)

@@ -14,11 +14,14 @@
 // tf32 x tf32 products are exact in the fp32 accumulator, so the blend error is ~1e-7 relative,
 // the same order as an fp32 FMA chain.  W' = [W_hi | W_lo] rows of a 128-vertex tile are RESIDENT
 // IN TENSOR MEMORY as the MMA A operand (no shared-memory re-reads); A' = [A_hi | A_lo] per
-// 16-body block (written by k2) is the B operand, streamed through a bulk-TMA / mbarrier ring.
-// Persistent CTAs own equal contiguous ranges of the tile-major (vertex tile, body block) units.
+// 8-body block (written by k2) is the B operand.  Both A' and the block's planar vposed rows
+// (512 B per body and plane) stream through 3-stage bulk-TMA / mbarrier rings, so ~90 KB of loads
+// are in flight per SM without holding registers; two ~95 KB CTAs share an SM so one CTA's
+// prologue/tail hides behind the other's steady state.  The grid is vertex-tile-fastest: the
+// CTAs resident at one time read and write adjacent row chunks of the same bodies (DRAM pages).
 //
 // Epilogue thread = vertex: reads its 12 blended entries per body from TMEM, the planar vposed
-// coordinates (prefetched, coalesced), applies the 3x4 transform with FMAs, transposes through a
+// coordinates (from the shared-memory ring, conflict-free), applies the 3x4 transform with FMAs, transposes through a
 // per-warp shared-memory row and emits coalesced stores.  k4 (weak-perspective projection,
 // SURVEY.md A.8) rides in the epilogue of the CTAs that own vertex tile 0.
 #pragma once
@@ -28,44 +31,53 @@
 
 namespace smplb200 {
 
-constexpr int kLbsTcThreads = 320;                       // TMA warp, MMA warp, 8 epilogue warps
+constexpr int kLbsTcThreads = 192;                       // TMA warp, MMA warp, 4 epilogue warps
 constexpr int kLbsTcStages = 3;
 constexpr int kLbsTcAcc = 2;
-constexpr int kLbsN = kLbsBlock * 12;                    // 192
-constexpr int kLbsTmemCols = 512;                        // 2 x 192 accumulators + 48 columns of W'
-constexpr int kLbsAccCols = kLbsTcAcc * kLbsN;           // 384
-constexpr uint32_t kLbsBStage = kLbsK * kLbsN * 4;       // 36,864
-constexpr uint32_t kLbsOutOff = kLbsTcStages * kLbsBStage;
-constexpr uint32_t kLbsBarOff = kLbsOutOff + 8 * 96 * 4;
-constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;
+constexpr int kLbsN = kLbsBlock * 12;                    // 96
+constexpr int kLbsTmemCols = 256;                        // 2 x 96 accumulators + 48 columns of W'
+constexpr int kLbsAccCols = kLbsTcAcc * kLbsN;           // 192
+constexpr uint32_t kLbsBStage = kLbsK * kLbsN * 4;       // 18,432  tf32 hi|lo image of A, one block
+constexpr uint32_t kLbsVRow = 128 * 4;                   // one (body, plane) row of the vertex tile
+constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 12,288
+constexpr uint32_t kLbsVOff = kLbsTcStages * kLbsBStage;
+constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsTcStages * kLbsVStage;
+constexpr uint32_t kLbsBarOff = kLbsOutOff + 4 * 96 * 4;
+constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~95 KB -> two CTAs per SM
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
-__global__ void __launch_bounds__(kLbsTcThreads, 1)
+__global__ void __launch_bounds__(kLbsTcThreads, 2)
 k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
-         const float* __restrict__ vposed, long long n, int nblocks, long long total_units,
+         const float* __restrict__ vposed, long long n, int nblocks, int blocks_per_cta,
          int V, int VP, float* __restrict__ verts, const float* __restrict__ joints_in,
          const float* __restrict__ cam, float* __restrict__ kp2d) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
+  uint8_t* sV = smem + kLbsVOff;
   float* sOut = reinterpret_cast<float*>(smem + kLbsOutOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLbsBarOff);
-  uint64_t* bar_w = bars;                          // W' rows resident in TMEM (4 warp arrivals)
-  uint64_t* bar_full = bars + 1;
-  uint64_t* bar_empty = bar_full + kLbsTcStages;
-  uint64_t* bar_tfull = bar_empty + kLbsTcStages;
-  uint64_t* bar_tempty = bar_tfull + kLbsTcAcc;
+  uint64_t* bar_w = bars;                            // W' rows resident in TMEM (4 warp arrivals)
+  uint64_t* bar_bfull = bars + 1;                    // [stages] A' image landed
+  uint64_t* bar_bempty = bar_bfull + kLbsTcStages;   // [stages] MMAs reading it retired
+  uint64_t* bar_vfull = bar_bempty + kLbsTcStages;   // [stages] vposed rows landed
+  uint64_t* bar_vempty = bar_vfull + kLbsTcStages;   // [stages] epilogue warps done with them (4)
+  uint64_t* bar_tfull = bar_vempty + kLbsTcStages;   // [acc] accumulator ready
+  uint64_t* bar_tempty = bar_tfull + kLbsTcAcc;      // [acc] accumulator drained (4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + kLbsTcAcc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // equal contiguous share of the tile-major (vertex tile, body block) unit list
-  const long long u0 = total_units * blockIdx.x / gridDim.x;
-  const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
-  const int nunits = (int)(u1 - u0);
+  const int tile = blockIdx.x;                       // tile-fastest grid: co-resident CTAs touch
+  const int blk_begin = blockIdx.y * blocks_per_cta; // adjacent 512-byte row chunks of the same bodies
+  const int blk_end = min(nblocks, blk_begin + blocks_per_cta);
+  const int nblk = blk_end - blk_begin;
 
   if (warp == 0 && lane == 0) {
     ptx::mbar_init(bar_w, 4);
-    for (int s = 0; s < kLbsTcStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 1); }
-    for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 8); }
+    for (int s = 0; s < kLbsTcStages; ++s) {
+      ptx::mbar_init(bar_bfull + s, 1); ptx::mbar_init(bar_bempty + s, 1);
+      ptx::mbar_init(bar_vfull + s, 1); ptx::mbar_init(bar_vempty + s, 4);
+    }
+    for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, kLbsTmemCols);
@@ -76,30 +88,35 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   const uint32_t tmem_w = tmem_base + kLbsAccCols;
 
   if (warp == 0) {
-    // ===== bulk-TMA producer: tf32 hi|lo images of the joint transforms =====
+    // ===== bulk-TMA producer: A' image + the block's vposed rows (512 B per body and plane) =====
     if (lane == 0) {
-      for (int i = 0; i < nunits; ++i) {
+      for (int i = 0; i < nblk; ++i) {
         const int s = i % kLbsTcStages;
-        const int blk = (int)((u0 + i) % nblocks);
-        ptx::mbar_wait(bar_empty + s, ((i / kLbsTcStages) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(bar_full + s, kLbsBStage);
-        ptx::bulk_g2s_split(sB + (size_t)s * kLbsBStage, a_img + (size_t)blk * kLbsBStage, kLbsBStage,
-                            bar_full + s);
+        const uint32_t par = ((i / kLbsTcStages) & 1) ^ 1;
+        const int blk = blk_begin + i;
+        ptx::mbar_wait(bar_bempty + s, par);
+        ptx::mbar_arrive_expect_tx(bar_bfull + s, kLbsBStage);
+        ptx::bulk_g2s(sB + (size_t)s * kLbsBStage, a_img + (size_t)blk * kLbsBStage, kLbsBStage, bar_bfull + s);
+        const long long b0 = (long long)blk * kLbsBlock;
+        const int nb = (int)min((long long)kLbsBlock, n - b0);
+        ptx::mbar_wait(bar_vempty + s, par);
+        ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nb * 3 * kLbsVRow);
+        const float* src = vposed + (size_t)b0 * 3 * VP + (size_t)tile * 128;
+        uint8_t* dst = sV + (size_t)s * kLbsVStage;
+        for (int r = 0; r < nb * 3; ++r)
+          ptx::bulk_g2s(dst + (size_t)r * kLbsVRow, src + (size_t)r * VP, kLbsVRow, bar_vfull + s);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (lane == 0 && nblk > 0) {
       constexpr uint32_t kLboB = kLbsN * 16, kSbo = 128;
       constexpr uint32_t kHalfB = 6 * kLboB;     // byte offset of the A_lo K half in the image
-      long long cur_tile = -1;
-      uint32_t w_phase = 0;
-      for (int i = 0; i < nunits; ++i) {
+      ptx::mbar_wait(bar_w, 0);
+      for (int i = 0; i < nblk; ++i) {
         const int s = i % kLbsTcStages, a = i % kLbsTcAcc;
-        const long long tile = (u0 + i) / nblocks;
-        if (tile != cur_tile) { ptx::mbar_wait(bar_w, w_phase); w_phase ^= 1; cur_tile = tile; }
         ptx::mbar_wait(bar_tempty + a, ((i / kLbsTcAcc) & 1) ^ 1);
-        ptx::mbar_wait(bar_full + s, (i / kLbsTcStages) & 1);
+        ptx::mbar_wait(bar_bfull + s, (i / kLbsTcStages) & 1);
         ptx::tc_fence_after();
         const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * kLbsBStage);
         const uint32_t d_tmem = tmem_base + a * kLbsN;
@@ -115,84 +132,64 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
             acc = 1;
           }
         }
-        ptx::tc_commit(bar_empty + s);
+        ptx::tc_commit(bar_bempty + s);
         ptx::tc_commit(bar_tfull + a);
       }
     }
   } else {
-    // ===== epilogue =====
-    const int ew = warp - 2;              // 0..7
-    const int q = warp & 3;               // TMEM lane quarter
-    const int h = ew >> 2;                // which 8 of the block's 16 bodies
+    // ===== epilogue (4 warps, TMEM lane quarter q) =====
+    const int q = warp & 3;
+    const int ew = warp - 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int v_local = q * 32 + lane;
+    const int warp_v0 = tile * 128 + q * 32;
+    const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
     float* so = sOut + ew * 96;
-    long long cur_tile = -1;
-
-    // vposed of this warp's 8 bodies of unit i, prefetched one unit ahead (planar, coalesced)
-    float cx[8], cy[8], cz[8], nx[8], ny[8], nz[8];
-    auto prefetch = [&](int i, float (&px)[8], float (&py)[8], float (&pz)[8]) {
-      const long long tile = (u0 + i) / nblocks;
-      const int blk = (int)((u0 + i) % nblocks);
-      const long long b0 = (long long)blk * kLbsBlock + h * 8;
-      const int nb = (int)max(0LL, min(8LL, n - b0));
-      const float* vp = vposed + (size_t)b0 * 3 * VP + tile * 128 + q * 32 + lane;
+    if (nblk > 0) {
+      // W' rows of this vertex tile -> TMEM (A operand of every blend MMA of this CTA)
+      const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + v_local) * kLbsK);
 #pragma unroll
-      for (int bi = 0; bi < 8; ++bi) {
-        if (bi < nb) {
-          px[bi] = __ldg(vp); py[bi] = __ldg(vp + VP); pz[bi] = __ldg(vp + 2 * VP);
-        } else {
-          px[bi] = py[bi] = pz[bi] = 0.f;
+      for (int c = 0; c < kLbsK / 16; ++c) {
+        uint32_t w[16];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 x = __ldg(src + c * 4 + v);
+          w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
         }
-        vp += 3 * (size_t)VP;
+        ptx::tmem_st16(tmem_w + lane_addr + c * 16, w);
       }
-    };
-    if (nunits > 0) prefetch(0, cx, cy, cz);
-
-    for (int i = 0; i < nunits; ++i) {
-      const int a = i % kLbsTcAcc;
-      const long long tile = (u0 + i) / nblocks;
-      const int blk = (int)((u0 + i) % nblocks);
-      if (tile != cur_tile) {
-        // all MMAs that read the old W' have retired (their accumulators were waited on below)
-        cur_tile = tile;
-        if (h == 0) {
-          const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + q * 32 + lane) * kLbsK);
-#pragma unroll
-          for (int c = 0; c < kLbsK / 16; ++c) {
-            uint32_t w[16];
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const uint4 x = __ldg(src + c * 4 + v);
-              w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-            }
-            ptx::tmem_st16(tmem_w + lane_addr + c * 16, w);
-          }
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_w);
-          __syncwarp();
-        }
-      }
-      if (i + 1 < nunits) prefetch(i + 1, nx, ny, nz);   // in flight while unit i is processed
-
-      const long long b0 = (long long)blk * kLbsBlock + h * 8;
-      const int nb = (int)max(0LL, min(8LL, n - b0));
-      const int warp_v0 = (int)tile * 128 + q * 32;
-      const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_w);
+      __syncwarp();
+    }
+    for (int i = 0; i < nblk; ++i) {
+      const int s = i % kLbsTcStages, a = i % kLbsTcAcc;
+      const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
+      const int nb = (int)min((long long)kLbsBlock, n - b0);
+      const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
+      ptx::mbar_wait(bar_vfull + s, (i / kLbsTcStages) & 1);
       ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN + h * 96;
+      const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {   // 4 bodies = 48 TMEM columns per round
         uint32_t r0[16], r1[16], r2[16];
         ptx::tmem_ld16(t_addr + half * 48, r0);
         ptx::tmem_ld16(t_addr + half * 48 + 16, r1);
         ptx::tmem_ld16(t_addr + half * 48 + 32, r2);
+        float px[4], py[4], pz[4];
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const float* p = sv + (half * 4 + bb) * 3 * 128;
+          px[bb] = p[0]; py[bb] = p[128]; pz[bb] = p[256];
+        }
         ptx::tmem_ld_wait();
-        if (half == 1) {
+        if (half == 1) {   // both the accumulator and the vposed stage are now in registers
           ptx::tc_fence_before();
-          if (lane == 0) ptx::mbar_arrive(bar_tempty + a);
+          __syncwarp();
+          if (lane == 0) { ptx::mbar_arrive(bar_tempty + a); ptx::mbar_arrive(bar_vempty + s); }
           __syncwarp();
         }
         float T[48];
@@ -204,7 +201,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         for (int bb = 0; bb < 4; ++bb) {
           const int bi = half * 4 + bb;
           const float* t = T + bb * 12;
-          const float x = cx[bi], y = cy[bi], z = cz[bi];
+          const float x = px[bb], y = py[bb], z = pz[bb];
           const float ox = fmaf(t[2], z, fmaf(t[1], y, fmaf(t[0], x, t[3])));
           const float oy = fmaf(t[6], z, fmaf(t[5], y, fmaf(t[4], x, t[7])));
           const float oz = fmaf(t[10], z, fmaf(t[9], y, fmaf(t[8], x, t[11])));
@@ -219,21 +216,17 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
           }
         }
       }
-      // k4: weak-perspective projection of this block's bodies, by the CTA that owns tile 0
-      if (tile == 0 && kp2d != nullptr) {
-        const int t = (int)threadIdx.x - 64;                       // 0..255
-        const long long bb0 = (long long)blk * kLbsBlock;
-        for (int r = t; r < kLbsBlock * kJ * 2; r += 256) {
-          const long long b = bb0 + r / (kJ * 2);
-          if (b < n) {
-            const int rr = r % (kJ * 2), j = rr >> 1, c = rr & 1;
-            const float sc = __ldg(cam + b * 3), tt = __ldg(cam + b * 3 + 1 + c);
-            kp2d[b * (kJ * 2) + rr] = __fmul_rn(sc, __fadd_rn(__ldg(joints_in + (b * kJ + j) * 3 + c), tt));
-          }
-        }
+    }
+    // k4: weak-perspective projection of this CTA's bodies (CTAs of vertex tile 0 only)
+    if (tile == 0 && kp2d != nullptr) {
+      const long long bb0 = (long long)blk_begin * kLbsBlock;
+      const long long bb1 = min(n, (long long)blk_end * kLbsBlock);
+      for (long long i = bb0 * (kJ * 2) + ((int)threadIdx.x - 64); i < bb1 * (kJ * 2); i += 128) {
+        const long long b = i / (kJ * 2);
+        const int r = int(i - b * (kJ * 2)), j = r >> 1, c = r & 1;
+        const float sc = __ldg(cam + b * 3), tt = __ldg(cam + b * 3 + 1 + c);
+        kp2d[i] = __fmul_rn(sc, __fadd_rn(__ldg(joints_in + (b * kJ + j) * 3 + c), tt));
       }
-#pragma unroll
-      for (int bi = 0; bi < 8; ++bi) { cx[bi] = nx[bi]; cy[bi] = ny[bi]; cz[bi] = nz[bi]; }
     }
   }
   ptx::tc_fence_before();
@@ -258,6 +251,22 @@ k_pack_a(const float* __restrict__ A, long long n, uint32_t* __restrict__ img) {
   im[(size_t)((24 + jj) >> 2) * (kLbsN * 4) + row * 4 + ((24 + jj) & 3)] = lo;
 }
 
+// Grid shape: x = vertex tile (fastest), y = body-block group.  The group count is chosen so the
+// CTA count lands just under a whole number of waves of (2 CTAs x SMs) resident slots.
+inline int lbs_tc_blocks_per_cta(int vtiles, int nblocks, int num_sms) {
+  const double slots = 2.0 * num_sms;
+  int best_bpc = nblocks;
+  double best_eff = -1.0;
+  for (int bpc = nblocks; bpc >= 1; --bpc) {
+    if (bpc < 8 && bpc < nblocks) break;                  // keep the W' load / prologue amortised
+    const int groups = (nblocks + bpc - 1) / bpc;
+    const double waves = vtiles * (double)groups / slots;
+    const double eff = waves / std::ceil(waves);
+    if (eff > best_eff + 0.02) { best_eff = eff; best_bpc = bpc; }
+  }
+  return best_bpc;
+}
+
 inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float* vposed,
                                  const uint32_t* a_img, long long n, float* verts,
                                  const float* joints_in, const float* cam, float* kp2d,
@@ -265,10 +274,10 @@ inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float*
   if (n == 0) return cudaSuccess;
   const int vtiles = m.VP / 128;
   const int nblocks = (int)((n + kLbsBlock - 1) / kLbsBlock);
-  const long long total = (long long)vtiles * nblocks;
-  const unsigned grid = (unsigned)std::min<long long>(num_sms, total);
+  const int bpc = lbs_tc_blocks_per_cta(vtiles, nblocks, num_sms);
+  const dim3 grid((unsigned)vtiles, (unsigned)((nblocks + bpc - 1) / bpc));
   k_lbs_tc<<<grid, kLbsTcThreads, kLbsSmemBytes, s>>>(
-      m.w_tf32, reinterpret_cast<const uint8_t*>(a_img), vposed, n, nblocks, total, m.V, m.VP, verts,
+      m.w_tf32, reinterpret_cast<const uint8_t*>(a_img), vposed, n, nblocks, bpc, m.V, m.VP, verts,
       joints_in, cam, kp2d);
   return cudaGetLastError();
 }
