@@ -11,9 +11,10 @@
 //     MMA re-reads 128 x 32 B of A, which at N <= 64 exceeds the 128 B/clk shared-memory port
 //     (round-1a ncu: tc pipe 65% busy for 21% math).  From TMEM the only shared-memory traffic
 //     per MMA is the B operand (64 B/clk).
-//   * a block of 64 bodies is the "B" operand (N = 64), streamed through a bulk-TMA/mbarrier
-//     ring from the K-major operand images that k2 writes.
-//   * an epilogue thread owns one planar column for 64 bodies, so each store instruction of a
+//   * a block of 128 bodies is the "B" operand (N = 128: 64 clk of tensor time per MMA, enough
+//     to hide the ~40 clk the single issuing thread needs per tcgen05.mma), streamed one K half
+//     per stage through a bulk-TMA/mbarrier ring from the K-major operand images k2 writes.
+//   * an epilogue thread owns one planar column for 128 bodies, so each store instruction of a
 //     warp is one fully coalesced 128-byte segment of the planar vposed[b, plane, v] layout.
 //
 // Scheduling: persistent CTAs (one per SM); the (tile, body-block) units are split into equal
@@ -35,7 +36,7 @@
 namespace smplb200 {
 
 constexpr int kTcThreads = 192;
-constexpr int kTcAccBufs = 4;                           // TMEM accumulator ring (4 x 64 columns)
+constexpr int kTcAccBufs = 2;                           // TMEM accumulator ring (2 x 128 columns)
 constexpr int kTcAccCols = kTcAccBufs * kCoefBlock;     // 256
 constexpr int kTcTmemCols = 512;
 
@@ -44,18 +45,21 @@ struct BlendTcCfg {
   static constexpr bool kTf32 = PREC == SMPLB200_PREC_TF32;
   static constexpr int kElem = kTf32 ? 4 : 2;
   static constexpr int kParts = PREC == SMPLB200_PREC_BF16X3 ? 2 : 1;   // hi (+ lo) operands
-  static constexpr int kStages = 3;
+  static constexpr int kStages = 3;                                      // ring of K-half stages
   static constexpr int kKSteps = kCoefK * kElem / 32;                    // 14 (bf16) or 28 (tf32)
+  static constexpr int kKHalf = kKSteps / 2;                             // MMA k-steps per stage
   static constexpr int kAColsPart = kCoefK * kElem / 4;                  // TMEM columns: 112 / 224
   static constexpr int kAWords = kAColsPart;                             // 32-bit words per basis row
-  static constexpr uint32_t kBBytesPart = kCoefK * kCoefBlock * kElem;   // one coef image
-  static constexpr uint32_t kBStage = kBBytesPart * kParts;
+  static constexpr uint32_t kBBytesPart = kCoefK * kCoefBlock * kElem;   // one coef image (block)
+  static constexpr uint32_t kBHalf = kBBytesPart / 2;                    // its first / second K half
+  static constexpr uint32_t kBStage = kBHalf * kParts;
   static constexpr uint32_t kBarOffset = kStages * kBStage;
   static constexpr uint32_t kSmemBytes = kBarOffset + 256;
   static constexpr uint32_t kLboB = kCoefBlock * 16, kSbo = 128;
   static constexpr uint32_t kIdesc =
       ptx::make_idesc(kTf32 ? ptx::kFmtTF32 : ptx::kFmtBF16, 128, kCoefBlock);
   static_assert(kTcAccCols + kAColsPart * kParts <= kTcTmemCols, "TMEM budget");
+  static_assert(kKSteps % 2 == 0, "K halves");
 };
 
 template <uint32_t PREC>
@@ -94,17 +98,17 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
   const uint32_t tmem_a = tmem_base + kTcAccCols;   // A operand columns follow the accumulators
 
   if (warp == 0) {
-    // ===== bulk-TMA producer: coef images of the body blocks =====
+    // ===== bulk-TMA producer: coef images of the body blocks, one K half per stage =====
     if (lane == 0) {
-      for (int i = 0; i < nunits; ++i) {
+      for (int i = 0; i < 2 * nunits; ++i) {
         const int s = i % C::kStages;
-        const int blk = (int)((u0 + i) % nblocks);
+        const int blk = (int)((u0 + (i >> 1)) % nblocks);
         ptx::mbar_wait(bar_empty + s, ((i / C::kStages) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(bar_full + s, C::kBStage);
         uint8_t* dst = sB + (size_t)s * C::kBStage;
-        const size_t src = (size_t)blk * C::kBBytesPart;
-        ptx::bulk_g2s(dst, coef_hi + src, C::kBBytesPart, bar_full + s);
-        if (C::kParts == 2) ptx::bulk_g2s(dst + C::kBBytesPart, coef_lo + src, C::kBBytesPart, bar_full + s);
+        const size_t src = (size_t)blk * C::kBBytesPart + (size_t)(i & 1) * C::kBHalf;
+        ptx::bulk_g2s(dst, coef_hi + src, C::kBHalf, bar_full + s);
+        if (C::kParts == 2) ptx::bulk_g2s(dst + C::kBHalf, coef_lo + src, C::kBHalf, bar_full + s);
       }
     }
   } else if (warp == 1) {
@@ -113,7 +117,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
       long long cur_tile = -1;
       uint32_t a_phase = 0;
       for (int i = 0; i < nunits; ++i) {
-        const int s = i % C::kStages, a = i % kTcAccBufs;
+        const int a = i % kTcAccBufs;
         const long long tile = (u0 + i) / nblocks;
         if (tile != cur_tile) {            // wait until the epilogue warps have (re)loaded A
           ptx::mbar_wait(bar_a, a_phase);
@@ -121,25 +125,29 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
           cur_tile = tile;
         }
         ptx::mbar_wait(bar_tempty + a, ((i / kTcAccBufs) & 1) ^ 1);
-        ptx::mbar_wait(bar_full + s, (i / C::kStages) & 1);
-        ptx::tc_fence_after();
-        const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * C::kBStage);
         const uint32_t d_tmem = tmem_base + a * kCoefBlock;
         uint32_t acc = 0;
-        constexpr int kGroups = C::kParts == 2 ? 3 : 1;   // (hi,hi) [, (hi,lo), (lo,hi)]
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-          const uint32_t ap = tmem_a + (g == 2 ? C::kAColsPart : 0);
-          const uint32_t bp = b_addr + (g == 1 ? C::kBBytesPart : 0);
+        for (int kh = 0; kh < 2; ++kh) {
+          const int st = 2 * i + kh, s = st % C::kStages;
+          ptx::mbar_wait(bar_full + s, (st / C::kStages) & 1);
+          ptx::tc_fence_after();
+          const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * C::kBStage);
+          constexpr int kGroups = C::kParts == 2 ? 3 : 1;   // (hi,hi) [, (hi,lo), (lo,hi)]
 #pragma unroll
-          for (int ks = 0; ks < C::kKSteps; ++ks) {
-            const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * C::kLboB, C::kLboB, C::kSbo);
-            if (C::kTf32) ptx::mma_tf32_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
-            else ptx::mma_bf16_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
-            acc = 1;
+          for (int g = 0; g < kGroups; ++g) {
+            const uint32_t ap = tmem_a + (g == 2 ? C::kAColsPart : 0) + kh * C::kKHalf * 8;
+            const uint32_t bp = b_addr + (g == 1 ? C::kBHalf : 0);
+#pragma unroll
+            for (int ks = 0; ks < C::kKHalf; ++ks) {
+              const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * C::kLboB, C::kLboB, C::kSbo);
+              if (C::kTf32) ptx::mma_tf32_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
+              else ptx::mma_bf16_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
+              acc = 1;
+            }
           }
+          ptx::tc_commit(bar_empty + s);   // stage reusable once these MMAs retire
         }
-        ptx::tc_commit(bar_empty + s);   // stage reusable once these MMAs retire
         ptx::tc_commit(bar_tfull + a);   // accumulator ready for the epilogue
       }
     }
@@ -179,23 +187,25 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
       }
       ptx::mbar_wait(bar_tfull + a, (i / kTcAccBufs) & 1);
       ptx::tc_fence_after();
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld32(tmem_base + lane_addr + a * kCoefBlock, r0);
-      ptx::tmem_ld32(tmem_base + lane_addr + a * kCoefBlock + 32, r1);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      if (lane == 0) ptx::mbar_arrive(bar_tempty + a);
-      __syncwarp();
       const long long b0 = (long long)blk * kCoefBlock;
       const int col = (int)tile * 128 + q * 32 + lane;    // planar column owned by this thread
       float* dst = vposed + (size_t)b0 * NC + col;
       const int nb = (int)min((long long)kCoefBlock, n - b0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < nb) dst[(size_t)j * NC] = __uint_as_float(r0[j]);
+      for (int c = 0; c < kCoefBlock / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_base + lane_addr + a * kCoefBlock + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (c == kCoefBlock / 32 - 1) {       // accumulator fully in registers: hand it back
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_tempty + a);
+          __syncwarp();
+        }
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j + 32 < nb) dst[(size_t)(j + 32) * NC] = __uint_as_float(r1[j]);
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < nb) dst[(size_t)(c * 32 + j) * NC] = __uint_as_float(r[j]);
+      }
     }
   }
   ptx::tc_fence_before();

@@ -65,7 +65,7 @@ __device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
 }
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(uint32_t(h) << 16); }
 
-constexpr int kCoefBlock = 64;   // bodies per tensor-core coefficient image (MMA N)
+constexpr int kCoefBlock = 128;   // bodies per tensor-core coefficient image (MMA N)
 constexpr int kLbsBlock = 8;     // bodies per LBS blend image (MMA N = 12 * 8 = 96)
 constexpr int kLbsK = 48;        // blend contraction: [A_hi | A_lo] over 24 joints (tf32 split)
 
