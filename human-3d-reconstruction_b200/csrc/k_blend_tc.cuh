@@ -21,8 +21,11 @@
 // contiguous ranges, tile-major, so every CTA does the same amount of work (no wave
 // quantisation) and switches basis tile at most a few times.
 //
-// Warp roles (192 threads): warp 0 = bulk-TMA producer, warp 1 = single-thread MMA issuer,
-// warps 2..5 = epilogue + basis loader (TMEM lane quarter = warp % 4).
+// Warp roles (192 threads): warps 0..3 = epilogue + basis loader (TMEM lane quarter = warp),
+// warp 4 = bulk-TMA producer, warp 5 = single-thread MMA issuer.  The MMA warp has the HIGHEST
+// warp id on its scheduler and every other role waits with nanosleep back-off: the issuing thread
+// needs ~50 issue slots per tcgen05.mma, and spin-polling neighbours starved it (round-1 ncu:
+// tensor pipe idle 67% with both sides of the TMEM ring waiting on each other).
 //
 // Precisions (operands; accumulation is always fp32 in TMEM):
 //   BF16    1 MMA group   hi*hi
@@ -84,26 +87,27 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
   const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
   const int nunits = (int)(u1 - u0);
 
-  if (warp == 0 && lane == 0) {
+  constexpr int kWarpTma = 4, kWarpMma = 5;
+  if (warp == kWarpTma && lane == 0) {
     ptx::mbar_init(bar_a, 4);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 1); }
     for (int a = 0; a < kTcAccBufs; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, kTcTmemCols);
+  if (warp == kWarpMma) ptx::tmem_alloc(tmem_slot, kTcTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_a = tmem_base + kTcAccCols;   // A operand columns follow the accumulators
 
-  if (warp == 0) {
+  if (warp == kWarpTma) {
     // ===== bulk-TMA producer: coef images of the body blocks, one K half per stage =====
     if (lane == 0) {
       for (int i = 0; i < 2 * nunits; ++i) {
         const int s = i % C::kStages;
         const int blk = (int)((u0 + (i >> 1)) % nblocks);
-        ptx::mbar_wait(bar_empty + s, ((i / C::kStages) & 1) ^ 1);
+        ptx::mbar_wait_relaxed(bar_empty + s, ((i / C::kStages) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(bar_full + s, C::kBStage);
         uint8_t* dst = sB + (size_t)s * C::kBStage;
         const size_t src = (size_t)blk * C::kBBytesPart + (size_t)(i & 1) * C::kBHalf;
@@ -111,7 +115,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
         if (C::kParts == 2) ptx::bulk_g2s(dst + C::kBHalf, coef_lo + src, C::kBHalf, bar_full + s);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       long long cur_tile = -1;
@@ -153,7 +157,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
     }
   } else {
     // ===== epilogue + basis loader =====
-    const int q = warp & 3;                               // TMEM lane quarter of this warp
+    const int q = warp;                                   // TMEM lane quarter of this warp
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long long cur_tile = -1;
     for (int i = 0; i < nunits; ++i) {
@@ -185,7 +189,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
         if (lane == 0) ptx::mbar_arrive(bar_a);
         __syncwarp();
       }
-      ptx::mbar_wait(bar_tfull + a, (i / kTcAccBufs) & 1);
+      ptx::mbar_wait_relaxed(bar_tfull + a, (i / kTcAccBufs) & 1);
       ptx::tc_fence_after();
       const long long b0 = (long long)blk * kCoefBlock;
       const int col = (int)tile * 128 + q * 32 + lane;    // planar column owned by this thread
@@ -210,7 +214,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTcTmemCols);
+  if (warp == kWarpMma) ptx::tmem_dealloc(tmem_base, kTcTmemCols);
 }
 
 // fp32 coef [n,224] -> operand images (stand-alone k1 entry point only; the fused forward has

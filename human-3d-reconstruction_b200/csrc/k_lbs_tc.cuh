@@ -31,7 +31,8 @@
 
 namespace smplb200 {
 
-constexpr int kLbsTcThreads = 192;                       // TMA warp, MMA warp, 4 epilogue warps
+constexpr int kLbsTcThreads = 192;                       // 4 epilogue warps, TMA warp, MMA warp
+constexpr int kLbsWarpTma = 4, kLbsWarpMma = 5;           // MMA issuer = highest warp id (see k_blend_tc.cuh)
 constexpr int kLbsTcStages = 3;
 constexpr int kLbsTcAcc = 2;
 constexpr int kLbsN = kLbsBlock * 12;                    // 96
@@ -71,7 +72,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   const int blk_end = min(nblocks, blk_begin + blocks_per_cta);
   const int nblk = blk_end - blk_begin;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kLbsWarpTma && lane == 0) {
     ptx::mbar_init(bar_w, 4);
     for (int s = 0; s < kLbsTcStages; ++s) {
       ptx::mbar_init(bar_bfull + s, 1); ptx::mbar_init(bar_bempty + s, 1);
@@ -80,26 +81,26 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
     for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, kLbsTmemCols);
+  if (warp == kLbsWarpMma) ptx::tmem_alloc(tmem_slot, kLbsTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_w = tmem_base + kLbsAccCols;
 
-  if (warp == 0) {
+  if (warp == kLbsWarpTma) {
     // ===== bulk-TMA producer: A' image + the block's vposed rows (512 B per body and plane) =====
     if (lane == 0) {
       for (int i = 0; i < nblk; ++i) {
         const int s = i % kLbsTcStages;
         const uint32_t par = ((i / kLbsTcStages) & 1) ^ 1;
         const int blk = blk_begin + i;
-        ptx::mbar_wait(bar_bempty + s, par);
+        ptx::mbar_wait_relaxed(bar_bempty + s, par);
         ptx::mbar_arrive_expect_tx(bar_bfull + s, kLbsBStage);
         ptx::bulk_g2s(sB + (size_t)s * kLbsBStage, a_img + (size_t)blk * kLbsBStage, kLbsBStage, bar_bfull + s);
         const long long b0 = (long long)blk * kLbsBlock;
         const int nb = (int)min((long long)kLbsBlock, n - b0);
-        ptx::mbar_wait(bar_vempty + s, par);
+        ptx::mbar_wait_relaxed(bar_vempty + s, par);
         ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nb * 3 * kLbsVRow);
         const float* src = vposed + (size_t)b0 * 3 * VP + (size_t)tile * 128;
         uint8_t* dst = sV + (size_t)s * kLbsVStage;
@@ -107,7 +108,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
           ptx::bulk_g2s(dst + (size_t)r * kLbsVRow, src + (size_t)r * VP, kLbsVRow, bar_vfull + s);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kLbsWarpMma) {
     // ===== MMA issuer =====
     if (lane == 0 && nblk > 0) {
       constexpr uint32_t kLboB = kLbsN * 16, kSbo = 128;
@@ -138,8 +139,8 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
     }
   } else {
     // ===== epilogue (4 warps, TMEM lane quarter q) =====
-    const int q = warp & 3;
-    const int ew = warp - 2;
+    const int q = warp;
+    const int ew = warp;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int v_local = q * 32 + lane;
     const int warp_v0 = tile * 128 + q * 32;
@@ -169,8 +170,8 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
       const int nb = (int)min((long long)kLbsBlock, n - b0);
       const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
-      ptx::mbar_wait(bar_vfull + s, (i / kLbsTcStages) & 1);
-      ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
+      ptx::mbar_wait_relaxed(bar_vfull + s, (i / kLbsTcStages) & 1);
+      ptx::mbar_wait_relaxed(bar_tfull + a, (i / kLbsTcAcc) & 1);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN;
 #pragma unroll
@@ -221,7 +222,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
     if (tile == 0 && kp2d != nullptr) {
       const long long bb0 = (long long)blk_begin * kLbsBlock;
       const long long bb1 = min(n, (long long)blk_end * kLbsBlock);
-      for (long long i = bb0 * (kJ * 2) + ((int)threadIdx.x - 64); i < bb1 * (kJ * 2); i += 128) {
+      for (long long i = bb0 * (kJ * 2) + (int)threadIdx.x; i < bb1 * (kJ * 2); i += 128) {
         const long long b = i / (kJ * 2);
         const int r = int(i - b * (kJ * 2)), j = r >> 1, c = r & 1;
         const float sc = __ldg(cam + b * 3), tt = __ldg(cam + b * 3 + 1 + c);
@@ -231,7 +232,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, kLbsTmemCols);
+  if (warp == kLbsWarpMma) ptx::tmem_dealloc(tmem_base, kLbsTmemCols);
 }
 
 // fp32 A [n,24,12] -> tf32 hi|lo operand image (stand-alone k3 entry point only).
