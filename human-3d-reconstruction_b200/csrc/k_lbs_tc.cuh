@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kLbsTcThreads, 2)
 k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
          const float* __restrict__ vposed, long long n, int nblocks, int blocks_per_cta,
          int V, int VP, float* __restrict__ verts, const float* __restrict__ joints_in,
-         const float* __restrict__ cam, float* __restrict__ kp2d) {
+         const float* __restrict__ cam, float* __restrict__ kp2d, int tune) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sV = smem + kLbsVOff;
@@ -95,12 +95,12 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         const int s = i % kLbsTcStages;
         const uint32_t par = ((i / kLbsTcStages) & 1) ^ 1;
         const int blk = blk_begin + i;
-        ptx::mbar_wait_relaxed(bar_bempty + s, par);
+        ptx::mbar_wait_relaxed(bar_bempty + s, par, tune & 2);
         ptx::mbar_arrive_expect_tx(bar_bfull + s, kLbsBStage);
         ptx::bulk_g2s(sB + (size_t)s * kLbsBStage, a_img + (size_t)blk * kLbsBStage, kLbsBStage, bar_bfull + s);
         const long long b0 = (long long)blk * kLbsBlock;
         const int nb = (int)min((long long)kLbsBlock, n - b0);
-        ptx::mbar_wait_relaxed(bar_vempty + s, par);
+        ptx::mbar_wait_relaxed(bar_vempty + s, par, tune & 2);
         ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nb * 3 * kLbsVRow);
         const float* src = vposed + (size_t)b0 * 3 * VP + (size_t)tile * 128;
         uint8_t* dst = sV + (size_t)s * kLbsVStage;
@@ -170,8 +170,8 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
       const int nb = (int)min((long long)kLbsBlock, n - b0);
       const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
-      ptx::mbar_wait_relaxed(bar_vfull + s, (i / kLbsTcStages) & 1);
-      ptx::mbar_wait_relaxed(bar_tfull + a, (i / kLbsTcAcc) & 1);
+      ptx::mbar_wait_relaxed(bar_vfull + s, (i / kLbsTcStages) & 1, tune & 1);
+      ptx::mbar_wait_relaxed(bar_tfull + a, (i / kLbsTcAcc) & 1, tune & 1);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN;
 #pragma unroll
@@ -279,7 +279,7 @@ inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float*
   const dim3 grid((unsigned)vtiles, (unsigned)((nblocks + bpc - 1) / bpc));
   k_lbs_tc<<<grid, kLbsTcThreads, kLbsSmemBytes, s>>>(
       m.w_tf32, reinterpret_cast<const uint8_t*>(a_img), vposed, n, nblocks, bpc, m.V, m.VP, verts,
-      joints_in, cam, kp2d);
+      joints_in, cam, kp2d, m.tune);
   return cudaGetLastError();
 }
 

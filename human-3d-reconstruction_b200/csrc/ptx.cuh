@@ -62,7 +62,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, bool relaxed = true) {
+  if (!relaxed) { mbar_wait(bar, parity); return; }
   if (mbar_try_wait(bar, parity)) return;
   unsigned long long t0 = 0;
   for (uint32_t it = 1;; ++it) {

@@ -435,6 +435,10 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     DeviceModel& d = m->d;
     d.V = V; d.VP = VP; d.NB = NB; d.KB = KB; d.NC = NC;
     d.max_nnz = max_nnz; d.max_depth = max_depth; d.jreg_nnz = (int)jval.size();
+    {  // experiment knob, read once per handle (default: producer backs off, epilogue polls tight)
+      const char* t = std::getenv("SMPLB200_TUNE");
+      d.tune = t ? std::atoi(t) : 2;
+    }
     d.basis = reinterpret_cast<const float*>(base + o_basis);
     d.j_template = reinterpret_cast<const float*>(base + o_jt);
     d.j_shapedirs = reinterpret_cast<const float*>(base + o_jsd);
