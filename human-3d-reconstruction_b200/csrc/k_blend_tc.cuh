@@ -21,11 +21,9 @@
 // contiguous ranges, tile-major, so every CTA does the same amount of work (no wave
 // quantisation) and switches basis tile at most a few times.
 //
-// Warp roles (192 threads): warps 0..3 = epilogue + basis loader (TMEM lane quarter = warp),
-// warp 4 = bulk-TMA producer, warp 5 = single-thread MMA issuer.  The MMA warp has the HIGHEST
-// warp id on its scheduler and every other role waits with nanosleep back-off: the issuing thread
-// needs ~50 issue slots per tcgen05.mma, and spin-polling neighbours starved it (round-1 ncu:
-// tensor pipe idle 67% with both sides of the TMEM ring waiting on each other).
+// Warp roles (192 threads): warp 0 = bulk-TMA producer, warp 1 = single-thread MMA issuer,
+// warps 2..5 = epilogue + basis loader (TMEM lane quarter = warp % 4).  All mbarrier waits use
+// try_wait with a suspend-time hint (hardware sleep, no issue-slot polling).
 //
 // Precisions (operands; accumulation is always fp32 in TMEM):
 //   BF16    1 MMA group   hi*hi
@@ -88,7 +86,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
   const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
   const int nunits = (int)(u1 - u0);
 
-  constexpr int kWarpTma = 4, kWarpMma = 5;
+  constexpr int kWarpTma = 0, kWarpMma = 1;
   if (warp == kWarpTma && lane == 0) {
     ptx::mbar_init(bar_a, 4);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 1); }
@@ -158,7 +156,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
     }
   } else {
     // ===== epilogue + basis loader =====
-    const int q = warp;                                   // TMEM lane quarter of this warp
+    const int q = warp & 3;                               // TMEM lane quarter of this warp
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     long long cur_tile = -1;
     for (int i = 0; i < nunits; ++i) {
@@ -194,22 +192,38 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
       ptx::tc_fence_after();
       const long long b0 = (long long)blk * kCoefBlock;
       const int col = (int)tile * 128 + q * 32 + lane;    // planar column owned by this thread
-      float* dst = vposed + (size_t)b0 * NC + col;
       const int nb = (int)min((long long)kCoefBlock, n - b0);
+      // whole accumulator -> registers, then hand the TMEM buffer straight back to the MMA warp
+      uint32_t r[kCoefBlock];
 #pragma unroll
-      for (int c = 0; c < kCoefBlock / 32; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld32(tmem_base + lane_addr + a * kCoefBlock + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c == kCoefBlock / 32 - 1) {       // accumulator fully in registers: hand it back
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_tempty + a);
-          __syncwarp();
+      for (int c = 0; c < kCoefBlock / 32; ++c)
+        ptx::tmem_ld32(tmem_base + lane_addr + a * kCoefBlock + c * 32,
+                       *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar_tempty + a);
+      __syncwarp();
+      // one coalesced 128-byte store per body row; four independent pointer chains, no predicates
+      // on the full-block fast path (the naive indexed form cost ~18 SASS instructions per store)
+      const size_t ld = (size_t)NC;
+      float* p0 = vposed + (size_t)b0 * ld + col;
+      if (nb == kCoefBlock) {
+        float* p1 = p0 + ld; float* p2 = p1 + ld; float* p3 = p2 + ld;
+        const size_t ld4 = 4 * ld;
+#pragma unroll
+        for (int j = 0; j < kCoefBlock; j += 4) {
+          *p0 = __uint_as_float(r[j]);     p0 += ld4;
+          *p1 = __uint_as_float(r[j + 1]); p1 += ld4;
+          *p2 = __uint_as_float(r[j + 2]); p2 += ld4;
+          *p3 = __uint_as_float(r[j + 3]); p3 += ld4;
         }
+      } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < nb) dst[(size_t)(c * 32 + j) * NC] = __uint_as_float(r[j]);
+        for (int j = 0; j < kCoefBlock; ++j) {
+          if (j < nb) *p0 = __uint_as_float(r[j]);
+          p0 += ld;
+        }
       }
     }
   }

@@ -33,49 +33,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase flips (or the
+// hint expires) instead of spinning.  A spinning waiter steals issue slots from the warp it is
+// waiting for when both share a scheduler (round-1 ncu: ~180 try_wait retries per unit on the MMA
+// thread while the epilogue warp on its scheduler crawled); wake-up after arrive is ~60 clk.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
   return ok != 0;
 }
-// Bounded waits: a protocol bug must fault the launch, never hang the GPU.
-// mbar_wait       -- tight poll, for the latency-critical MMA-issuing thread.
-// mbar_wait_relaxed -- polls with nanosleep back-off, for producer / epilogue warps: a spinning
-//                    warp competes for issue slots with the single MMA-issuing warp on its
-//                    scheduler (the arbiter favours higher warp ids), which starves the tensor pipe.
+// Bounded wait: a protocol bug must fault the launch, never hang the GPU (~2 s).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  unsigned long long t0 = 0;
-  for (uint32_t it = 1;; ++it) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((it & 0xfffu) == 0) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t0 == 0) t0 = t1;
-      else if (t1 - t0 > 2000000000ull) __trap();  // 2 s
-    }
-  }
+  for (uint32_t it = 0; it < 2000u; ++it)
+    if (mbar_try_wait(bar, parity, 1000000u)) return;   // up to 1 ms asleep per attempt
+  __trap();
 }
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, bool relaxed = true) {
-  if (!relaxed) { mbar_wait(bar, parity); return; }
-  if (mbar_try_wait(bar, parity)) return;
-  unsigned long long t0 = 0;
-  for (uint32_t it = 1;; ++it) {
-    __nanosleep(40);
-    if (mbar_try_wait(bar, parity)) return;
-    if ((it & 0x3ffu) == 0) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t0 == 0) t0 = t1;
-      else if (t1 - t0 > 2000000000ull) __trap();  // 2 s
-    }
-  }
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, bool = true) {
+  mbar_wait(bar, parity);
 }
 
 // ---- bulk TMA: global -> shared, completion counted on an mbarrier --------------------------
