@@ -170,6 +170,9 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
       const int nb = (int)min((long long)kLbsBlock, n - b0);
       const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
+      const bool full = (nb == kLbsBlock) && (nf == 96);
+      const size_t body_stride = (size_t)V * 3;
+      float* dst = verts + ((size_t)b0 * V + warp_v0) * 3 + lane;
       ptx::mbar_wait_relaxed(bar_vfull + s, (i / kLbsTcStages) & 1, tune & 1);
       ptx::mbar_wait_relaxed(bar_tfull + a, (i / kLbsTcAcc) & 1, tune & 1);
       ptx::tc_fence_after();
@@ -209,12 +212,14 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
           __syncwarp();
           so[3 * lane] = ox; so[3 * lane + 1] = oy; so[3 * lane + 2] = oz;
           __syncwarp();
-          if (bi < nb) {
-            float* dst = verts + ((size_t)(b0 + bi) * V + warp_v0) * 3;
+          if (full) {            // fast path: whole block, whole warp -> three unpredicated stores
+            dst[0] = so[lane]; dst[32] = so[lane + 32]; dst[64] = so[lane + 64];
+          } else if (bi < nb) {
 #pragma unroll
             for (int k = 0; k < 3; ++k)
-              if (lane + 32 * k < nf) dst[lane + 32 * k] = so[lane + 32 * k];
+              if (lane + 32 * k < nf) dst[32 * k] = so[lane + 32 * k];
           }
+          dst += body_stride;
         }
       }
     }

@@ -27,6 +27,7 @@ struct SmplB200Model {
   DeviceModel d;
   int device = 0;
   int num_sms = 0;
+  int chunk = 0;        // bodies per k1->k3 pass (tensor-core paths); 0 = whole batch in one pass
   void* blob = nullptr;
   size_t blob_bytes = 0;
 };
@@ -34,6 +35,8 @@ struct SmplB200Model {
 namespace {
 
 thread_local int tl_last_cuda_error = 0;
+
+constexpr int kDefaultChunk = 0;
 
 inline int cuda_fail(cudaError_t e) {
   tl_last_cuda_error = (int)e;
@@ -145,7 +148,9 @@ Workspace carve(const SmplB200Model* m, long long n, const Plan& p) {
   const size_t nn = (size_t)std::max<long long>(n, 1);
   w.coef = take(nn * kCoefK * sizeof(float));
   w.A = take(nn * kJ * 12 * sizeof(float));
-  w.vposed = take(nn * 3 * (size_t)m->d.VP * sizeof(float));
+  const bool chunked = m->chunk > 0 && p.prec != SMPLB200_PREC_FP32 && p.lbs == SMPLB200_LBS_TC &&
+                       nn > (size_t)m->chunk;
+  w.vposed = take((chunked ? (size_t)m->chunk : nn) * 3 * (size_t)m->d.VP * sizeof(float));
   w.joints = take(nn * kJ * 3 * sizeof(float));
   const size_t coef_blocks = (nn + kCoefBlock - 1) / kCoefBlock;
   const size_t lbs_blocks = (nn + kLbsBlock - 1) / kLbsBlock;
@@ -435,9 +440,11 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     DeviceModel& d = m->d;
     d.V = V; d.VP = VP; d.NB = NB; d.KB = KB; d.NC = NC;
     d.max_nnz = max_nnz; d.max_depth = max_depth; d.jreg_nnz = (int)jval.size();
-    {  // experiment knob, read once per handle (default: producer backs off, epilogue polls tight)
-      const char* t = std::getenv("SMPLB200_TUNE");
-      d.tune = t ? std::atoi(t) : 2;
+    d.tune = 0;
+    {  // bodies per k1->k3 pass: keeps the vposed intermediate L2-resident (multiple of 128)
+      const char* t = std::getenv("SMPLB200_CHUNK");
+      int c = t ? std::atoi(t) : kDefaultChunk;
+      m->chunk = c <= 0 ? 0 : (c + kCoefBlock - 1) / kCoefBlock * kCoefBlock;
     }
     d.basis = reinterpret_cast<const float*>(base + o_basis);
     d.j_template = reinterpret_cast<const float*>(base + o_jt);
@@ -489,7 +496,10 @@ int smplb200_forward_launch_count(const SmplB200Model* model, int64_t n, uint32_
   Plan p;
   if (!model || n <= 0 || !resolve_plan(model, n, flags, &p)) return 0;
   (void)with_projection;
-  return 3 + (p.regressed ? 1 : 0);
+  const bool chunked = model->chunk > 0 && p.prec != SMPLB200_PREC_FP32 && p.lbs == SMPLB200_LBS_TC &&
+                       n > model->chunk;
+  const int passes = chunked ? (int)((n + model->chunk - 1) / model->chunk) : 1;
+  return 1 + 2 * passes + (p.regressed ? 1 : 0);
 }
 
 int smplb200_pose_chain(const SmplB200Model* model, const float* betas, const float* pose,
@@ -614,6 +624,29 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
   int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
   if (st) return st;
 
+  const bool proj_in_lbs = (kp2d != nullptr) && !p.regressed;
+  const bool chunked = model->chunk > 0 && p.prec != SMPLB200_PREC_FP32 && p.lbs == SMPLB200_LBS_TC &&
+                       n > model->chunk;
+  if (chunked) {
+    // k1 -> k3 per chunk of bodies: the planar vposed scratch (chunk * 83 KB) is written by k1 and
+    // consumed by k3 while still L2-resident, so it costs L2 bandwidth but (mostly) no HBM traffic.
+    const long long C = model->chunk;   // multiple of kCoefBlock (128) and kLbsBlock (8)
+    const int V = model->d.V;
+    for (long long c0 = 0; c0 < n; c0 += C) {
+      const long long nc = std::min<long long>(C, n - c0);
+      const size_t cb = (size_t)(c0 / kCoefBlock) * kCoefBlock * kCoefK;   // elements into coef images
+      CU_TRY(launch_blend_tc(model->d, model->num_sms, p.prec,
+                             out.coef_bf16_hi ? out.coef_bf16_hi + cb : nullptr,
+                             out.coef_bf16_lo ? out.coef_bf16_lo + cb : nullptr,
+                             out.coef_tf32 ? out.coef_tf32 + cb : nullptr, nc, vposed, s));
+      const size_t ab = (size_t)(c0 / kLbsBlock) * kLbsBlock * 12 * kLbsK;  // elements into A' images
+      CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, out.a_tf32 + ab, nc,
+                           vertices + (size_t)c0 * V * 3,
+                           proj_in_lbs ? jbuf + (size_t)c0 * kJ * 3 : nullptr,
+                           proj_in_lbs ? cam + (size_t)c0 * 3 : nullptr,
+                           proj_in_lbs ? kp2d + (size_t)c0 * kJ * 2 : nullptr, s));
+    }
+  } else {
   // k1
   if (p.prec == SMPLB200_PREC_FP32)
     st = launch_blend_fma(model, coef, n, vposed, s);
@@ -623,7 +656,6 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
   if (st) return st;
 
   // k3 (+k4 when joints are kinematic)
-  const bool proj_in_lbs = (kp2d != nullptr) && !p.regressed;
   if (p.lbs == SMPLB200_LBS_TC)
     CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, out.a_tf32, n, vertices,
                          proj_in_lbs ? jbuf : nullptr, proj_in_lbs ? cam : nullptr,
@@ -633,6 +665,7 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
                         proj_in_lbs ? jbuf : nullptr, proj_in_lbs ? cam : nullptr,
                         proj_in_lbs ? kp2d : nullptr, s);
   if (st) return st;
+  }
 
   if (p.regressed && (joints || kp2d)) st = launch_regress(model, vertices, n, jbuf, cam, kp2d, s);
   return st;
