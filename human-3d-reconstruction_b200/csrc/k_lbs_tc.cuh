@@ -43,7 +43,7 @@ constexpr uint32_t kLbsVRow = 128 * 4;                   // one (body, plane) ro
 constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 12,288
 constexpr uint32_t kLbsVOff = kLbsTcStages * kLbsBStage;
 constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsTcStages * kLbsVStage;
-constexpr uint32_t kLbsBarOff = kLbsOutOff + 4 * 96 * 4;
+constexpr uint32_t kLbsBarOff = kLbsOutOff + 4 * 4 * 96 * 4;   // 4 warps x 4 bodies x 96 floats
 constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~95 KB -> two CTAs per SM
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
@@ -145,7 +145,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
     const int v_local = q * 32 + lane;
     const int warp_v0 = tile * 128 + q * 32;
     const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
-    float* so = sOut + ew * 96;
+    float* so = sOut + ew * (4 * 96);
     if (nblk > 0) {
       // W' rows of this vertex tile -> TMEM (A operand of every blend MMA of this CTA)
       const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + v_local) * kLbsK);
@@ -201,26 +201,44 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         for (int e = 0; e < 16; ++e) {
           T[e] = __uint_as_float(r0[e]); T[16 + e] = __uint_as_float(r1[e]); T[32 + e] = __uint_as_float(r2[e]);
         }
+        // four bodies per round: all FMAs, then ONE shared-memory transpose (xyz interleave) and
+        // twelve independent coalesced stores, so the STS -> LDS -> STG latency chain is paid once
+        // per round instead of once per body.
+        __syncwarp();
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
-          const int bi = half * 4 + bb;
           const float* t = T + bb * 12;
           const float x = px[bb], y = py[bb], z = pz[bb];
-          const float ox = fmaf(t[2], z, fmaf(t[1], y, fmaf(t[0], x, t[3])));
-          const float oy = fmaf(t[6], z, fmaf(t[5], y, fmaf(t[4], x, t[7])));
-          const float oz = fmaf(t[10], z, fmaf(t[9], y, fmaf(t[8], x, t[11])));
-          __syncwarp();
-          so[3 * lane] = ox; so[3 * lane + 1] = oy; so[3 * lane + 2] = oz;
-          __syncwarp();
-          if (full) {            // fast path: whole block, whole warp -> three unpredicated stores
-            dst[0] = so[lane]; dst[32] = so[lane + 32]; dst[64] = so[lane + 64];
-          } else if (bi < nb) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-              if (lane + 32 * k < nf) dst[32 * k] = so[lane + 32 * k];
-          }
-          dst += body_stride;
+          float* sb = so + bb * 96 + 3 * lane;
+          sb[0] = fmaf(t[2], z, fmaf(t[1], y, fmaf(t[0], x, t[3])));
+          sb[1] = fmaf(t[6], z, fmaf(t[5], y, fmaf(t[4], x, t[7])));
+          sb[2] = fmaf(t[10], z, fmaf(t[9], y, fmaf(t[8], x, t[11])));
         }
+        __syncwarp();
+        if (full) {            // fast path: whole block, whole warp -> unpredicated stores
+          float o[12];
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            o[3 * bb] = so[bb * 96 + lane]; o[3 * bb + 1] = so[bb * 96 + lane + 32];
+            o[3 * bb + 2] = so[bb * 96 + lane + 64];
+          }
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            float* d = dst + bb * body_stride;
+            d[0] = o[3 * bb]; d[32] = o[3 * bb + 1]; d[64] = o[3 * bb + 2];
+          }
+        } else {
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            if (half * 4 + bb < nb) {
+              float* d = dst + bb * body_stride;
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                if (lane + 32 * k < nf) d[32 * k] = so[bb * 96 + lane + 32 * k];
+            }
+          }
+        }
+        dst += 4 * body_stride;
       }
     }
     // k4: weak-perspective projection of this CTA's bodies (CTAs of vertex tile 0 only)
