@@ -15,8 +15,9 @@
 // the same order as an fp32 FMA chain.  W' = [W_hi | W_lo] rows of a 128-vertex tile are RESIDENT
 // IN TENSOR MEMORY as the MMA A operand (no shared-memory re-reads); A' = [A_hi | A_lo] per
 // 8-body block (written by k2) is the B operand.  Both A' and the block's planar vposed rows
-// (512 B per body and plane) stream through 3-stage bulk-TMA / mbarrier rings, so ~90 KB of loads
-// are in flight per SM without holding registers; two ~95 KB CTAs share an SM so one CTA's
+// (512 B per body and plane) stream through bulk-TMA / mbarrier rings with their own producer
+// warps (A': 2 stages from L2; vposed: 5 stages from HBM), so ~120 KB of loads are in flight per SM
+// without holding registers; two ~105 KB CTAs share an SM so one CTA's
 // prologue/tail hides behind the other's steady state.  The grid is vertex-tile-fastest: the
 // CTAs resident at one time read and write adjacent row chunks of the same bodies (DRAM pages).
 //
@@ -31,9 +32,10 @@
 
 namespace smplb200 {
 
-constexpr int kLbsTcThreads = 192;                       // 4 epilogue warps, TMA warp, MMA warp
-constexpr int kLbsWarpTma = 4, kLbsWarpMma = 5;           // MMA issuer = highest warp id (see k_blend_tc.cuh)
-constexpr int kLbsTcStages = 3;
+constexpr int kLbsTcThreads = 224;                       // vposed TMA, MMA, 4 epilogue, A' TMA warps
+constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 6;   // epilogue = warps 2..5
+constexpr int kLbsBStages = 2;                           // A' images come from L2: shallow ring
+constexpr int kLbsVStages = 5;                           // vposed rows come from HBM: deep ring
 constexpr int kLbsTcAcc = 2;
 constexpr int kLbsN = kLbsBlock * 12;                    // 96
 constexpr int kLbsTmemCols = 256;                        // 2 x 96 accumulators + 48 columns of W'
@@ -41,10 +43,10 @@ constexpr int kLbsAccCols = kLbsTcAcc * kLbsN;           // 192
 constexpr uint32_t kLbsBStage = kLbsK * kLbsN * 4;       // 18,432  tf32 hi|lo image of A, one block
 constexpr uint32_t kLbsVRow = 128 * 4;                   // one (body, plane) row of the vertex tile
 constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 12,288
-constexpr uint32_t kLbsVOff = kLbsTcStages * kLbsBStage;
-constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsTcStages * kLbsVStage;
+constexpr uint32_t kLbsVOff = kLbsBStages * kLbsBStage;
+constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsVStages * kLbsVStage;
 constexpr uint32_t kLbsBarOff = kLbsOutOff + 4 * 4 * 96 * 4;   // 4 warps x 4 bodies x 96 floats
-constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~95 KB -> two CTAs per SM
+constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~105 KB -> two CTAs per SM
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
 __global__ void __launch_bounds__(kLbsTcThreads, 2)
@@ -58,11 +60,11 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   float* sOut = reinterpret_cast<float*>(smem + kLbsOutOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLbsBarOff);
   uint64_t* bar_w = bars;                            // W' rows resident in TMEM (4 warp arrivals)
-  uint64_t* bar_bfull = bars + 1;                    // [stages] A' image landed
-  uint64_t* bar_bempty = bar_bfull + kLbsTcStages;   // [stages] MMAs reading it retired
-  uint64_t* bar_vfull = bar_bempty + kLbsTcStages;   // [stages] vposed rows landed
-  uint64_t* bar_vempty = bar_vfull + kLbsTcStages;   // [stages] epilogue warps done with them (4)
-  uint64_t* bar_tfull = bar_vempty + kLbsTcStages;   // [acc] accumulator ready
+  uint64_t* bar_bfull = bars + 1;                    // [B stages] A' image landed
+  uint64_t* bar_bempty = bar_bfull + kLbsBStages;    // [B stages] MMAs reading it retired
+  uint64_t* bar_vfull = bar_bempty + kLbsBStages;    // [V stages] vposed rows landed
+  uint64_t* bar_vempty = bar_vfull + kLbsVStages;    // [V stages] epilogue warps done with them (4)
+  uint64_t* bar_tfull = bar_vempty + kLbsVStages;    // [acc] accumulator ready
   uint64_t* bar_tempty = bar_tfull + kLbsTcAcc;      // [acc] accumulator drained (4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + kLbsTcAcc);
 
@@ -72,12 +74,10 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   const int blk_end = min(nblocks, blk_begin + blocks_per_cta);
   const int nblk = blk_end - blk_begin;
 
-  if (warp == kLbsWarpTma && lane == 0) {
+  if (warp == kLbsWarpTmaV && lane == 0) {
     ptx::mbar_init(bar_w, 4);
-    for (int s = 0; s < kLbsTcStages; ++s) {
-      ptx::mbar_init(bar_bfull + s, 1); ptx::mbar_init(bar_bempty + s, 1);
-      ptx::mbar_init(bar_vfull + s, 1); ptx::mbar_init(bar_vempty + s, 4);
-    }
+    for (int s = 0; s < kLbsBStages; ++s) { ptx::mbar_init(bar_bfull + s, 1); ptx::mbar_init(bar_bempty + s, 1); }
+    for (int s = 0; s < kLbsVStages; ++s) { ptx::mbar_init(bar_vfull + s, 1); ptx::mbar_init(bar_vempty + s, 4); }
     for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4); }
     ptx::fence_barrier_init();
   }
@@ -88,24 +88,30 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_w = tmem_base + kLbsAccCols;
 
-  if (warp == kLbsWarpTma) {
-    // ===== bulk-TMA producer: A' image + the block's vposed rows (512 B per body and plane) =====
+  if (warp == kLbsWarpTmaV) {
+    // ===== bulk-TMA producer 1: the block's vposed rows (512 B per body and plane), from HBM =====
     if (lane == 0) {
       for (int i = 0; i < nblk; ++i) {
-        const int s = i % kLbsTcStages;
-        const uint32_t par = ((i / kLbsTcStages) & 1) ^ 1;
-        const int blk = blk_begin + i;
-        ptx::mbar_wait_relaxed(bar_bempty + s, par, tune & 2);
-        ptx::mbar_arrive_expect_tx(bar_bfull + s, kLbsBStage);
-        ptx::bulk_g2s(sB + (size_t)s * kLbsBStage, a_img + (size_t)blk * kLbsBStage, kLbsBStage, bar_bfull + s);
-        const long long b0 = (long long)blk * kLbsBlock;
+        const int s = i % kLbsVStages;
+        const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
         const int nb = (int)min((long long)kLbsBlock, n - b0);
-        ptx::mbar_wait_relaxed(bar_vempty + s, par, tune & 2);
+        ptx::mbar_wait(bar_vempty + s, ((i / kLbsVStages) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nb * 3 * kLbsVRow);
         const float* src = vposed + (size_t)b0 * 3 * VP + (size_t)tile * 128;
         uint8_t* dst = sV + (size_t)s * kLbsVStage;
         for (int r = 0; r < nb * 3; ++r)
           ptx::bulk_g2s(dst + (size_t)r * kLbsVRow, src + (size_t)r * VP, kLbsVRow, bar_vfull + s);
+      }
+    }
+  } else if (warp == kLbsWarpTmaB) {
+    // ===== bulk-TMA producer 2: tf32 hi|lo image of the block's joint transforms (L2-resident) =====
+    if (lane == 0) {
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % kLbsBStages;
+        ptx::mbar_wait(bar_bempty + s, ((i / kLbsBStages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar_bfull + s, kLbsBStage);
+        ptx::bulk_g2s(sB + (size_t)s * kLbsBStage, a_img + (size_t)(blk_begin + i) * kLbsBStage, kLbsBStage,
+                      bar_bfull + s);
       }
     }
   } else if (warp == kLbsWarpMma) {
@@ -115,9 +121,9 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       constexpr uint32_t kHalfB = 6 * kLboB;     // byte offset of the A_lo K half in the image
       ptx::mbar_wait(bar_w, 0);
       for (int i = 0; i < nblk; ++i) {
-        const int s = i % kLbsTcStages, a = i % kLbsTcAcc;
+        const int s = i % kLbsBStages, a = i % kLbsTcAcc;
         ptx::mbar_wait(bar_tempty + a, ((i / kLbsTcAcc) & 1) ^ 1);
-        ptx::mbar_wait(bar_bfull + s, (i / kLbsTcStages) & 1);
+        ptx::mbar_wait(bar_bfull + s, (i / kLbsBStages) & 1);
         ptx::tc_fence_after();
         const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * kLbsBStage);
         const uint32_t d_tmem = tmem_base + a * kLbsN;
@@ -139,8 +145,8 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
     }
   } else {
     // ===== epilogue (4 warps, TMEM lane quarter q) =====
-    const int q = warp;
-    const int ew = warp;
+    const int q = warp & 3;
+    const int ew = warp - 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int v_local = q * 32 + lane;
     const int warp_v0 = tile * 128 + q * 32;
@@ -166,15 +172,15 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       __syncwarp();
     }
     for (int i = 0; i < nblk; ++i) {
-      const int s = i % kLbsTcStages, a = i % kLbsTcAcc;
+      const int s = i % kLbsVStages, a = i % kLbsTcAcc;
       const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
       const int nb = (int)min((long long)kLbsBlock, n - b0);
       const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
       const bool full = (nb == kLbsBlock) && (nf == 96);
       const size_t body_stride = (size_t)V * 3;
       float* dst = verts + ((size_t)b0 * V + warp_v0) * 3 + lane;
-      ptx::mbar_wait_relaxed(bar_vfull + s, (i / kLbsTcStages) & 1, tune & 1);
-      ptx::mbar_wait_relaxed(bar_tfull + a, (i / kLbsTcAcc) & 1, tune & 1);
+      ptx::mbar_wait(bar_vfull + s, (i / kLbsVStages) & 1);
+      ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN;
 #pragma unroll
@@ -245,7 +251,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
     if (tile == 0 && kp2d != nullptr) {
       const long long bb0 = (long long)blk_begin * kLbsBlock;
       const long long bb1 = min(n, (long long)blk_end * kLbsBlock);
-      for (long long i = bb0 * (kJ * 2) + (int)threadIdx.x; i < bb1 * (kJ * 2); i += 128) {
+      for (long long i = bb0 * (kJ * 2) + ((int)threadIdx.x - 64); i < bb1 * (kJ * 2); i += 128) {
         const long long b = i / (kJ * 2);
         const int r = int(i - b * (kJ * 2)), j = r >> 1, c = r & 1;
         const float sc = __ldg(cam + b * 3), tt = __ldg(cam + b * 3 + 1 + c);
