@@ -32,10 +32,11 @@
 
 namespace smplb200 {
 
-constexpr int kLbsTcThreads = 224;                       // vposed TMA, MMA, 4 epilogue, A' TMA warps
-constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 6;   // epilogue = warps 2..5
+constexpr int kLbsTcThreads = 352;                       // vposed TMA, MMA, 8 epilogue, A' TMA warps
+constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 10;  // epilogue = warps 2..9
+constexpr int kLbsEpiWarps = 8;                          // two per TMEM lane quarter, 4 bodies each
 constexpr int kLbsBStages = 2;                           // A' images come from L2: shallow ring
-constexpr int kLbsVStages = 5;                           // vposed rows come from HBM: deep ring
+constexpr int kLbsVStages = 4;                           // vposed rows come from HBM: deep ring
 constexpr int kLbsTcAcc = 2;
 constexpr int kLbsN = kLbsBlock * 12;                    // 96
 constexpr int kLbsTmemCols = 256;                        // 2 x 96 accumulators + 48 columns of W'
@@ -45,7 +46,7 @@ constexpr uint32_t kLbsVRow = 128 * 4;                   // one (body, plane) ro
 constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 12,288
 constexpr uint32_t kLbsVOff = kLbsBStages * kLbsBStage;
 constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsVStages * kLbsVStage;
-constexpr uint32_t kLbsBarOff = kLbsOutOff + 4 * 4 * 96 * 4;   // 4 warps x 4 bodies x 96 floats
+constexpr uint32_t kLbsBarOff = kLbsOutOff + kLbsEpiWarps * 4 * 96 * 4;   // per warp: 4 bodies x 96 floats
 constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~105 KB -> two CTAs per SM
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
@@ -77,8 +78,8 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   if (warp == kLbsWarpTmaV && lane == 0) {
     ptx::mbar_init(bar_w, 4);
     for (int s = 0; s < kLbsBStages; ++s) { ptx::mbar_init(bar_bfull + s, 1); ptx::mbar_init(bar_bempty + s, 1); }
-    for (int s = 0; s < kLbsVStages; ++s) { ptx::mbar_init(bar_vfull + s, 1); ptx::mbar_init(bar_vempty + s, 4); }
-    for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4); }
+    for (int s = 0; s < kLbsVStages; ++s) { ptx::mbar_init(bar_vfull + s, 1); ptx::mbar_init(bar_vempty + s, kLbsEpiWarps); }
+    for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, kLbsEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == kLbsWarpMma) ptx::tmem_alloc(tmem_slot, kLbsTmemCols);
@@ -144,15 +145,16 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       }
     }
   } else {
-    // ===== epilogue (4 warps, TMEM lane quarter q) =====
+    // ===== epilogue (8 warps: TMEM lane quarter q, bodies 4h .. 4h+3 of each block) =====
     const int q = warp & 3;
     const int ew = warp - 2;
+    const int h = ew >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int v_local = q * 32 + lane;
     const int warp_v0 = tile * 128 + q * 32;
     const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
     float* so = sOut + ew * (4 * 96);
-    if (nblk > 0) {
+    if (nblk > 0 && h == 0) {
       // W' rows of this vertex tile -> TMEM (A operand of every blend MMA of this CTA)
       const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + v_local) * kLbsK);
 #pragma unroll
@@ -178,39 +180,35 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
       const bool full = (nb == kLbsBlock) && (nf == 96);
       const size_t body_stride = (size_t)V * 3;
-      float* dst = verts + ((size_t)b0 * V + warp_v0) * 3 + lane;
+      float* dst = verts + ((size_t)(b0 + 4 * h) * V + warp_v0) * 3 + lane;
       ptx::mbar_wait(bar_vfull + s, (i / kLbsVStages) & 1);
       ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {   // 4 bodies = 48 TMEM columns per round
+      const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN + h * 48;
+      {   // this warp's 4 bodies = 48 TMEM columns
         uint32_t r0[16], r1[16], r2[16];
-        ptx::tmem_ld16(t_addr + half * 48, r0);
-        ptx::tmem_ld16(t_addr + half * 48 + 16, r1);
-        ptx::tmem_ld16(t_addr + half * 48 + 32, r2);
+        ptx::tmem_ld16(t_addr, r0);
+        ptx::tmem_ld16(t_addr + 16, r1);
+        ptx::tmem_ld16(t_addr + 32, r2);
         float px[4], py[4], pz[4];
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
-          const float* p = sv + (half * 4 + bb) * 3 * 128;
+          const float* p = sv + (h * 4 + bb) * 3 * 128;
           px[bb] = p[0]; py[bb] = p[128]; pz[bb] = p[256];
         }
         ptx::tmem_ld_wait();
-        if (half == 1) {   // both the accumulator and the vposed stage are now in registers
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { ptx::mbar_arrive(bar_tempty + a); ptx::mbar_arrive(bar_vempty + s); }
-          __syncwarp();
-        }
+        // both the accumulator columns and the vposed stage are now in registers: release them
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { ptx::mbar_arrive(bar_tempty + a); ptx::mbar_arrive(bar_vempty + s); }
+        __syncwarp();
         float T[48];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           T[e] = __uint_as_float(r0[e]); T[16 + e] = __uint_as_float(r1[e]); T[32 + e] = __uint_as_float(r2[e]);
         }
-        // four bodies per round: all FMAs, then ONE shared-memory transpose (xyz interleave) and
-        // twelve independent coalesced stores, so the STS -> LDS -> STG latency chain is paid once
-        // per round instead of once per body.
-        __syncwarp();
+        // all FMAs, then ONE shared-memory transpose (xyz interleave) and twelve independent
+        // coalesced stores: the STS -> LDS -> STG latency chain is paid once per block.
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
           const float* t = T + bb * 12;
@@ -236,7 +234,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         } else {
 #pragma unroll
           for (int bb = 0; bb < 4; ++bb) {
-            if (half * 4 + bb < nb) {
+            if (h * 4 + bb < nb) {
               float* d = dst + bb * body_stride;
 #pragma unroll
               for (int k = 0; k < 3; ++k)
@@ -244,14 +242,14 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
             }
           }
         }
-        dst += 4 * body_stride;
+        __syncwarp();          // staging row is reused by the next block
       }
     }
     // k4: weak-perspective projection of this CTA's bodies (CTAs of vertex tile 0 only)
     if (tile == 0 && kp2d != nullptr) {
       const long long bb0 = (long long)blk_begin * kLbsBlock;
       const long long bb1 = min(n, (long long)blk_end * kLbsBlock);
-      for (long long i = bb0 * (kJ * 2) + ((int)threadIdx.x - 64); i < bb1 * (kJ * 2); i += 128) {
+      for (long long i = bb0 * (kJ * 2) + ((int)threadIdx.x - 64); i < bb1 * (kJ * 2); i += 256) {
         const long long b = i / (kJ * 2);
         const int r = int(i - b * (kJ * 2)), j = r >> 1, c = r & 1;
         const float sc = __ldg(cam + b * 3), tt = __ldg(cam + b * 3 + 1 + c);
