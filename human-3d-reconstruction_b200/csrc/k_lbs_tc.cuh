@@ -15,10 +15,11 @@
 // the same order as an fp32 FMA chain.  W' = [W_hi | W_lo] rows of a 128-vertex tile are RESIDENT
 // IN TENSOR MEMORY as the MMA A operand (no shared-memory re-reads); A' = [A_hi | A_lo] per
 // 8-body block (written by k2) is the B operand.  Both A' and the block's planar vposed rows
-// (512 B per body and plane) stream through bulk-TMA / mbarrier rings with their own producer
-// warps (A': 2 stages from L2; vposed: 5 stages from HBM), so ~120 KB of loads are in flight per SM
-// without holding registers; two ~105 KB CTAs share an SM so one CTA's
-// prologue/tail hides behind the other's steady state.  The grid is vertex-tile-fastest: the
+// stream through bulk-TMA / mbarrier rings with their own producer warps (A': 2 stages from L2;
+// vposed: 4 stages from HBM).  The kernel is bound by L2 throughput (~8 TB/s of operand re-reads +
+// vposed + vertex traffic; round-1 ablation: 73 us with MMAs, loads and stores all disabled), so
+// each CTA blends TWO adjacent vertex tiles per A' stage (2 x W' in TMEM, 4 accumulators): the A'
+// re-read traffic halves and every vposed TMA row is 1 KB.  The grid is tile-pair-fastest: the
 // CTAs resident at one time read and write adjacent row chunks of the same bodies (DRAM pages).
 //
 // Epilogue thread = vertex: reads its 12 blended entries per body from TMEM, the planar vposed
@@ -32,25 +33,27 @@
 
 namespace smplb200 {
 
-constexpr int kLbsTcThreads = 352;                       // vposed TMA, MMA, 8 epilogue, A' TMA warps
-constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 10;  // epilogue = warps 2..9
-constexpr int kLbsEpiWarps = 8;                          // two per TMEM lane quarter, 4 bodies each
+constexpr int kLbsTiles = 2;                             // vertex tiles per CTA sharing one B stage
+constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 2;   // warp 3 idle; epilogue = warps 4..19
+constexpr int kLbsEpiWarp0 = 4;
+constexpr int kLbsEpiWarps = 8 * kLbsTiles;              // per tile: two per TMEM lane quarter, 4 bodies each
+constexpr int kLbsTcThreads = (kLbsEpiWarp0 + kLbsEpiWarps) * 32;    // 640
 constexpr int kLbsBStages = 2;                           // A' images come from L2: shallow ring
 constexpr int kLbsVStages = 4;                           // vposed rows come from HBM: deep ring
 constexpr int kLbsTcAcc = 2;
 constexpr int kLbsN = kLbsBlock * 12;                    // 96
-constexpr int kLbsTmemCols = 256;                        // 2 x 96 accumulators + 48 columns of W'
-constexpr int kLbsAccCols = kLbsTcAcc * kLbsN;           // 192
+constexpr int kLbsTmemCols = 512;                        // 2 tiles x 2 x 96 accumulators + 2 x 48 of W'
+constexpr int kLbsAccCols = kLbsTiles * kLbsTcAcc * kLbsN;   // 384
 constexpr uint32_t kLbsBStage = kLbsK * kLbsN * 4;       // 18,432  tf32 hi|lo image of A, one block
-constexpr uint32_t kLbsVRow = 128 * 4;                   // one (body, plane) row of the vertex tile
-constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 12,288
+constexpr uint32_t kLbsVRow = kLbsTiles * 128 * 4;       // one (body, plane) row of the tile pair: 1 KB
+constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 24,576
 constexpr uint32_t kLbsVOff = kLbsBStages * kLbsBStage;
 constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsVStages * kLbsVStage;
 constexpr uint32_t kLbsBarOff = kLbsOutOff + kLbsEpiWarps * 4 * 96 * 4;   // per warp: 4 bodies x 96 floats
-constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~105 KB -> two CTAs per SM
+constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~160 KB, one CTA per SM
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
-__global__ void __launch_bounds__(kLbsTcThreads, 2)
+__global__ void __launch_bounds__(kLbsTcThreads, 1)
 k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
          const float* __restrict__ vposed, long long n, int nblocks, int blocks_per_cta,
          int V, int VP, float* __restrict__ verts, const float* __restrict__ joints_in,
@@ -60,23 +63,25 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   uint8_t* sV = smem + kLbsVOff;
   float* sOut = reinterpret_cast<float*>(smem + kLbsOutOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLbsBarOff);
-  uint64_t* bar_w = bars;                            // W' rows resident in TMEM (4 warp arrivals)
+  uint64_t* bar_w = bars;                            // W' rows resident in TMEM (8 warp arrivals)
   uint64_t* bar_bfull = bars + 1;                    // [B stages] A' image landed
   uint64_t* bar_bempty = bar_bfull + kLbsBStages;    // [B stages] MMAs reading it retired
   uint64_t* bar_vfull = bar_bempty + kLbsBStages;    // [V stages] vposed rows landed
-  uint64_t* bar_vempty = bar_vfull + kLbsVStages;    // [V stages] epilogue warps done with them (4)
-  uint64_t* bar_tfull = bar_vempty + kLbsVStages;    // [acc] accumulator ready
-  uint64_t* bar_tempty = bar_tfull + kLbsTcAcc;      // [acc] accumulator drained (4)
+  uint64_t* bar_vempty = bar_vfull + kLbsVStages;    // [V stages] epilogue warps done with them
+  uint64_t* bar_tfull = bar_vempty + kLbsVStages;    // [acc] accumulators (both tiles) ready
+  uint64_t* bar_tempty = bar_tfull + kLbsTcAcc;      // [acc] accumulators drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + kLbsTcAcc);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;                       // tile-fastest grid: co-resident CTAs touch
-  const int blk_begin = blockIdx.y * blocks_per_cta; // adjacent 512-byte row chunks of the same bodies
+  const int vtiles = VP / 128;
+  const int tile0 = blockIdx.x * kLbsTiles;          // tile-pair-fastest grid: co-resident CTAs touch
+  const int ntile = min(kLbsTiles, vtiles - tile0);  // adjacent row chunks of the same bodies
+  const int blk_begin = blockIdx.y * blocks_per_cta;
   const int blk_end = min(nblocks, blk_begin + blocks_per_cta);
   const int nblk = blk_end - blk_begin;
 
   if (warp == kLbsWarpTmaV && lane == 0) {
-    ptx::mbar_init(bar_w, 4);
+    ptx::mbar_init(bar_w, 4 * kLbsTiles);
     for (int s = 0; s < kLbsBStages; ++s) { ptx::mbar_init(bar_bfull + s, 1); ptx::mbar_init(bar_bempty + s, 1); }
     for (int s = 0; s < kLbsVStages; ++s) { ptx::mbar_init(bar_vfull + s, 1); ptx::mbar_init(bar_vempty + s, kLbsEpiWarps); }
     for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, kLbsEpiWarps); }
@@ -90,18 +95,20 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   const uint32_t tmem_w = tmem_base + kLbsAccCols;
 
   if (warp == kLbsWarpTmaV) {
-    // ===== bulk-TMA producer 1: the block's vposed rows (512 B per body and plane), from HBM =====
+    // ===== bulk-TMA producer 1: vposed rows of the tile pair (1 KB per body and plane), from HBM =====
     if (lane == 0) {
+      const uint32_t row_bytes = (uint32_t)ntile * 128 * 4;
       for (int i = 0; i < nblk; ++i) {
         const int s = i % kLbsVStages;
         const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
         const int nb = (int)min((long long)kLbsBlock, n - b0);
+        const int nrows = (tune & 2) ? 1 : nb * 3;   // experiment knob: bit1 = load a single row
         ptx::mbar_wait(bar_vempty + s, ((i / kLbsVStages) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nb * 3 * kLbsVRow);
-        const float* src = vposed + (size_t)b0 * 3 * VP + (size_t)tile * 128;
+        ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nrows * row_bytes);
+        const float* src = vposed + (size_t)b0 * 3 * VP + (size_t)tile0 * 128;
         uint8_t* dst = sV + (size_t)s * kLbsVStage;
-        for (int r = 0; r < nb * 3; ++r)
-          ptx::bulk_g2s(dst + (size_t)r * kLbsVRow, src + (size_t)r * VP, kLbsVRow, bar_vfull + s);
+        for (int r = 0; r < nrows; ++r)
+          ptx::bulk_g2s(dst + (size_t)r * kLbsVRow, src + (size_t)r * VP, row_bytes, bar_vfull + s);
       }
     }
   } else if (warp == kLbsWarpTmaB) {
@@ -116,7 +123,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       }
     }
   } else if (warp == kLbsWarpMma) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: one B stage feeds the blend MMAs of BOTH vertex tiles =====
     if (lane == 0 && nblk > 0) {
       constexpr uint32_t kLboB = kLbsN * 16, kSbo = 128;
       constexpr uint32_t kHalfB = 6 * kLboB;     // byte offset of the A_lo K half in the image
@@ -127,47 +134,53 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         ptx::mbar_wait(bar_bfull + s, (i / kLbsBStages) & 1);
         ptx::tc_fence_after();
         const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * kLbsBStage);
-        const uint32_t d_tmem = tmem_base + a * kLbsN;
-        uint32_t acc = 0;
+        for (int t = 0; t < ntile; ++t) {
+          const uint32_t d_tmem = tmem_base + (t * kLbsTcAcc + a) * kLbsN;
+          uint32_t acc = 0;
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {  // (W_hi,A_hi), (W_hi,A_lo), (W_lo,A_hi)
-          const uint32_t wp = tmem_w + (g == 2 ? 24 : 0);
-          const uint32_t bp = b_addr + (g == 1 ? kHalfB : 0);
+          for (int g = 0; g < 3; ++g) {  // (W_hi,A_hi), (W_hi,A_lo), (W_lo,A_hi)
+            const uint32_t wp = tmem_w + t * kLbsK + (g == 2 ? 24 : 0);
+            const uint32_t bp = b_addr + (g == 1 ? kHalfB : 0);
 #pragma unroll
-          for (int ks = 0; ks < 3; ++ks) {  // 24 joints = 3 tf32 k-steps of 8
-            const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * kLboB, kLboB, kSbo);
-            ptx::mma_tf32_ts(d_tmem, wp + ks * 8, bd, kLbsIdesc, acc);
-            acc = 1;
+            for (int ks = 0; ks < 3; ++ks) {  // 24 joints = 3 tf32 k-steps of 8
+              const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * kLboB, kLboB, kSbo);
+              if (!(tune & 4)) ptx::mma_tf32_ts(d_tmem, wp + ks * 8, bd, kLbsIdesc, acc);   // bit2 = no MMA
+              acc = 1;
+            }
           }
         }
         ptx::tc_commit(bar_bempty + s);
         ptx::tc_commit(bar_tfull + a);
       }
     }
-  } else {
-    // ===== epilogue (8 warps: TMEM lane quarter q, bodies 4h .. 4h+3 of each block) =====
+  } else if (warp >= kLbsEpiWarp0) {
+    // ===== epilogue (16 warps: tile t, TMEM lane quarter q, bodies 4h .. 4h+3 of each block) =====
+    const int ew = warp - kLbsEpiWarp0;
     const int q = warp & 3;
-    const int ew = warp - 2;
-    const int h = ew >> 2;
+    const int t = (ew >> 2) & 1;
+    const int h = ew >> 3;
+    const bool live = t < ntile;                       // second tile may not exist (odd tile count)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int v_local = q * 32 + lane;
-    const int warp_v0 = tile * 128 + q * 32;
+    const int v_local = t * 128 + q * 32 + lane;       // column inside the staged tile-pair row
+    const int warp_v0 = (tile0 + t) * 128 + q * 32;
     const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
     float* so = sOut + ew * (4 * 96);
     if (nblk > 0 && h == 0) {
-      // W' rows of this vertex tile -> TMEM (A operand of every blend MMA of this CTA)
-      const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + v_local) * kLbsK);
+      // W' rows of this vertex tile -> TMEM (A operand of every blend MMA of this tile)
+      if (live) {
+        const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)(tile0 + t) * 128 + q * 32 + lane) * kLbsK);
 #pragma unroll
-      for (int c = 0; c < kLbsK / 16; ++c) {
-        uint32_t w[16];
+        for (int c = 0; c < kLbsK / 16; ++c) {
+          uint32_t w[16];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint4 x = __ldg(src + c * 4 + v);
-          w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+          for (int v = 0; v < 4; ++v) {
+            const uint4 x = __ldg(src + c * 4 + v);
+            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+          }
+          ptx::tmem_st16(tmem_w + lane_addr + t * kLbsK + c * 16, w);
         }
-        ptx::tmem_st16(tmem_w + lane_addr + c * 16, w);
+        ptx::tmem_st_wait();
       }
-      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar_w);
@@ -178,13 +191,13 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
       const int nb = (int)min((long long)kLbsBlock, n - b0);
       const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
-      const bool full = (nb == kLbsBlock) && (nf == 96);
+      const bool full = live && (nb == kLbsBlock) && (nf == 96);
       const size_t body_stride = (size_t)V * 3;
       float* dst = verts + ((size_t)(b0 + 4 * h) * V + warp_v0) * 3 + lane;
       ptx::mbar_wait(bar_vfull + s, (i / kLbsVStages) & 1);
       ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
       ptx::tc_fence_after();
-      const uint32_t t_addr = tmem_base + lane_addr + a * kLbsN + h * 48;
+      const uint32_t t_addr = tmem_base + lane_addr + (t * kLbsTcAcc + a) * kLbsN + h * 48;
       {   // this warp's 4 bodies = 48 TMEM columns
         uint32_t r0[16], r1[16], r2[16];
         ptx::tmem_ld16(t_addr, r0);
@@ -193,8 +206,8 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         float px[4], py[4], pz[4];
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
-          const float* p = sv + (h * 4 + bb) * 3 * 128;
-          px[bb] = p[0]; py[bb] = p[128]; pz[bb] = p[256];
+          const float* p = sv + (h * 4 + bb) * 3 * (kLbsTiles * 128);
+          px[bb] = p[0]; py[bb] = p[kLbsTiles * 128]; pz[bb] = p[2 * kLbsTiles * 128];
         }
         ptx::tmem_ld_wait();
         // both the accumulator columns and the vposed stage are now in registers: release them
@@ -211,15 +224,16 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         // coalesced stores: the STS -> LDS -> STG latency chain is paid once per block.
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
-          const float* t = T + bb * 12;
+          const float* tt = T + bb * 12;
           const float x = px[bb], y = py[bb], z = pz[bb];
           float* sb = so + bb * 96 + 3 * lane;
-          sb[0] = fmaf(t[2], z, fmaf(t[1], y, fmaf(t[0], x, t[3])));
-          sb[1] = fmaf(t[6], z, fmaf(t[5], y, fmaf(t[4], x, t[7])));
-          sb[2] = fmaf(t[10], z, fmaf(t[9], y, fmaf(t[8], x, t[11])));
+          sb[0] = fmaf(tt[2], z, fmaf(tt[1], y, fmaf(tt[0], x, tt[3])));
+          sb[1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
+          sb[2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
         }
         __syncwarp();
-        if (full) {            // fast path: whole block, whole warp -> unpredicated stores
+        if (full && (tune & 1)) {   // experiment knob: bit0 = no vertex stores
+        } else if (full) {          // fast path: whole block, whole warp -> unpredicated stores
           float o[12];
 #pragma unroll
           for (int bb = 0; bb < 4; ++bb) {
@@ -231,7 +245,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
             float* d = dst + bb * body_stride;
             d[0] = o[3 * bb]; d[32] = o[3 * bb + 1]; d[64] = o[3 * bb + 2];
           }
-        } else {
+        } else if (live) {
 #pragma unroll
           for (int bb = 0; bb < 4; ++bb) {
             if (h * 4 + bb < nb) {
@@ -245,11 +259,12 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         __syncwarp();          // staging row is reused by the next block
       }
     }
-    // k4: weak-perspective projection of this CTA's bodies (CTAs of vertex tile 0 only)
-    if (tile == 0 && kp2d != nullptr) {
+    // k4: weak-perspective projection of this CTA's bodies (CTAs of the first tile pair only)
+    if (tile0 == 0 && kp2d != nullptr) {
       const long long bb0 = (long long)blk_begin * kLbsBlock;
       const long long bb1 = min(n, (long long)blk_end * kLbsBlock);
-      for (long long i = bb0 * (kJ * 2) + ((int)threadIdx.x - 64); i < bb1 * (kJ * 2); i += 256) {
+      for (long long i = bb0 * (kJ * 2) + ((int)threadIdx.x - kLbsEpiWarp0 * 32); i < bb1 * (kJ * 2);
+           i += kLbsEpiWarps * 32) {
         const long long b = i / (kJ * 2);
         const int r = int(i - b * (kJ * 2)), j = r >> 1, c = r & 1;
         const float sc = __ldg(cam + b * 3), tt = __ldg(cam + b * 3 + 1 + c);
@@ -279,16 +294,16 @@ k_pack_a(const float* __restrict__ A, long long n, uint32_t* __restrict__ img) {
   im[(size_t)((24 + jj) >> 2) * (kLbsN * 4) + row * 4 + ((24 + jj) & 3)] = lo;
 }
 
-// Grid shape: x = vertex tile (fastest), y = body-block group.  The group count is chosen so the
-// CTA count lands just under a whole number of waves of (2 CTAs x SMs) resident slots.
-inline int lbs_tc_blocks_per_cta(int vtiles, int nblocks, int num_sms) {
-  const double slots = 2.0 * num_sms;
+// Grid shape: x = vertex tile pair (fastest), y = body-block group.  The group count is chosen so
+// the CTA count lands just under a whole number of waves (one CTA per SM).
+inline int lbs_tc_blocks_per_cta(int cta_x, int nblocks, int num_sms) {
+  const double slots = (double)num_sms;
   int best_bpc = nblocks;
   double best_eff = -1.0;
   for (int bpc = nblocks; bpc >= 1; --bpc) {
-    if (bpc < 8 && bpc < nblocks) break;                  // keep the W' load / prologue amortised
+    if (bpc < 16 && bpc < nblocks) break;                 // keep the W' load / prologue amortised
     const int groups = (nblocks + bpc - 1) / bpc;
-    const double waves = vtiles * (double)groups / slots;
+    const double waves = cta_x * (double)groups / slots;
     const double eff = waves / std::ceil(waves);
     if (eff > best_eff + 0.02) { best_eff = eff; best_bpc = bpc; }
   }
@@ -301,9 +316,10 @@ inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float*
                                  cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   const int vtiles = m.VP / 128;
+  const int cta_x = (vtiles + kLbsTiles - 1) / kLbsTiles;
   const int nblocks = (int)((n + kLbsBlock - 1) / kLbsBlock);
-  const int bpc = lbs_tc_blocks_per_cta(vtiles, nblocks, num_sms);
-  const dim3 grid((unsigned)vtiles, (unsigned)((nblocks + bpc - 1) / bpc));
+  const int bpc = lbs_tc_blocks_per_cta(cta_x, nblocks, num_sms);
+  const dim3 grid((unsigned)cta_x, (unsigned)((nblocks + bpc - 1) / bpc));
   k_lbs_tc<<<grid, kLbsTcThreads, kLbsSmemBytes, s>>>(
       m.w_tf32, reinterpret_cast<const uint8_t*>(a_img), vposed, n, nblocks, bpc, m.V, m.VP, verts,
       joints_in, cam, kp2d, m.tune);
