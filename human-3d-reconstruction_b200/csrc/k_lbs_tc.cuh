@@ -38,7 +38,7 @@ constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 2;   // warp 3 i
 constexpr int kLbsEpiWarp0 = 4;
 constexpr int kLbsEpiWarps = 8 * kLbsTiles;              // per tile: two per TMEM lane quarter, 4 bodies each
 constexpr int kLbsTcThreads = (kLbsEpiWarp0 + kLbsEpiWarps) * 32;    // 640
-constexpr int kLbsBStages = 2;                           // A' images come from L2: shallow ring
+constexpr int kLbsBStages = 4;                           // A' images (L2-resident)
 constexpr int kLbsVStages = 4;                           // vposed rows come from HBM: deep ring
 constexpr int kLbsTcAcc = 2;
 constexpr int kLbsN = kLbsBlock * 12;                    // 96
