@@ -95,8 +95,11 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   const uint32_t tmem_w = tmem_base + kLbsAccCols;
 
   if (warp == kLbsWarpTmaV) {
-    // ===== bulk-TMA producer 1: vposed rows of the tile pair (1 KB per body and plane), from HBM =====
-    if (lane == 0) {
+    // ===== bulk-TMA producer 1: vposed rows of the tile pair (1 KB per body and plane), from HBM.
+    // The block's 24 rows are issued by 24 LANES in one warp-wide instruction: a single thread
+    // needs ~100 clk per cp.async.bulk (address + uniform-register shuffling), i.e. ~2400 clk per
+    // block, which was the whole "loads-only" time of the round-1 ablation.
+    {
       const uint32_t row_bytes = (uint32_t)ntile * 128 * 4;
       for (int i = 0; i < nblk; ++i) {
         const int s = i % kLbsVStages;
@@ -104,11 +107,13 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         const int nb = (int)min((long long)kLbsBlock, n - b0);
         const int nrows = (tune & 2) ? 1 : nb * 3;   // experiment knob: bit1 = load a single row
         ptx::mbar_wait(bar_vempty + s, ((i / kLbsVStages) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nrows * row_bytes);
+        if (lane == 0) ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nrows * row_bytes);
+        __syncwarp();
         const float* src = vposed + (size_t)b0 * 3 * VP + (size_t)tile0 * 128;
         uint8_t* dst = sV + (size_t)s * kLbsVStage;
-        for (int r = 0; r < nrows; ++r)
-          ptx::bulk_g2s(dst + (size_t)r * kLbsVRow, src + (size_t)r * VP, row_bytes, bar_vfull + s);
+        if (lane < nrows)
+          ptx::bulk_g2s(dst + (size_t)lane * kLbsVRow, src + (size_t)lane * VP, row_bytes, bar_vfull + s);
+        __syncwarp();
       }
     }
   } else if (warp == kLbsWarpTmaB) {
