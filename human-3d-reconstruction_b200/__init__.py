@@ -8,7 +8,7 @@ Public surface:
 """
 from . import synthetic  # noqa: F401
 from . import capi  # noqa: F401
-from .smpl import SMPL  # noqa: F401
+from .smpl import SMPL, GraphedSMPL, HostRunner  # noqa: F401
 from . import sharding  # noqa: F401
 
-__all__ = ["SMPL", "capi", "synthetic", "sharding"]
+__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "capi", "synthetic", "sharding"]

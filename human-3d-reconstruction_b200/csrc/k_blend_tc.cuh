@@ -17,9 +17,12 @@
 //   * an epilogue thread owns one planar column for 128 bodies, so each store instruction of a
 //     warp is one fully coalesced 128-byte segment of the planar vposed[b, plane, v] layout.
 //
-// Scheduling: persistent CTAs (one per SM); the (tile, body-block) units are split into equal
-// contiguous ranges, tile-major, so every CTA does the same amount of work (no wave
-// quantisation) and switches basis tile at most a few times.
+// Scheduling: persistent CTA PAIRS (2-CTA clusters, one CTA per SM).  A pair works on two adjacent
+// basis tiles and the same body blocks in lockstep; each CTA fetches half of every coef stage and
+// TMA-MULTICASTS it to both (tcgen05.commit multicasts the "stage consumed" arrival back), which
+// halves the operand re-read traffic through L2 (round-1 ncu: bf16x3 needed ~10 TB/s of L2->SM
+// traffic, above the ~8 TB/s the chip sustained).  The (tile pair, body block) units are split
+// into equal contiguous ranges, pair-major: no wave quantisation, few basis-tile switches.
 //
 // Warp roles (192 threads): warp 0 = bulk-TMA producer, warp 1 = single-thread MMA issuer,
 // warps 2..5 = epilogue + basis loader (TMEM lane quarter = warp % 4).  All mbarrier waits use
@@ -64,7 +67,7 @@ struct BlendTcCfg {
 };
 
 template <uint32_t PREC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ basis_lo,
            const uint8_t* __restrict__ coef_hi, const uint8_t* __restrict__ coef_lo,
            long long n, int nblocks, long long total_units, int NC, float* __restrict__ vposed,
@@ -81,37 +84,51 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + kTcAccBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // equal contiguous share of the tile-major unit list
-  const long long u0 = total_units * blockIdx.x / gridDim.x;
-  const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
+  // A cluster is a PAIR of CTAs working on two adjacent basis tiles and the same body blocks in
+  // lockstep; `total_units` counts (tile pair, body block) units and every cluster takes an equal
+  // contiguous share of the pair-major list.  Each CTA loads half of every coef stage and
+  // multicasts it to both, so the operand re-read traffic through L2 is halved.
+  const uint32_t crank = ptx::cluster_ctarank();
+  const long long cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const long long u0 = total_units * cid / nclusters;
+  const long long u1 = total_units * (cid + 1) / nclusters;
   const int nunits = (int)(u1 - u0);
+  const int ntile = NC / 128;
 
   constexpr int kWarpTma = 0, kWarpMma = 1;
   if (warp == kWarpTma && lane == 0) {
     ptx::mbar_init(bar_a, 4);
-    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 1); }
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(bar_full + s, 1); ptx::mbar_init(bar_empty + s, 2); }
     for (int a = 0; a < kTcAccBufs; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4); }
     ptx::fence_barrier_init();
   }
   if (warp == kWarpMma) ptx::tmem_alloc(tmem_slot, kTcTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrival
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_a = tmem_base + kTcAccCols;   // A operand columns follow the accumulators
 
   if (warp == kWarpTma) {
-    // ===== bulk-TMA producer: coef images of the body blocks, one K half per stage =====
+    // ===== bulk-TMA producer: coef images of the body blocks, one K half per stage.  This CTA
+    // fetches HALF of the stage and multicasts it to both CTAs of the pair. =====
     if (lane == 0) {
+      constexpr uint32_t kMy = C::kBStage / 2;          // bytes this CTA fetches per stage
       for (int i = 0; i < 2 * nunits; ++i) {
         const int s = i % C::kStages;
         const int blk = (int)((u0 + (i >> 1)) % nblocks);
-        ptx::mbar_wait_relaxed(bar_empty + s, ((i / C::kStages) & 1) ^ 1, tune & 2);
+        ptx::mbar_wait(bar_empty + s, ((i / C::kStages) & 1) ^ 1);   // both CTAs' MMAs retired
         ptx::mbar_arrive_expect_tx(bar_full + s, C::kBStage);
         uint8_t* dst = sB + (size_t)s * C::kBStage;
         const size_t src = (size_t)blk * C::kBBytesPart + (size_t)(i & 1) * C::kBHalf;
-        ptx::bulk_g2s(dst, coef_hi + src, C::kBHalf, bar_full + s);
-        if (C::kParts == 2) ptx::bulk_g2s(dst + C::kBHalf, coef_lo + src, C::kBHalf, bar_full + s);
+        if (C::kParts == 2) {     // stage = [hi half-K image | lo half-K image]: rank 0 -> hi, rank 1 -> lo
+          ptx::bulk_g2s_multicast(dst + crank * C::kBHalf, (crank ? coef_lo : coef_hi) + src, C::kBHalf,
+                                  bar_full + s, (uint16_t)3);
+        } else {                  // single image: each rank fetches half of its bytes
+          ptx::bulk_g2s_multicast(dst + crank * kMy, coef_hi + src + crank * kMy, kMy, bar_full + s,
+                                  (uint16_t)3);
+        }
       }
     }
   } else if (warp == kWarpMma) {
@@ -121,7 +138,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
       uint32_t a_phase = 0;
       for (int i = 0; i < nunits; ++i) {
         const int a = i % kTcAccBufs;
-        const long long tile = (u0 + i) / nblocks;
+        const long long tile = 2 * ((u0 + i) / nblocks) + crank;
         if (tile != cur_tile) {            // wait until the epilogue warps have (re)loaded A
           ptx::mbar_wait(bar_a, a_phase);
           a_phase ^= 1;
@@ -149,7 +166,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
               acc = 1;
             }
           }
-          ptx::tc_commit(bar_empty + s);   // stage reusable once these MMAs retire
+          ptx::tc_commit_multicast(bar_empty + s, (uint16_t)3);   // tell BOTH producers: stage consumed here
         }
         ptx::tc_commit(bar_tfull + a);   // accumulator ready for the epilogue
       }
@@ -161,13 +178,14 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
     long long cur_tile = -1;
     for (int i = 0; i < nunits; ++i) {
       const int a = i % kTcAccBufs;
-      const long long tile = (u0 + i) / nblocks;
+      const long long tile = 2 * ((u0 + i) / nblocks) + crank;
+      const bool live = tile < ntile;                     // odd tile count: the pair's second tile is a dummy
       const int blk = (int)((u0 + i) % nblocks);
       if (tile != cur_tile) {
         // Every earlier unit's accumulator was waited on below, so all MMAs that read the old
         // basis tile have retired: overwrite the A operand columns with the new tile's rows.
         cur_tile = tile;
-        const size_t row = (size_t)tile * 128 + q * 32 + lane;
+        const size_t row = (size_t)(live ? tile : 0) * 128 + q * 32 + lane;
 #pragma unroll
         for (int part = 0; part < C::kParts; ++part) {
           const uint4* src = reinterpret_cast<const uint4*>((part ? basis_lo : basis_hi) + row * C::kAWords);
@@ -208,7 +226,8 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
       // on the full-block fast path (the naive indexed form cost ~18 SASS instructions per store)
       const size_t ld = (size_t)NC;
       float* p0 = vposed + (size_t)b0 * ld + col;
-      if (nb == kCoefBlock) {
+      if (!live) {
+      } else if (nb == kCoefBlock) {
         float* p1 = p0 + ld; float* p2 = p1 + ld; float* p3 = p2 + ld;
         const size_t ld4 = 4 * ld;
 #pragma unroll
@@ -229,6 +248,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
   }
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync_all();          // no CTA exits while its partner may still multicast into it
   if (warp == kWarpMma) ptx::tmem_dealloc(tmem_base, kTcTmemCols);
 }
 
@@ -266,9 +286,10 @@ inline void blend_tc_launch(const DeviceModel& m, int num_sms, const void* chi, 
                             long long n, float* vposed, cudaStream_t s) {
   using C = BlendTcCfg<PREC>;
   const int ntile = m.NC / 128;
+  const int npair = (ntile + 1) / 2;
   const int nblocks = (int)((n + kCoefBlock - 1) / kCoefBlock);
-  const long long total = (long long)ntile * nblocks;
-  const unsigned grid = (unsigned)std::min<long long>(num_sms, total);
+  const long long total = (long long)npair * nblocks;                 // (tile pair, body block) units
+  const unsigned grid = 2u * (unsigned)std::min<long long>(num_sms / 2, total);   // CTA pairs
   const uint32_t* bh = C::kTf32 ? m.basis_rows_tf32 : m.basis_rows_bf16_hi;
   k_blend_tc<PREC><<<grid, kTcThreads, C::kSmemBytes, s>>>(
       bh, m.basis_rows_bf16_lo, static_cast<const uint8_t*>(chi), static_cast<const uint8_t*>(clo), n,

@@ -142,6 +142,41 @@ class SMPL(nn.Module):
         return h.launch_count(n, self.flags, with_projection)
 
 
+class GraphedSMPL:
+    """CUDA-graph replay of the forward for a fixed batch size (small-batch / latency regime).
+
+    At N <= ~256 the forward is launch-bound (three ~5-20 us kernels behind ~40 us of Python and
+    launch overhead per call); capturing the k2 -> k1 -> k3 sequence once and replaying it removes
+    the per-call host cost.  Inputs are static device tensors (``betas``, ``pose``, ``cam``): write
+    new parameters into them (``copy_``), call ``replay()``, read ``vertices`` / ``joints`` / ``kp2d``.
+    """
+
+    def __init__(self, smpl: "SMPL", n: int, device, with_cam: bool = True):
+        self.device = torch.device(device)
+        dev = self.device
+        self.betas = torch.zeros((n, smpl.num_betas), dtype=torch.float32, device=dev)
+        self.pose = torch.zeros((n, 3 * smpl.num_joints), dtype=torch.float32, device=dev)
+        self.cam = torch.zeros((n, 3), dtype=torch.float32, device=dev) if with_cam else None
+        if self.cam is not None:
+            self.cam[:, 0] = 1.0
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):       # warm-up: creates the per-device handle, primes caches
+                for _ in range(2):
+                    smpl(self.betas, self.pose, self.cam)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                out = smpl(self.betas, self.pose, self.cam)
+        self.vertices, self.joints = out[0], out[1]
+        self.kp2d = out[2] if len(out) > 2 else None
+
+    def replay(self):
+        self.graph.replay()
+        return (self.vertices, self.joints) if self.kp2d is None else (self.vertices, self.joints, self.kp2d)
+
+
 class HostRunner:
     """End-to-end runner over HOST buffers through ``smplb200_forward_host``.
 

@@ -231,6 +231,21 @@ def test_non_default_stream_and_reentrancy(dev, models):
         assert all(torch.equal(x, y) for x, y in zip(o, ref))
 
 
+def test_cuda_graph_replay_matches_eager(dev, models):
+    from human_3d_reconstruction_b200 import GraphedSMPL
+    for n, kw in ((64, dict(precision="fp32", lbs="fma")), (300, dict(precision="bf16x3", lbs="tc"))):
+        layer = SMPL(models["sparse"], **kw).to(dev)
+        g = GraphedSMPL(layer, n, dev, with_cam=True)
+        for seed in (51, 52):  # replay twice with different parameters
+            betas, pose, cam = synthetic.make_inputs(n, seed)
+            tb, tp, tc = to_dev(dev, betas, pose, cam)
+            g.betas.copy_(tb); g.pose.copy_(tp); g.cam.copy_(tc)
+            v, j, k = g.replay()
+            torch.cuda.synchronize()
+            ref = layer(tb, tp, tc)
+            assert torch.equal(v, ref[0]) and torch.equal(j, ref[1]) and torch.equal(k, ref[2])
+
+
 def test_errors(dev, models):
     layer = SMPL(models["sparse"]).to(dev)
     b, p = torch.zeros(2, 10, device=dev), torch.zeros(2, 72, device=dev)
