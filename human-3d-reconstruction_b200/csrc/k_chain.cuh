@@ -171,38 +171,54 @@ k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __rest
     const float4* src = reinterpret_cast<const float4*>(sa);
     for (int k = lane; k < kJ * 3; k += 32) dst[k] = src[k];
   }
-  // tensor-core operand images: row = body within its block, K-chunk-major (see k_blend_tc.cuh)
+  // tensor-core operand images: row = body within its block, K-chunk-major (see k_blend_tc.cuh).
+  // Every store is one whole 16-byte chunk (8 bf16 / 4 tf32 of consecutive k for this body); the
+  // eight bodies of a CTA fill adjacent chunks, so L2 sees full 128-byte lines.
   if (out.coef_bf16_hi) {
     const long long blk = b / kCoefBlock; const int row = int(b % kCoefBlock);
-    uint16_t* hi = out.coef_bf16_hi + blk * (long long)(kCoefK * kCoefBlock);
-    uint16_t* lo = out.coef_bf16_lo ? out.coef_bf16_lo + blk * (long long)(kCoefK * kCoefBlock) : nullptr;
-    for (int k = lane; k < kCoefK; k += 32) {
-      const float v = sc[k];
-      const uint16_t h = f32_to_bf16_rn(v);
-      const size_t off = (size_t)(k >> 3) * (kCoefBlock * 8) + row * 8 + (k & 7);
-      hi[off] = h;
-      if (lo) lo[off] = f32_to_bf16_rn(__fsub_rn(v, bf16_to_f32(h)));
+    uint4* hi = reinterpret_cast<uint4*>(out.coef_bf16_hi + blk * (long long)(kCoefK * kCoefBlock));
+    uint4* lo = out.coef_bf16_lo
+        ? reinterpret_cast<uint4*>(out.coef_bf16_lo + blk * (long long)(kCoefK * kCoefBlock)) : nullptr;
+    if (lane < kCoefK / 8) {
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v0 = sc[8 * lane + 2 * u], v1 = sc[8 * lane + 2 * u + 1];
+        const uint16_t h0 = f32_to_bf16_rn(v0), h1 = f32_to_bf16_rn(v1);
+        wh[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        wl[u] = (uint32_t)f32_to_bf16_rn(__fsub_rn(v0, bf16_to_f32(h0))) |
+                ((uint32_t)f32_to_bf16_rn(__fsub_rn(v1, bf16_to_f32(h1))) << 16);
+      }
+      const size_t off = (size_t)lane * kCoefBlock + row;    // in 16-byte chunks
+      hi[off] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      if (lo) lo[off] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
   }
   if (out.coef_tf32) {
     const long long blk = b / kCoefBlock; const int row = int(b % kCoefBlock);
-    uint32_t* im = out.coef_tf32 + blk * (long long)(kCoefK * kCoefBlock);
-    for (int k = lane; k < kCoefK; k += 32)
-      im[(size_t)(k >> 2) * (kCoefBlock * 4) + row * 4 + (k & 3)] = f32_to_tf32_rn(sc[k]);
+    uint4* im = reinterpret_cast<uint4*>(out.coef_tf32 + blk * (long long)(kCoefK * kCoefBlock));
+    for (int c = lane; c < kCoefK / 4; c += 32)
+      im[(size_t)c * kCoefBlock + row] =
+          make_uint4(f32_to_tf32_rn(sc[4 * c]), f32_to_tf32_rn(sc[4 * c + 1]),
+                     f32_to_tf32_rn(sc[4 * c + 2]), f32_to_tf32_rn(sc[4 * c + 3]));
   }
   if (out.a_tf32) {
-    // B operand of the blend MMA: rows n = (body_in_block*12 + e), K = 48 = [A_hi | A_lo]
+    // B operand of the blend MMA: rows n = (body_in_block*12 + e), K = 48 = [A_hi | A_lo];
+    // chunk c (0..11) holds joints 4(c%6)..4(c%6)+3 of part c/6 for every row.
     const long long blk = b / kLbsBlock; const int bi = int(b % kLbsBlock);
     constexpr int rows = kLbsBlock * 12;
-    uint32_t* im = out.a_tf32 + blk * (long long)(kLbsK * rows);
-    for (int idx = lane; idx < kJ * 12; idx += 32) {
-      const int jj = idx / 12, e = idx % 12;
-      const float v = sa[idx];
-      const uint32_t hi = f32_to_tf32_rn(v);
-      const uint32_t lo = f32_to_tf32_rn(__fsub_rn(v, __uint_as_float(hi)));
-      const int row = bi * 12 + e;
-      auto at = [&](int k) { return (size_t)(k >> 2) * (rows * 4) + row * 4 + (k & 3); };
-      im[at(jj)] = hi; im[at(24 + jj)] = lo;
+    uint4* im = reinterpret_cast<uint4*>(out.a_tf32 + blk * (long long)(kLbsK * rows));
+    for (int item = lane; item < 12 * 12; item += 32) {
+      const int c = item / 12, e = item % 12;
+      const int j0 = 4 * (c % 6);
+      uint32_t w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v = sa[(j0 + u) * 12 + e];
+        const uint32_t hi = f32_to_tf32_rn(v);
+        w[u] = c < 6 ? hi : f32_to_tf32_rn(__fsub_rn(v, __uint_as_float(hi)));
+      }
+      im[(size_t)c * rows + bi * 12 + e] = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }

@@ -231,6 +231,21 @@ def test_non_default_stream_and_reentrancy(dev, models):
         assert all(torch.equal(x, y) for x, y in zip(o, ref))
 
 
+@pytest.mark.parametrize("num_verts,num_betas", [(300, 10), (1000, 8), (129, 14)])
+def test_other_model_shapes(dev, num_verts, num_betas):
+    """Odd tile counts (dummy second tile of a CTA pair / tile pair), V not a multiple of 128, NB != 10."""
+    model = synthetic.make_model(5, num_verts=num_verts, num_betas=num_betas)
+    n = 200
+    betas, pose, cam = synthetic.make_inputs(n, 61, num_betas=num_betas)
+    ref_v, ref_j, ref_k = smpl_forward(model, betas, pose, cam)
+    for precision, lbs in (("fp32", "fma"), ("fp32", "tc"), ("bf16x3", "tc"), ("tf32", "tc")):
+        layer = SMPL(model, precision=precision, lbs=lbs).to(dev)
+        v, j, k = layer(*to_dev(dev, betas, pose, cam))
+        check_verts(v, ref_v, precision, f"V={num_verts} NB={num_betas} {precision}/{lbs}")
+        assert_close(j, ref_j, what="joints")
+        assert_close(k, ref_k, atol=2e-6, what="kp2d")
+
+
 def test_cuda_graph_replay_matches_eager(dev, models):
     from human_3d_reconstruction_b200 import GraphedSMPL
     for n, kw in ((64, dict(precision="fp32", lbs="fma")), (300, dict(precision="bf16x3", lbs="tc"))):
