@@ -91,19 +91,32 @@ k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __rest
   rodrigues_hmr(th0, th1, th2, R);
 
   // ---- folded joint regression: Jrest = J_template + betas . J_shapedirs
-  float J0 = m.j_template[3 * j], J1 = m.j_template[3 * j + 1], J2 = m.j_template[3 * j + 2];
+  // (all loads are issued before the first FMA: the loop is fully unrolled over kMaxBetas so the
+  //  ~30 L2 round trips overlap instead of chaining)
   const float* bb = betas + b * NB;
-  for (int k = 0; k < NB; ++k) {
-    float bk = __ldg(bb + k);
-    const float* js = m.j_shapedirs + k * (3 * kJ) + 3 * j;
-    J0 = fmaf(bk, js[0], J0); J1 = fmaf(bk, js[1], J1); J2 = fmaf(bk, js[2], J2);
+  const float my_beta = lane < NB ? __ldg(bb + lane) : 0.f;
+  float js0[kMaxBetas], js1[kMaxBetas], js2[kMaxBetas];
+#pragma unroll
+  for (int k = 0; k < kMaxBetas; ++k) {
+    if (k < NB) {
+      const float* js = m.j_shapedirs + k * (3 * kJ) + 3 * j;
+      js0[k] = __ldg(js); js1[k] = __ldg(js + 1); js2[k] = __ldg(js + 2);
+    } else {
+      js0[k] = js1[k] = js2[k] = 0.f;
+    }
+  }
+  float J0 = __ldg(m.j_template + 3 * j), J1 = __ldg(m.j_template + 3 * j + 1), J2 = __ldg(m.j_template + 3 * j + 2);
+#pragma unroll
+  for (int k = 0; k < kMaxBetas; ++k) {
+    const float bk = __shfl_sync(0xffffffffu, my_beta, k);
+    J0 = fmaf(bk, js0[k], J0); J1 = fmaf(bk, js1[k], J1); J2 = fmaf(bk, js2[k], J2);
   }
 
   // ---- blendshape coefficients: betas | (R - I) of joints 1..23 | 1 1 1 | zeros
   float* sc = s_coef[warp];
   for (int k = lane; k < kCoefK; k += 32) sc[k] = 0.f;
   __syncwarp();
-  if (lane < NB) sc[lane] = __ldg(bb + lane);
+  if (lane < NB) sc[lane] = my_beta;
   if (lane < 3) sc[NB + kP + lane] = 1.0f;   // v_template rows (split in 3 exact pieces for tcgen05)
   if (active && j >= 1) {
     float* pf = sc + NB + 9 * (j - 1);
