@@ -4,45 +4,63 @@
 //                  + ( ( sum_{k<NB} betas[b,k] * shapedirs[k,col] ) + v_template[col] )
 //
 // with the same association as the eager layer (shape sum, + template, then + pose sum;
-// SURVEY.md A.2/A.5) and every sum taken k-ascending into a single fp32 accumulator
-//  so results are reproducible and independent of the batch split.
+// SURVEY.md A.2/A.5).  The 207 pose terms are split into KS contiguous K slices, one per group of
+// 64 threads; every slice is summed k-ascending into a single fp32 accumulator and the slices are
+// combined in slice order through shared memory -- a FIXED order, so results are reproducible and
+// independent of how the batch is split.  The K split exists because at N <= 64
+// the op is latency-bound: one serial 207-step loop per thread with ~4 warps per SM left the FMA
+// pipes idle (round-1 launch list: 66 us cold at N = 1); KS = 4 gives 4x the warps and the loads
+// are software-pipelined 8 deep.
 //
-// Thread tile: 4 adjacent planar columns x BB bodies.  Per k: one float4 of the basis
-// (coalesced, read once per CTA) and BB/4 broadcast LDS.128 of coefficients feed 4*BB FMAs, the
-// 16 FMA : 1 LDS.128 ratio that keeps the FMA pipe, not the shared-memory crossbar, the limiter.
+// Thread tile: 4 adjacent planar columns x BB bodies.  Per k: one float4 of the basis (coalesced)
+// and BB/4 broadcast LDS.128 of coefficients feed 4*BB FMAs -- the 16 FMA : 1 LDS.128 ratio that
+// keeps the FMA pipe, not the shared-memory crossbar, the limiter.
 #pragma once
 #include "common.cuh"
 
 namespace smplb200 {
 
-constexpr int kFmaThreads = 64;                       // 64 threads x 4 columns = 256 columns / CTA
-constexpr int kFmaColsPerCta = kFmaThreads * 4;
+constexpr int kFmaColThreads = 64;                    // 64 threads x 4 columns = 256 columns / CTA
+constexpr int kFmaColsPerCta = kFmaColThreads * 4;
 
-template <int BB>
-__global__ void __launch_bounds__(kFmaThreads)
+template <int BB, int KS>
+struct BlendFmaCfg {
+  static constexpr int kThreads = kFmaColThreads * KS;
+  static constexpr int kCoefStride = BB + 4;          // +4: transpose-store conflicts 32-way -> 4-way
+  static constexpr size_t kCoefBytes = (size_t)kCoefK * kCoefStride * sizeof(float);
+  static constexpr size_t kRedBytes = (size_t)(KS - 1) * BB * 4 * kFmaColThreads * sizeof(float);
+  static constexpr size_t kSmemBytes = kCoefBytes + kRedBytes;
+};
+
+template <int BB, int KS>
+__global__ void __launch_bounds__(kFmaColThreads * KS)
 k_blend_fma(DeviceModel m, const float* __restrict__ coef, long long n, float* __restrict__ vposed) {
-  // coefficients of this CTA's BB bodies, transposed to [k][body] for broadcast LDS.128
-  __shared__ __align__(16) float s_c[kCoefK][BB + 4];  // +4: transpose-store conflicts 32-way -> 4-way
+  using C = BlendFmaCfg<BB, KS>;
+  extern __shared__ __align__(16) float smem_f[];
+  float (*s_c)[C::kCoefStride] = reinterpret_cast<float (*)[C::kCoefStride]>(smem_f);  // [k][body]
+  float* s_red = smem_f + kCoefK * C::kCoefStride;                                     // [ks-1][i][t]
+  const int t = threadIdx.x % kFmaColThreads, ks = threadIdx.x / kFmaColThreads;
   const long long b0 = (long long)blockIdx.y * BB;
   const int nb = (int)min((long long)BB, n - b0);
-  for (int idx = threadIdx.x; idx < kCoefK * BB; idx += kFmaThreads) {
+  for (int idx = threadIdx.x; idx < kCoefK * BB; idx += C::kThreads) {
     const int bi = idx / kCoefK, k = idx % kCoefK;  // coalesced over k
     s_c[k][bi] = bi < nb ? __ldg(coef + (b0 + bi) * kCoefK + k) : 0.f;
   }
   __syncthreads();
-  const int col = blockIdx.x * kFmaColsPerCta + threadIdx.x * 4;
-  if (col >= m.NC) return;
+  const int col = blockIdx.x * kFmaColsPerCta + t * 4;
+  const bool in_range = col < m.NC;
   const int NB = m.NB;
-  const float* bp = m.basis + col;
+  const float* bp = m.basis + (in_range ? col : 0);
   const size_t ld = (size_t)m.NC;
 
   float acc[BB][4];
 #pragma unroll
   for (int i = 0; i < BB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
 
-  // pose blend: rows NB .. NB+206
-#pragma unroll 2
-  for (int k = 0; k < kP; ++k) {
+  // this slice of the pose blend: rows NB + [k0, k1)
+  const int k0 = ks * kP / KS, k1 = (ks + 1) * kP / KS;
+#pragma unroll 8
+  for (int k = k0; k < k1; ++k) {
     const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(NB + k) * ld));
 #pragma unroll
     for (int i4 = 0; i4 < BB / 4; ++i4) {
@@ -57,18 +75,45 @@ k_blend_fma(DeviceModel m, const float* __restrict__ coef, long long n, float* _
       }
     }
   }
-  // shape blend + template, then the final add, body by body
+  if (KS > 1) {
+    if (ks > 0) {
+      float* r = s_red + (size_t)(ks - 1) * (BB * 4 * kFmaColThreads) + t;
+#pragma unroll
+      for (int i = 0; i < BB; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[(i * 4 + u) * kFmaColThreads] = acc[i][u];
+    }
+    __syncthreads();
+    if (ks > 0) return;
+#pragma unroll
+    for (int s = 1; s < KS; ++s) {      // fixed slice order
+      const float* r = s_red + (size_t)(s - 1) * (BB * 4 * kFmaColThreads) + t;
+#pragma unroll
+      for (int i = 0; i < BB; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[i][u] = __fadd_rn(acc[i][u], r[(i * 4 + u) * kFmaColThreads]);
+    }
+  }
+  if (!in_range) return;
+
+  // shape blend + template, then the final add, body by body (shapedirs rows held in registers)
   const float4 vt = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(NB + kP) * ld));
+  float4 sv[kMaxBetas];
+#pragma unroll
+  for (int k = 0; k < kMaxBetas; ++k)
+    sv[k] = k < NB ? __ldg(reinterpret_cast<const float4*>(bp + (size_t)k * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
   const int plane = col / m.VP;           // a float4 never straddles planes (VP % 128 == 0)
   const int v = col - plane * m.VP;
 #pragma unroll
   for (int i = 0; i < BB; ++i) {
     if (i >= nb) break;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int k = 0; k < NB; ++k) {
-      const float4 sv = __ldg(reinterpret_cast<const float4*>(bp + (size_t)k * ld));
-      const float c = s_c[k][i];
-      s0 = fmaf(c, sv.x, s0); s1 = fmaf(c, sv.y, s1); s2 = fmaf(c, sv.z, s2); s3 = fmaf(c, sv.w, s3);
+#pragma unroll
+    for (int k = 0; k < kMaxBetas; ++k) {
+      if (k < NB) {
+        const float c = s_c[k][i];
+        s0 = fmaf(c, sv[k].x, s0); s1 = fmaf(c, sv[k].y, s1); s2 = fmaf(c, sv[k].z, s2); s3 = fmaf(c, sv[k].w, s3);
+      }
     }
     float4 o;
     o.x = __fadd_rn(acc[i][0], __fadd_rn(s0, vt.x));
@@ -77,6 +122,20 @@ k_blend_fma(DeviceModel m, const float* __restrict__ coef, long long n, float* _
     o.w = __fadd_rn(acc[i][3], __fadd_rn(s3, vt.w));
     *reinterpret_cast<float4*>(vposed + ((b0 + i) * 3 + plane) * (size_t)m.VP + v) = o;
   }
+}
+
+template <int BB, int KS>
+inline cudaError_t blend_fma_set_smem() {
+  return cudaFuncSetAttribute(k_blend_fma<BB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)BlendFmaCfg<BB, KS>::kSmemBytes);
+}
+
+template <int BB, int KS>
+inline void blend_fma_launch(const DeviceModel& m, const float* coef, long long n, float* vposed,
+                             cudaStream_t s) {
+  using C = BlendFmaCfg<BB, KS>;
+  const unsigned gx = (unsigned)((m.NC + kFmaColsPerCta - 1) / kFmaColsPerCta);
+  k_blend_fma<BB, KS><<<dim3(gx, (unsigned)((n + BB - 1) / BB)), C::kThreads, C::kSmemBytes, s>>>(m, coef, n, vposed);
 }
 
 }  // namespace smplb200

@@ -176,14 +176,10 @@ int launch_chain(const SmplB200Model* m, const float* betas, const float* pose, 
 int launch_blend_fma(const SmplB200Model* m, const float* coef, long long n, float* vposed,
                      cudaStream_t s) {
   if (n == 0) return SMPLB200_OK;
-  const unsigned gx = (unsigned)((m->d.NC + kFmaColsPerCta - 1) / kFmaColsPerCta);
-  if (n <= 8) {
-    k_blend_fma<8><<<dim3(gx, (unsigned)((n + 7) / 8)), kFmaThreads, 0, s>>>(m->d, coef, n, vposed);
-  } else if (n <= 128) {
-    k_blend_fma<16><<<dim3(gx, (unsigned)((n + 15) / 16)), kFmaThreads, 0, s>>>(m->d, coef, n, vposed);
-  } else {
-    k_blend_fma<32><<<dim3(gx, (unsigned)((n + 31) / 32)), kFmaThreads, 0, s>>>(m->d, coef, n, vposed);
-  }
+  // small batches: 4-way K split for parallelism; large fp32 batches: bigger body tiles
+  if (n <= 8) blend_fma_launch<8, 4>(m->d, coef, n, vposed, s);
+  else if (n <= 128) blend_fma_launch<16, 4>(m->d, coef, n, vposed, s);
+  else blend_fma_launch<32, 2>(m->d, coef, n, vposed, s);
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }
@@ -219,6 +215,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // opt-in dynamic shared memory for the tcgen05 kernels (per device, idempotent)
 cudaError_t configure_tc_kernels() {
   cudaError_t e;
+  if ((e = blend_fma_set_smem<8, 4>()) != cudaSuccess) return e;
+  if ((e = blend_fma_set_smem<16, 4>()) != cudaSuccess) return e;
+  if ((e = blend_fma_set_smem<32, 2>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
