@@ -10,7 +10,8 @@
 // independent of how the batch is split.  The K split exists because at N <= 64
 // the op is latency-bound: one serial 207-step loop per thread with ~4 warps per SM left the FMA
 // pipes idle (round-1 launch list: 66 us cold at N = 1); KS = 4 gives 4x the warps and the loads
-// are software-pipelined 8 deep.
+// are software-pipelined 4 deep.  Every batch size uses the same KS, so the summation order -- and
+// therefore every output bit -- is independent of the batch size and of how a batch is sharded.
 //
 // Thread tile: 4 adjacent planar columns x BB bodies.  Per k: one float4 of the basis (coalesced)
 // and BB/4 broadcast LDS.128 of coefficients feed 4*BB FMAs -- the 16 FMA : 1 LDS.128 ratio that
@@ -25,21 +26,22 @@ constexpr int kFmaColsPerCta = kFmaColThreads * 4;
 
 template <int BB, int KS>
 struct BlendFmaCfg {
-  static constexpr int kThreads = kFmaColThreads * KS;
+  static constexpr int kGroups = KS + 1;              // KS pose K-slices + one shape/template group
+  static constexpr int kThreads = kFmaColThreads * kGroups;
   static constexpr int kCoefStride = BB + 4;          // +4: transpose-store conflicts 32-way -> 4-way
   static constexpr size_t kCoefBytes = (size_t)kCoefK * kCoefStride * sizeof(float);
-  static constexpr size_t kRedBytes = (size_t)(KS - 1) * BB * 4 * kFmaColThreads * sizeof(float);
+  static constexpr size_t kRedBytes = (size_t)KS * BB * 4 * kFmaColThreads * sizeof(float);
   static constexpr size_t kSmemBytes = kCoefBytes + kRedBytes;
 };
 
 template <int BB, int KS>
-__global__ void __launch_bounds__(kFmaColThreads * KS)
+__global__ void __launch_bounds__(kFmaColThreads * (KS + 1), 2)
 k_blend_fma(DeviceModel m, const float* __restrict__ coef, long long n, float* __restrict__ vposed) {
   using C = BlendFmaCfg<BB, KS>;
   extern __shared__ __align__(16) float smem_f[];
   float (*s_c)[C::kCoefStride] = reinterpret_cast<float (*)[C::kCoefStride]>(smem_f);  // [k][body]
-  float* s_red = smem_f + kCoefK * C::kCoefStride;                                     // [ks-1][i][t]
-  const int t = threadIdx.x % kFmaColThreads, ks = threadIdx.x / kFmaColThreads;
+  float* s_red = smem_f + kCoefK * C::kCoefStride;                                     // [g-1][i][t]
+  const int t = threadIdx.x % kFmaColThreads, g = threadIdx.x / kFmaColThreads;
   const long long b0 = (long long)blockIdx.y * BB;
   const int nb = (int)min((long long)BB, n - b0);
   for (int idx = threadIdx.x; idx < kCoefK * BB; idx += C::kThreads) {
@@ -57,14 +59,15 @@ k_blend_fma(DeviceModel m, const float* __restrict__ coef, long long n, float* _
 #pragma unroll
   for (int i = 0; i < BB; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
 
-  // this slice of the pose blend: rows NB + [k0, k1)
-  const int k0 = ks * kP / KS, k1 = (ks + 1) * kP / KS;
-#pragma unroll 8
+  // group g < KS: pose rows NB + [k0, k1);  group KS: the NB shape rows (then + template)
+  const int k0 = g < KS ? NB + g * kP / KS : 0;
+  const int k1 = g < KS ? NB + (g + 1) * kP / KS : NB;
+#pragma unroll 4
   for (int k = k0; k < k1; ++k) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(NB + k) * ld));
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + (size_t)k * ld));
 #pragma unroll
     for (int i4 = 0; i4 < BB / 4; ++i4) {
-      const float4 c = *reinterpret_cast<const float4*>(&s_c[NB + k][4 * i4]);
+      const float4 c = *reinterpret_cast<const float4*>(&s_c[k][4 * i4]);
       const float cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -75,52 +78,39 @@ k_blend_fma(DeviceModel m, const float* __restrict__ coef, long long n, float* _
       }
     }
   }
-  if (KS > 1) {
-    if (ks > 0) {
-      float* r = s_red + (size_t)(ks - 1) * (BB * 4 * kFmaColThreads) + t;
+  if (g == KS) {   // v_shaped = shape sum + template
+    const float4 vt = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(NB + kP) * ld));
 #pragma unroll
-      for (int i = 0; i < BB; ++i)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) r[(i * 4 + u) * kFmaColThreads] = acc[i][u];
-    }
-    __syncthreads();
-    if (ks > 0) return;
-#pragma unroll
-    for (int s = 1; s < KS; ++s) {      // fixed slice order
-      const float* r = s_red + (size_t)(s - 1) * (BB * 4 * kFmaColThreads) + t;
-#pragma unroll
-      for (int i = 0; i < BB; ++i)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[i][u] = __fadd_rn(acc[i][u], r[(i * 4 + u) * kFmaColThreads]);
+    for (int i = 0; i < BB; ++i) {
+      acc[i][0] = __fadd_rn(acc[i][0], vt.x); acc[i][1] = __fadd_rn(acc[i][1], vt.y);
+      acc[i][2] = __fadd_rn(acc[i][2], vt.z); acc[i][3] = __fadd_rn(acc[i][3], vt.w);
     }
   }
-  if (!in_range) return;
-
-  // shape blend + template, then the final add, body by body (shapedirs rows held in registers)
-  const float4 vt = __ldg(reinterpret_cast<const float4*>(bp + (size_t)(NB + kP) * ld));
-  float4 sv[kMaxBetas];
+  if (g > 0) {
+    float* r = s_red + (size_t)(g - 1) * (BB * 4 * kFmaColThreads) + t;
 #pragma unroll
-  for (int k = 0; k < kMaxBetas; ++k)
-    sv[k] = k < NB ? __ldg(reinterpret_cast<const float4*>(bp + (size_t)k * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < BB; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[(i * 4 + u) * kFmaColThreads] = acc[i][u];
+  }
+  __syncthreads();
+  if (g > 0 || !in_range) return;
+  // pose slices in slice order, then v_posed = pose sum + v_shaped  (fixed association)
+#pragma unroll
+  for (int s = 1; s <= KS; ++s) {
+    const float* r = s_red + (size_t)(s - 1) * (BB * 4 * kFmaColThreads) + t;
+#pragma unroll
+    for (int i = 0; i < BB; ++i)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[i][u] = __fadd_rn(acc[i][u], r[(i * 4 + u) * kFmaColThreads]);
+  }
   const int plane = col / m.VP;           // a float4 never straddles planes (VP % 128 == 0)
   const int v = col - plane * m.VP;
 #pragma unroll
   for (int i = 0; i < BB; ++i) {
     if (i >= nb) break;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int k = 0; k < kMaxBetas; ++k) {
-      if (k < NB) {
-        const float c = s_c[k][i];
-        s0 = fmaf(c, sv[k].x, s0); s1 = fmaf(c, sv[k].y, s1); s2 = fmaf(c, sv[k].z, s2); s3 = fmaf(c, sv[k].w, s3);
-      }
-    }
-    float4 o;
-    o.x = __fadd_rn(acc[i][0], __fadd_rn(s0, vt.x));
-    o.y = __fadd_rn(acc[i][1], __fadd_rn(s1, vt.y));
-    o.z = __fadd_rn(acc[i][2], __fadd_rn(s2, vt.z));
-    o.w = __fadd_rn(acc[i][3], __fadd_rn(s3, vt.w));
-    *reinterpret_cast<float4*>(vposed + ((b0 + i) * 3 + plane) * (size_t)m.VP + v) = o;
+    *reinterpret_cast<float4*>(vposed + ((b0 + i) * 3 + plane) * (size_t)m.VP + v) =
+        make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
 }
 

@@ -176,10 +176,9 @@ int launch_chain(const SmplB200Model* m, const float* betas, const float* pose, 
 int launch_blend_fma(const SmplB200Model* m, const float* coef, long long n, float* vposed,
                      cudaStream_t s) {
   if (n == 0) return SMPLB200_OK;
-  // small batches: 4-way K split for parallelism; large fp32 batches: bigger body tiles
+  // same 4-way K split for every batch size (bitwise shard invariance); body tile 8 or 16
   if (n <= 8) blend_fma_launch<8, 4>(m->d, coef, n, vposed, s);
-  else if (n <= 128) blend_fma_launch<16, 4>(m->d, coef, n, vposed, s);
-  else blend_fma_launch<32, 2>(m->d, coef, n, vposed, s);
+  else blend_fma_launch<16, 4>(m->d, coef, n, vposed, s);
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }
@@ -217,7 +216,6 @@ cudaError_t configure_tc_kernels() {
   cudaError_t e;
   if ((e = blend_fma_set_smem<8, 4>()) != cudaSuccess) return e;
   if ((e = blend_fma_set_smem<16, 4>()) != cudaSuccess) return e;
-  if ((e = blend_fma_set_smem<32, 2>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
