@@ -66,7 +66,7 @@ def ncu_traffic(kernel: str):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled in the background with host timestamps."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -84,10 +84,15 @@ class ClockSampler:
             self.proc = None
 
     def _pump(self):
+        import datetime
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) >= 7:
-                self.samples.append((time.time(), parts))
+            if len(parts) >= 8:
+                try:  # nvidia-smi's own timestamp: the pipe is block-buffered, read time is useless
+                    t = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    t = time.time()
+                self.samples.append((t, parts[1:]))
 
     def stop(self):
         if self.proc is not None:
