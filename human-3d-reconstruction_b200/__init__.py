@@ -5,10 +5,12 @@ Public surface:
     capi                 ctypes binding of include/smpl_b200.h (libsmpl_b200.so)
     synthetic            seeded SMPL-shaped model tensors / parameters
     sharding             batch sharding across ranks (+ optional NCCL gather of joints)
+    decode_gather        fused NMS + top-K + head gather (the producer of the per-person vectors)
 """
 from . import synthetic  # noqa: F401
 from . import capi  # noqa: F401
 from .smpl import SMPL, GraphedSMPL, HostRunner  # noqa: F401
 from . import sharding  # noqa: F401
+from .decode import decode_gather  # noqa: F401
 
-__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "capi", "synthetic", "sharding"]
+__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "decode_gather", "capi", "synthetic", "sharding"]

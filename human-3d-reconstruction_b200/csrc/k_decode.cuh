@@ -1,0 +1,171 @@
+// Fused decode -> gather: the producer of the SMPL layer's per-person parameter vectors.
+//
+// Replaces, in ONE launch and without the reference's NHWC permute-copy of every head
+// (reference src/lib/models/utils.py:23-27 materialises feat.permute(0,2,3,1).contiguous() per
+// gather), the chain the reference runs before the SMPL layer:
+//     _nms   3x3 max-pool equality mask           reference src/lib/models/decode.py:6-13
+//     _topk  per-class top-K, then top-K of C*K   reference src/lib/models/decode.py:26-41
+//     _transpose_and_gather_feat(head, inds)      reference src/lib/models/utils.py:12-27
+//
+// One CTA per image.  The two-stage top-K of the reference is a global top-K by score, so the
+// kernel selects the K largest NMS-ed values with an MSB-first radix select (3 passes of a
+// 2048-bin shared-memory histogram over order-preserving uint32 keys), collects them, rank-sorts
+// the K survivors by (score descending, flat index ascending) and gathers the head channels
+// straight from NCHW.  Scores are the heat values themselves (heat * keep), so every output is
+// bit-exact against the reference for inputs without score ties (torch.topk leaves the order of
+// equal scores implementation-defined; here equal scores are taken lowest index first).
+#pragma once
+#include "common.cuh"
+
+namespace smplb200 {
+
+constexpr int kDecThreads = 512;
+constexpr int kDecMaxK = 256;
+constexpr int kDecMaxHeads = 8;
+
+struct DecodeHeads {
+  const float* src[kDecMaxHeads];   // [B, ch, H, W]
+  float* dst[kDecMaxHeads];         // [B, K, ch]
+  int ch[kDecMaxHeads];
+  int n;
+};
+
+// NMS-ed value of flat element e = (c, y, x) of one image: heat if it equals its 3x3 max
+// (padding = -inf, i.e. neighbours outside the map are ignored), else heat * 0.
+__device__ __forceinline__ float nms_value(const float* __restrict__ img, int e, int H, int W) {
+  const int hw = H * W;
+  const int c = e / hw, r = e - c * hw, y = r / W, x = r - y * W;
+  const float* p = img + (size_t)c * hw;
+  const float v = __ldg(p + r);
+  float mx = v;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= W) continue;
+      mx = fmaxf(mx, __ldg(p + yy * W + xx));
+    }
+  }
+  return v == mx ? v : __fmul_rn(v, 0.f);
+}
+__device__ __forceinline__ uint32_t sortable_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kDecThreads)
+k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, DecodeHeads heads,
+                float* __restrict__ scores, long long* __restrict__ inds, int* __restrict__ clses,
+                float* __restrict__ ys, float* __restrict__ xs) {
+  __shared__ uint32_t s_hist[2048];
+  __shared__ uint32_t s_key[kDecMaxK];
+  __shared__ int s_idx[kDecMaxK];
+  __shared__ int s_rank_idx[kDecMaxK];
+  __shared__ uint32_t s_prefix, s_need, s_count, s_eq_base;
+  __shared__ uint32_t s_warp_sum[kDecThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hw = H * W, M = C * hw;
+  const float* img = heat + (size_t)b * M;
+
+  // ---- radix select: key T of the K-th largest element and how many == T to take ---------------
+  if (tid == 0) { s_prefix = 0; s_need = (uint32_t)K; }
+  __syncthreads();
+  const int shifts[3] = {21, 10, 0};
+  const uint32_t masks[3] = {0x7ffu, 0x7ffu, 0x3ffu};
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = tid; i < 2048; i += kDecThreads) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const uint32_t hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
+    for (int e = tid; e < M; e += kDecThreads) {
+      const uint32_t key = sortable_key(nms_value(img, e, H, W));
+      if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shifts[pass]) & masks[pass]], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {   // walk the bins from the top until the running count covers `need`
+      uint32_t need = s_need, above = 0;
+      int d = (int)masks[pass];
+      for (; d > 0; --d) {
+        if (above + s_hist[d] >= need) break;
+        above += s_hist[d];
+      }
+      s_need = need - above;
+      s_prefix = prefix | ((uint32_t)d << shifts[pass]);
+    }
+    __syncthreads();
+  }
+  const uint32_t T = s_prefix;         // key of the K-th largest NMS-ed value
+  const uint32_t need_eq = s_need;     // how many elements with key == T belong to the top K
+
+  // ---- collect: everything above T (any order), then == T in flat-index order ------------------
+  if (tid == 0) { s_count = 0; s_eq_base = 0; }
+  __syncthreads();
+  for (int e0 = 0; e0 < M; e0 += kDecThreads) {
+    const int e = e0 + tid;
+    uint32_t key = 0;
+    bool gt = false, eq = false;
+    if (e < M) {
+      key = sortable_key(nms_value(img, e, H, W));
+      gt = key > T; eq = key == T;
+    }
+    if (gt) {
+      const uint32_t slot = atomicAdd(&s_count, 1u);
+      s_key[slot] = key; s_idx[slot] = e;
+    }
+    // ordered selection among the ties: block-wide exclusive scan of the `eq` flags
+    const uint32_t ball = __ballot_sync(0xffffffffu, eq);
+    const uint32_t in_warp = __popc(ball & ((1u << lane) - 1u));
+    if (lane == 0) s_warp_sum[warp] = __popc(ball);
+    __syncthreads();
+    uint32_t before = s_eq_base;
+    for (int w = 0; w < warp; ++w) before += s_warp_sum[w];
+    if (eq && before + in_warp < need_eq) {
+      const uint32_t slot = atomicAdd(&s_count, 1u);
+      s_key[slot] = key; s_idx[slot] = e;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t tot = 0;
+      for (int w = 0; w < kDecThreads / 32; ++w) tot += s_warp_sum[w];
+      s_eq_base += tot;
+    }
+    __syncthreads();
+  }
+
+  // ---- rank sort of the K survivors: score descending, flat index ascending ---------------------
+  if (tid < K) {
+    const uint32_t ki = s_key[tid];
+    const int ei = s_idx[tid];
+    int rank = 0;
+    for (int j = 0; j < K; ++j) {
+      const uint32_t kj = s_key[j];
+      rank += (kj > ki) || (kj == ki && s_idx[j] < ei);
+    }
+    s_rank_idx[rank] = ei;
+    const int cls = ei / hw, r = ei - cls * hw;
+    const size_t o = (size_t)b * K + rank;
+    scores[o] = nms_value(img, ei, H, W);
+    inds[o] = r;
+    clses[o] = cls;
+    ys[o] = (float)(r / W);
+    xs[o] = (float)(r % W);
+  }
+  __syncthreads();
+
+  // ---- gather every head channel at the K peaks, straight from NCHW -----------------------------
+  for (int h = 0; h < heads.n; ++h) {
+    const int ch = heads.ch[h];
+    const float* src = heads.src[h] + (size_t)b * ch * hw;
+    float* dst = heads.dst[h] + (size_t)b * K * ch;
+    for (int i = tid; i < K * ch; i += kDecThreads) {
+      const int k = i / ch, c = i - k * ch;
+      const int e = s_rank_idx[k];
+      dst[i] = __ldg(src + (size_t)c * hw + (e % hw));
+    }
+  }
+}
+
+}  // namespace smplb200

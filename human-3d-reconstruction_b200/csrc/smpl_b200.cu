@@ -20,6 +20,7 @@
 #include "k_lbs_fma.cuh"
 #include "k_blend_tc.cuh"
 #include "k_lbs_tc.cuh"
+#include "k_decode.cuh"
 
 using namespace smplb200;
 
@@ -666,6 +667,33 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
 
   if (p.regressed && (joints || kp2d)) st = launch_regress(model, vertices, n, jbuf, cam, kp2d, s);
   return st;
+}
+
+int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int32_t num_classes,
+                           int32_t height, int32_t width, const float* const* heads,
+                           const int32_t* head_channels, int32_t num_heads, int32_t k,
+                           float* scores, int64_t* inds, int32_t* clses, float* ys, float* xs,
+                           float* const* gathered, void* stream) {
+  if (batch < 0 || num_classes < 1 || height < 1 || width < 1 || num_heads < 0 ||
+      num_heads > kDecMaxHeads || k < 1 || k > kDecMaxK)
+    return SMPLB200_ERR_INVALID_ARG;
+  if ((long long)num_classes * height * width < k || (long long)num_classes * height * width > (1LL << 30))
+    return SMPLB200_ERR_INVALID_ARG;
+  if (batch == 0) return SMPLB200_OK;
+  if (!heat || !scores || !inds || !clses || !ys || !xs) return SMPLB200_ERR_INVALID_ARG;
+  if (num_heads > 0 && (!heads || !head_channels || !gathered)) return SMPLB200_ERR_INVALID_ARG;
+  DecodeHeads dh{};
+  dh.n = num_heads;
+  for (int h = 0; h < num_heads; ++h) {
+    if (!heads[h] || !gathered[h] || head_channels[h] < 1) return SMPLB200_ERR_INVALID_ARG;
+    dh.src[h] = heads[h]; dh.dst[h] = gathered[h]; dh.ch[h] = head_channels[h];
+  }
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  k_decode_gather<<<(unsigned)batch, kDecThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      heat, num_classes, height, width, k, dh, scores, reinterpret_cast<long long*>(inds), clses, ys, xs);
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
 }
 
 size_t smplb200_host_staging_bytes(const SmplB200Model* model, int64_t n, uint32_t flags) {

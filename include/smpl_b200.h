@@ -163,6 +163,21 @@ int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A
 int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, int64_t n,
                             float* joints, const float* cam, float* kp2d, void* stream);
 
+/* ---- the producer of the per-person vectors ------------------------ */
+/* Fused NMS + top-K + head gather, one launch:
+ *   heat [B,C,H,W] (sigmoid-ed centre heat map), heads[h] [B,ch_h,H,W] (NCHW, e.g. pose72/shape10/cam3)
+ *   -> scores[B,K], inds[B,K] (int64 index into H*W), clses[B,K] (int32), ys[B,K], xs[B,K],
+ *      gathered[h] [B,K,ch_h]
+ * Replaces: _nms + _topk (reference src/lib/models/decode.py:6-13, 26-41) followed by
+ * _transpose_and_gather_feat per head (reference src/lib/models/utils.py:12-27), as called at
+ * reference src/lib/models/decode.py:80-88.  `heads`, `head_channels`, `gathered` are HOST arrays of
+ * `num_heads` (<= 8) entries holding DEVICE pointers; 1 <= k <= 256; bit-exact for tie-free scores. */
+int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int32_t num_classes,
+                           int32_t height, int32_t width, const float* const* heads,
+                           const int32_t* head_channels, int32_t num_heads, int32_t k,
+                           float* scores, int64_t* inds, int32_t* clses, float* ys, float* xs,
+                           float* const* gathered, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------- */
 const char* smplb200_strerror(int status);
 int smplb200_version(void);

@@ -1,0 +1,68 @@
+"""CPU oracle for the decode -> gather producer of the SMPL path -- TEST INFRASTRUCTURE.
+
+Restates, in plain torch, the reference functions that turn head maps into per-person parameter
+vectors (the caller of the SMPL layer in inference):
+
+  * `_nms`                       reference src/lib/models/decode.py:6-13
+  * `_topk`                      reference src/lib/models/decode.py:26-41
+  * `_gather_feat`               reference src/lib/models/utils.py:12-21
+  * `_transpose_and_gather_feat` reference src/lib/models/utils.py:23-27
+
+PARITY PINNED: unlike the SMPL layer these functions exist in the reference snapshot.
+tests/golden/decode_golden_v1.npz holds outputs of the UNMODIFIED reference functions (generated in
+the build container by tests/golden/make_decode_golden.py, which imports /root/reference) and
+tests/test_decode_oracle.py checks this restatement against them bit for bit.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def nms(heat: torch.Tensor, kernel: int = 3) -> torch.Tensor:
+    """Keep a value where it equals the max of its kernel x kernel neighbourhood, else heat*0."""
+    pad = (kernel - 1) // 2
+    hmax = F.max_pool2d(heat, (kernel, kernel), stride=1, padding=pad)
+    keep = (hmax == heat).float()
+    return heat * keep
+
+
+def gather_feat(feat: torch.Tensor, ind: torch.Tensor) -> torch.Tensor:
+    """feat [B, M, C], ind [B, K] -> [B, K, C]."""
+    dim = feat.size(2)
+    ind = ind.unsqueeze(2).expand(ind.size(0), ind.size(1), dim)
+    return feat.gather(1, ind)
+
+
+def transpose_and_gather_feat(feat: torch.Tensor, ind: torch.Tensor) -> torch.Tensor:
+    """feat [B, C, H, W] (NCHW), ind [B, K] into H*W -> [B, K, C]."""
+    feat = feat.permute(0, 2, 3, 1).contiguous()
+    feat = feat.view(feat.size(0), -1, feat.size(3))
+    return gather_feat(feat, ind)
+
+
+def topk(scores: torch.Tensor, K: int):
+    """Two-stage top-K: per class over H*W, then over the C*K survivors."""
+    batch, cat, height, width = scores.size()
+    topk_scores, topk_inds = torch.topk(scores.view(batch, cat, -1), K)
+    topk_inds = topk_inds % (height * width)
+    topk_ys = torch.div(topk_inds, width, rounding_mode="floor").int().float()
+    topk_xs = (topk_inds % width).int().float()
+    topk_score, topk_ind = torch.topk(topk_scores.view(batch, -1), K)
+    topk_clses = torch.div(topk_ind, K, rounding_mode="floor").int()
+    topk_inds = gather_feat(topk_inds.view(batch, -1, 1), topk_ind).view(batch, K)
+    topk_ys = gather_feat(topk_ys.view(batch, -1, 1), topk_ind).view(batch, K)
+    topk_xs = gather_feat(topk_xs.view(batch, -1, 1), topk_ind).view(batch, K)
+    return topk_score, topk_inds, topk_clses, topk_ys, topk_xs
+
+
+def decode_gather(heat: torch.Tensor, heads, K: int):
+    """heat [B,C,H,W] (already sigmoid-ed, as the reference's decode expects) and a list of head
+    maps [B,Ch,H,W] -> (scores[B,K], inds[B,K] int64, clses[B,K] int32, ys[B,K], xs[B,K],
+    [gathered_h [B,K,Ch] ...]) exactly as `multi_pose_decode` obtains them
+    (reference src/lib/models/decode.py:77-88)."""
+    heat = nms(heat)
+    scores, inds, clses, ys, xs = topk(heat, K)
+    return scores, inds, clses, ys, xs, [transpose_and_gather_feat(h, inds) for h in heads]
