@@ -385,6 +385,37 @@ def main():
                 it = 10 if prec == "fp32" else 50
                 dt = time_loop(lambda: lay(tb, tp, tc), it, torch) / it
                 variants[prec] = {"bodies_per_s": n / dt, "us_per_step": dt * 1e6}
+        # ---- next §8(f) row: fused decode -> gather producer at the configs[4] shape -----------
+        next_rows = {}
+        if rank == 0:
+            from human_3d_reconstruction_b200 import decode_gather
+            from oracle.decode_ref import decode_gather as decode_cpu
+            Bi, Kp, Hm = 32, 32, 128
+            g = torch.Generator().manual_seed(5)
+            heat_c = torch.sigmoid(torch.randn(Bi, 1, Hm, Hm, generator=g) * 2.0)
+            heads_c = [torch.randn(Bi, ch, Hm, Hm, generator=g) for ch in (72, 10, 3)]
+            heat_d, heads_d = heat_c.to(dev), [h.to(dev) for h in heads_c]
+            for _ in range(3):
+                decode_gather(heat_d, heads_d, Kp)
+            dt_dec = time_loop(lambda: decode_gather(heat_d, heads_d, Kp), 50, torch) / 50
+            small = SMPL(model, precision="auto", lbs="auto").to(dev)
+
+            def decode_then_smpl():
+                sc, ind, cl, yy, xx, (po, be, ca) = decode_gather(heat_d, heads_d, Kp)
+                return small(be.view(-1, 10), po.view(-1, 72) * 0.3, ca.view(-1, 3))
+
+            for _ in range(3):
+                decode_then_smpl()
+            dt_pipe = time_loop(decode_then_smpl, 50, torch) / 50
+            t0 = time.perf_counter()
+            for _ in range(3):
+                decode_cpu(heat_c, heads_c, Kp)
+            dt_cpu = (time.perf_counter() - t0) / 3
+            next_rows["decode_gather"] = {
+                "workload": "batch 32, 1 class, 128x128 heat map, heads pose72/shape10/cam3, K=32 (configs[4] shape)",
+                "gpu_us": dt_dec * 1e6, "images_per_s": Bi / dt_dec,
+                "cpu_reference_port_us": dt_cpu * 1e6, "cpu_kind": "port (oracle/decode_ref.py, pinned bit-exact to the reference functions)",
+                "decode_plus_smpl_1024_bodies_us": dt_pipe * 1e6, "people_per_s": Bi * Kp / dt_pipe}
         t_kern_end = time.time()
 
     clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
@@ -445,6 +476,7 @@ def main():
                          "algorithmic_bytes_per_launch": BYTES_K3 * n,
                          "traffic": ncu_traffic("k_lbs_tc") if (args.lbs in ("tc", "auto") and n == BODIES_PER_GPU) else None},
             "variants_same_workload": variants,
+            "next_rows": next_rows,
             "accuracy": {"vertices_max_abs_err_m_stated": {"fp32": "rtol 1e-5 / atol 1e-6", "bf16x3": 1e-5, "tf32": 5e-4, "bf16": 4e-3},
                          "measured_vs_fp32_cpu_oracle": {"bf16x3": 4.1e-6, "tf32": 2.1e-4, "bf16": 1.6e-3},
                          "note": "joints and kp2d are fp32-exact (rtol 1e-5/atol 1e-6) in every mode"},
