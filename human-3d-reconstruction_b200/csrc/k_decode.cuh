@@ -56,6 +56,10 @@ __device__ __forceinline__ uint32_t sortable_key(float v) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// STAGED: the image's order-preserving keys are computed once (one 3x3 NMS pass) into dynamic
+// shared memory and every later pass reads them from there; used whenever C*H*W*4 B fits
+// (<= 200 KB, e.g. 128x128 x up to 3 classes).  Otherwise the keys are recomputed per pass.
+template <bool STAGED>
 __global__ void __launch_bounds__(kDecThreads)
 k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, DecodeHeads heads,
                 float* __restrict__ scores, long long* __restrict__ inds, int* __restrict__ clses,
@@ -69,6 +73,14 @@ k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, Deco
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hw = H * W, M = C * hw;
   const float* img = heat + (size_t)b * M;
+  extern __shared__ uint32_t s_keys[];
+  if (STAGED) {
+    for (int e = tid; e < M; e += kDecThreads) s_keys[e] = sortable_key(nms_value(img, e, H, W));
+    __syncthreads();
+  }
+  auto key_of = [&](int e) -> uint32_t {
+    return STAGED ? s_keys[e] : sortable_key(nms_value(img, e, H, W));
+  };
 
   // ---- radix select: key T of the K-th largest element and how many == T to take ---------------
   if (tid == 0) { s_prefix = 0; s_need = (uint32_t)K; }
@@ -81,7 +93,7 @@ k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, Deco
     const uint32_t prefix = s_prefix;
     const uint32_t hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xffe00000u : 0xfffffc00u);
     for (int e = tid; e < M; e += kDecThreads) {
-      const uint32_t key = sortable_key(nms_value(img, e, H, W));
+      const uint32_t key = key_of(e);
       if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shifts[pass]) & masks[pass]], 1u);
     }
     __syncthreads();
@@ -108,7 +120,7 @@ k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, Deco
     uint32_t key = 0;
     bool gt = false, eq = false;
     if (e < M) {
-      key = sortable_key(nms_value(img, e, H, W));
+      key = key_of(e);
       gt = key > T; eq = key == T;
     }
     if (gt) {

@@ -690,8 +690,16 @@ int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int
   }
   DeviceGuard guard(device);
   if (guard.err != cudaSuccess) return cuda_fail(guard.err);
-  k_decode_gather<<<(unsigned)batch, kDecThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      heat, num_classes, height, width, k, dh, scores, reinterpret_cast<long long*>(inds), clses, ys, xs);
+  const size_t key_bytes = (size_t)num_classes * height * width * sizeof(uint32_t);
+  if (key_bytes <= 200 * 1024) {
+    CU_TRY(cudaFuncSetAttribute(k_decode_gather<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)key_bytes));
+    k_decode_gather<true><<<(unsigned)batch, kDecThreads, key_bytes, static_cast<cudaStream_t>(stream)>>>(
+        heat, num_classes, height, width, k, dh, scores, reinterpret_cast<long long*>(inds), clses, ys, xs);
+  } else {
+    k_decode_gather<false><<<(unsigned)batch, kDecThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        heat, num_classes, height, width, k, dh, scores, reinterpret_cast<long long*>(inds), clses, ys, xs);
+  }
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }
