@@ -36,6 +36,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner
+# to fd 1), so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 BODIES_PER_GPU = 4096
 BYTES_E2E = 83_500          # per body: 340 in + 83,160 out
 BYTES_K1 = 83_020           # write vposed 82,680 + read coefficients 340
@@ -184,7 +194,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -484,7 +494,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
