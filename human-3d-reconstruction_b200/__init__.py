@@ -8,9 +8,10 @@ Public surface:
     decode_gather        fused NMS + top-K + head gather (the producer of the per-person vectors)
 """
 from . import synthetic  # noqa: F401
+from . import model_io  # noqa: F401
 from . import capi  # noqa: F401
 from .smpl import SMPL, GraphedSMPL, HostRunner  # noqa: F401
 from . import sharding  # noqa: F401
 from .decode import decode_gather  # noqa: F401
 
-__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "decode_gather", "capi", "synthetic", "sharding"]
+__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "decode_gather", "capi", "synthetic", "sharding", "model_io"]

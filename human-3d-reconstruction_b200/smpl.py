@@ -22,7 +22,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import capi, synthetic
+from . import capi, model_io, synthetic
 
 _BUFFERS = ("v_template", "shapedirs", "posedirs", "J_regressor", "weights")
 
@@ -51,9 +51,10 @@ class SMPL(nn.Module):
     """SMPL body model on B200.
 
     Args:
-      model: dict (or path to an .npz) with ``v_template[V,3]``, ``shapedirs[NB,3V]``,
-             ``posedirs[207,3V]``, ``J_regressor[V,24]``, ``weights[V,24]``, ``parents[24]``
-             in the eager layer's layouts.
+      model: dict, or path to an ``.npz``/pickle, with ``v_template[V,3]``, ``shapedirs[NB,3V]``,
+             ``posedirs[207,3V]``, ``J_regressor[V,24]``, ``weights[V,24]``, ``parents[24]`` in the
+             eager layer's layouts -- or the official SMPL file layout
+             (``shapedirs[V,3,NB]``, ``J_regressor[24,V]`` dense/sparse, ``kintree_table``), see model_io.
       precision: 'auto' | 'fp32' | 'bf16' | 'tf32' | 'bf16x3'  (blendshape operands)
       joints: 'kinematic' (J_posed of the chain, default) | 'regressed' (HMR-style, from vertices)
       rotate_base: HMR's root pre-rotation by diag(1,-1,-1); default False
@@ -62,9 +63,10 @@ class SMPL(nn.Module):
 
     def __init__(self, model, precision="auto", joints="kinematic", rotate_base=False, lbs="auto"):
         super().__init__()
-        if isinstance(model, (str, bytes)):
-            with np.load(model) as z:
-                model = {k: z[k] for k in z.files}
+        if isinstance(model, (str, bytes)):      # .npz / pickle, official SMPL layout or the eager layer's
+            model = model_io.load_model(model)
+        elif "kintree_table" in model or np.asarray(model["shapedirs"]).ndim == 3:
+            model = model_io.from_official_layout(model)
         for k in _BUFFERS:
             self.register_buffer(k, torch.as_tensor(np.asarray(model[k], dtype=np.float32)).clone())
         self.register_buffer(
