@@ -18,7 +18,6 @@ struct DeviceModel {
   int max_nnz;                     // max skinning weights per vertex
   int max_depth;                   // kinematic tree depth
   int jreg_nnz;                    // total non-zeros of the joint regressor
-  int tune;                        // wait-policy bits for the tcgen05 kernels (bit0 epilogue, bit1 producer back-off)
   const float* basis;              // [KB, NC] planar, row NB+207 = v_template
   const float* j_template;         // [J*3]   folded J_regressor^T v_template
   const float* j_shapedirs;        // [NB, J*3] folded J_regressor^T shapedirs

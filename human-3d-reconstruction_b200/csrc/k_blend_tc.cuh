@@ -70,8 +70,7 @@ template <uint32_t PREC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ basis_lo,
            const uint8_t* __restrict__ coef_hi, const uint8_t* __restrict__ coef_lo,
-           long long n, int nblocks, long long total_units, int NC, float* __restrict__ vposed,
-           int tune) {
+           long long n, int nblocks, long long total_units, int NC, float* __restrict__ vposed) {
   using C = BlendTcCfg<PREC>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
@@ -206,7 +205,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
         if (lane == 0) ptx::mbar_arrive(bar_a);
         __syncwarp();
       }
-      ptx::mbar_wait_relaxed(bar_tfull + a, (i / kTcAccBufs) & 1, tune & 1);
+      ptx::mbar_wait(bar_tfull + a, (i / kTcAccBufs) & 1);
       ptx::tc_fence_after();
       const long long b0 = (long long)blk * kCoefBlock;
       const int col = (int)tile * 128 + q * 32 + lane;    // planar column owned by this thread
@@ -293,7 +292,7 @@ inline void blend_tc_launch(const DeviceModel& m, int num_sms, const void* chi, 
   const uint32_t* bh = C::kTf32 ? m.basis_rows_tf32 : m.basis_rows_bf16_hi;
   k_blend_tc<PREC><<<grid, kTcThreads, C::kSmemBytes, s>>>(
       bh, m.basis_rows_bf16_lo, static_cast<const uint8_t*>(chi), static_cast<const uint8_t*>(clo), n,
-      nblocks, total, m.NC, vposed, m.tune);
+      nblocks, total, m.NC, vposed);
 }
 
 inline cudaError_t launch_blend_tc(const DeviceModel& m, int num_sms, uint32_t prec,

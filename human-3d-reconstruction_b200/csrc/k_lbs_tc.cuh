@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kLbsTcThreads, 1)
 k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
          const float* __restrict__ vposed, long long n, int nblocks, int blocks_per_cta,
          int V, int VP, float* __restrict__ verts, const float* __restrict__ joints_in,
-         const float* __restrict__ cam, float* __restrict__ kp2d, int tune) {
+         const float* __restrict__ cam, float* __restrict__ kp2d) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sV = smem + kLbsVOff;
@@ -105,7 +105,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         const int s = i % kLbsVStages;
         const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
         const int nb = (int)min((long long)kLbsBlock, n - b0);
-        const int nrows = (tune & 2) ? 1 : nb * 3;   // experiment knob: bit1 = load a single row
+        const int nrows = nb * 3;
         ptx::mbar_wait(bar_vempty + s, ((i / kLbsVStages) & 1) ^ 1);
         if (lane == 0) ptx::mbar_arrive_expect_tx(bar_vfull + s, (uint32_t)nrows * row_bytes);
         __syncwarp();
@@ -149,7 +149,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
 #pragma unroll
             for (int ks = 0; ks < 3; ++ks) {  // 24 joints = 3 tf32 k-steps of 8
               const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * kLboB, kLboB, kSbo);
-              if (!(tune & 4)) ptx::mma_tf32_ts(d_tmem, wp + ks * 8, bd, kLbsIdesc, acc);   // bit2 = no MMA
+              ptx::mma_tf32_ts(d_tmem, wp + ks * 8, bd, kLbsIdesc, acc);
               acc = 1;
             }
           }
@@ -237,8 +237,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
           sb[2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
         }
         __syncwarp();
-        if (full && (tune & 1)) {   // experiment knob: bit0 = no vertex stores
-        } else if (full) {          // fast path: whole block, whole warp -> unpredicated stores
+        if (full) {                 // fast path: whole block, whole warp -> unpredicated stores
           float o[12];
 #pragma unroll
           for (int bb = 0; bb < 4; ++bb) {
@@ -327,7 +326,7 @@ inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float*
   const dim3 grid((unsigned)cta_x, (unsigned)((nblocks + bpc - 1) / bpc));
   k_lbs_tc<<<grid, kLbsTcThreads, kLbsSmemBytes, s>>>(
       m.w_tf32, reinterpret_cast<const uint8_t*>(a_img), vposed, n, nblocks, bpc, m.V, m.VP, verts,
-      joints_in, cam, kp2d, m.tune);
+      joints_in, cam, kp2d);
   return cudaGetLastError();
 }
 

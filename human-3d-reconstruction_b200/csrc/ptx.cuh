@@ -54,10 +54,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity, 1000000u)) return;   // up to 1 ms asleep per attempt
   __trap();
 }
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, bool = true) {
-  mbar_wait(bar, parity);
-}
-
 // ---- bulk TMA: global -> shared, completion counted on an mbarrier --------------------------
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                          uint64_t* bar) {

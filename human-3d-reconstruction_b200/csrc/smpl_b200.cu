@@ -438,7 +438,6 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     DeviceModel& d = m->d;
     d.V = V; d.VP = VP; d.NB = NB; d.KB = KB; d.NC = NC;
     d.max_nnz = max_nnz; d.max_depth = max_depth; d.jreg_nnz = (int)jval.size();
-    { const char* t = std::getenv("SMPLB200_TUNE"); d.tune = t ? std::atoi(t) : 0; }
     {  // bodies per k1->k3 pass: keeps the vposed intermediate L2-resident (multiple of 128)
       const char* t = std::getenv("SMPLB200_CHUNK");
       int c = t ? std::atoi(t) : kDefaultChunk;
