@@ -22,6 +22,7 @@ struct ChainOut {
   uint16_t* coef_bf16_hi; // tensor-core operand images (null unless a tcgen05 path follows)
   uint16_t* coef_bf16_lo;
   uint32_t* coef_tf32;
+  uint32_t* a_tf32;       // [n/8 blocks][12 chunks][96 rows][4] tf32 hi|lo image of A (LBS blend)
 };
 
 __device__ __forceinline__ void rodrigues_hmr(float tx, float ty, float tz, float R[9]) {
@@ -213,6 +214,25 @@ k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __rest
       im[(size_t)c * kCoefBlock + row] =
           make_uint4(f32_to_tf32_rn(sc[4 * c]), f32_to_tf32_rn(sc[4 * c + 1]),
                      f32_to_tf32_rn(sc[4 * c + 2]), f32_to_tf32_rn(sc[4 * c + 3]));
+  }
+  if (out.a_tf32) {
+    // B operand of the blend MMA: rows n = (body_in_block*12 + e), K = 48 = [A_hi | A_lo];
+    // chunk c (0..11) holds joints 4(c%6)..4(c%6)+3 of part c/6 for every row.
+    const long long blk = b / kLbsBlock; const int bi = int(b % kLbsBlock);
+    constexpr int rows = kLbsBlock * 12;
+    uint4* im = reinterpret_cast<uint4*>(out.a_tf32 + blk * (long long)(kLbsK * rows));
+    for (int item = lane; item < 12 * 12; item += 32) {
+      const int c = item / 12, e = item % 12;
+      const int j0 = 4 * (c % 6);
+      uint32_t w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v = sa[(j0 + u) * 12 + e];
+        const uint32_t hi = f32_to_tf32_rn(v);
+        w[u] = c < 6 ? hi : f32_to_tf32_rn(__fsub_rn(v, __uint_as_float(hi)));
+      }
+      im[(size_t)c * rows + bi * 12 + e] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
 }
 

@@ -14,11 +14,9 @@
 // tf32 x tf32 products are exact in the fp32 accumulator, so the blend error is ~1e-7 relative,
 // the same order as an fp32 FMA chain.  W' = [W_hi | W_lo] rows of a 128-vertex tile are RESIDENT
 // IN TENSOR MEMORY as the MMA A operand (no shared-memory re-reads); A' = [A_hi | A_lo] per
-// 8-body block is the B operand.  The block's fp32 joint transforms (9 KB, written by k2) arrive
-// by bulk TMA and two converter warps split them into the K-major tf32 hi|lo image in shared
-// memory (generic-proxy stores + fence.proxy.async) -- streaming the pre-split image instead cost
-// twice the SM<->L2 bytes for this operand, and that crossbar is what bounds the kernel.  The
-// block's planar vposed rows stream through their own 4-stage bulk-TMA ring from HBM.  The kernel is bound by L2 throughput (~8 TB/s of operand re-reads +
+// 8-body block (written by k2) is the B operand.  Both A' and the block's planar vposed rows
+// stream through bulk-TMA / mbarrier rings with their own producer warps (A': 2 stages from L2;
+// vposed: 4 stages from HBM).  The kernel is bound by L2 throughput (~8 TB/s of operand re-reads +
 // vposed + vertex traffic; round-1 ablation: 73 us with MMAs, loads and stores all disabled), so
 // each CTA blends TWO adjacent vertex tiles per A' stage (2 x W' in TMEM, 4 accumulators): the A'
 // re-read traffic halves and every vposed TMA row is 1 KB.  The grid is tile-pair-fastest: the
@@ -36,46 +34,39 @@
 namespace smplb200 {
 
 constexpr int kLbsTiles = 2;                             // vertex tiles per CTA sharing one B stage
-// warp roles: 0 = vposed TMA producer, 1 = MMA issuer, 2..3 = raw-A TMA + tf32 hi|lo converters,
-// 4..19 = epilogue
-constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpCvt0 = 2, kLbsCvtWarps = 2;
+constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 2;   // warp 3 idle; epilogue = warps 4..19
 constexpr int kLbsEpiWarp0 = 4;
 constexpr int kLbsEpiWarps = 8 * kLbsTiles;              // per tile: two per TMEM lane quarter, 4 bodies each
 constexpr int kLbsTcThreads = (kLbsEpiWarp0 + kLbsEpiWarps) * 32;    // 640
-constexpr int kLbsBStages = 2;                           // converted A' images (MMA B operand)
-constexpr int kLbsRStages = 4;                           // raw fp32 A blocks (L2-resident)
+constexpr int kLbsBStages = 4;                           // A' images (L2-resident)
 constexpr int kLbsVStages = 4;                           // vposed rows come from HBM: deep ring
 constexpr int kLbsTcAcc = 2;
 constexpr int kLbsN = kLbsBlock * 12;                    // 96
 constexpr int kLbsTmemCols = 512;                        // 2 tiles x 2 x 96 accumulators + 2 x 48 of W'
 constexpr int kLbsAccCols = kLbsTiles * kLbsTcAcc * kLbsN;   // 384
 constexpr uint32_t kLbsBStage = kLbsK * kLbsN * 4;       // 18,432  tf32 hi|lo image of A, one block
-constexpr uint32_t kLbsRStage = kLbsBlock * kJ * 12 * 4; //  9,216  fp32 A of one block
 constexpr uint32_t kLbsVRow = kLbsTiles * 128 * 4;       // one (body, plane) row of the tile pair: 1 KB
 constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 24,576
-constexpr uint32_t kLbsROff = kLbsBStages * kLbsBStage;
-constexpr uint32_t kLbsVOff = kLbsROff + kLbsRStages * kLbsRStage;
+constexpr uint32_t kLbsVOff = kLbsBStages * kLbsBStage;
 constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsVStages * kLbsVStage;
 constexpr uint32_t kLbsBarOff = kLbsOutOff + kLbsEpiWarps * 4 * 96 * 4;   // per warp: 4 bodies x 96 floats
-constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~197 KB, one CTA per SM
+constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~160 KB, one CTA per SM
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
 __global__ void __launch_bounds__(kLbsTcThreads, 1)
-k_lbs_tc(const uint32_t* __restrict__ w_rows, const float* __restrict__ A,
+k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
          const float* __restrict__ vposed, long long n, int nblocks, int blocks_per_cta,
          int V, int VP, float* __restrict__ verts, const float* __restrict__ joints_in,
          const float* __restrict__ cam, float* __restrict__ kp2d) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
-  uint8_t* sR = smem + kLbsROff;
   uint8_t* sV = smem + kLbsVOff;
   float* sOut = reinterpret_cast<float*>(smem + kLbsOutOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLbsBarOff);
   uint64_t* bar_w = bars;                            // W' rows resident in TMEM (8 warp arrivals)
-  uint64_t* bar_bfull = bars + 1;                    // [B stages] A' image converted (2 warp arrivals)
+  uint64_t* bar_bfull = bars + 1;                    // [B stages] A' image landed
   uint64_t* bar_bempty = bar_bfull + kLbsBStages;    // [B stages] MMAs reading it retired
-  uint64_t* bar_rfull = bar_bempty + kLbsBStages;    // [R stages] raw fp32 A block landed
-  uint64_t* bar_vfull = bar_rfull + kLbsRStages;     // [V stages] vposed rows landed
+  uint64_t* bar_vfull = bar_bempty + kLbsBStages;    // [V stages] vposed rows landed
   uint64_t* bar_vempty = bar_vfull + kLbsVStages;    // [V stages] epilogue warps done with them
   uint64_t* bar_tfull = bar_vempty + kLbsVStages;    // [acc] accumulators (both tiles) ready
   uint64_t* bar_tempty = bar_tfull + kLbsTcAcc;      // [acc] accumulators drained
@@ -91,8 +82,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const float* __restrict__ A,
 
   if (warp == kLbsWarpTmaV && lane == 0) {
     ptx::mbar_init(bar_w, 4 * kLbsTiles);
-    for (int s = 0; s < kLbsBStages; ++s) { ptx::mbar_init(bar_bfull + s, kLbsCvtWarps); ptx::mbar_init(bar_bempty + s, 1); }
-    for (int s = 0; s < kLbsRStages; ++s) ptx::mbar_init(bar_rfull + s, 1);
+    for (int s = 0; s < kLbsBStages; ++s) { ptx::mbar_init(bar_bfull + s, 1); ptx::mbar_init(bar_bempty + s, 1); }
     for (int s = 0; s < kLbsVStages; ++s) { ptx::mbar_init(bar_vfull + s, 1); ptx::mbar_init(bar_vempty + s, kLbsEpiWarps); }
     for (int a = 0; a < kLbsTcAcc; ++a) { ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, kLbsEpiWarps); }
     ptx::fence_barrier_init();
@@ -126,51 +116,16 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const float* __restrict__ A,
         __syncwarp();
       }
     }
-  } else if (warp >= kLbsWarpCvt0 && warp < kLbsWarpCvt0 + kLbsCvtWarps) {
-    // ===== raw-A TMA producer + converters: fp32 A block -> K-major tf32 hi|lo image (B operand).
-    // image[chunk c][row r][4]: chunk c holds joints 4(c%6)..+3 of part c/6 (hi | lo), row r =
-    // body*12 + e.  Each item converts one (c%6, r) pair: 4 raw values -> one hi and one lo 16-byte
-    // chunk.  64 threads x 9 items per block.
-    const int ct = (warp - kLbsWarpCvt0) * 32 + lane;          // 0..63
-    const bool issuer = (warp == kLbsWarpCvt0 && lane == 0);
-    auto load_raw = [&](int i) {
-      const int s = i % kLbsRStages;
-      const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
-      const uint32_t bytes = (uint32_t)min((long long)kLbsBlock, n - b0) * (kJ * 12 * 4);
-      ptx::mbar_arrive_expect_tx(bar_rfull + s, bytes);
-      ptx::bulk_g2s(sR + (size_t)s * kLbsRStage, A + (size_t)b0 * (kJ * 12), bytes, bar_rfull + s);
-    };
-    if (issuer)
-      for (int i = 0; i < min(nblk, kLbsRStages); ++i) load_raw(i);
-    for (int i = 0; i < nblk; ++i) {
-      const int sr = i % kLbsRStages, sb = i % kLbsBStages;
-      ptx::mbar_wait(bar_rfull + sr, (i / kLbsRStages) & 1);
-      ptx::mbar_wait(bar_bempty + sb, ((i / kLbsBStages) & 1) ^ 1);
-      const float* raw = reinterpret_cast<const float*>(sR + (size_t)sr * kLbsRStage);
-      uint4* img = reinterpret_cast<uint4*>(sB + (size_t)sb * kLbsBStage);
-#pragma unroll
-      for (int it = 0; it < (6 * kLbsN) / (kLbsCvtWarps * 32); ++it) {
-        const int item = it * (kLbsCvtWarps * 32) + ct;         // 0..575
-        const int c6 = item / kLbsN, r = item - c6 * kLbsN;
-        const int bi = r / 12, e = r - bi * 12;
-        const float* src = raw + bi * (kJ * 12) + (4 * c6) * 12 + e;
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float v = src[u * 12];
-          hi[u] = f32_to_tf32_rn(v);
-          lo[u] = f32_to_tf32_rn(__fsub_rn(v, __uint_as_float(hi[u])));
-        }
-        img[c6 * kLbsN + r] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        img[(c6 + 6) * kLbsN + r] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  } else if (warp == kLbsWarpTmaB) {
+    // ===== bulk-TMA producer 2: tf32 hi|lo image of the block's joint transforms (L2-resident) =====
+    if (lane == 0) {
+      for (int i = 0; i < nblk; ++i) {
+        const int s = i % kLbsBStages;
+        ptx::mbar_wait(bar_bempty + s, ((i / kLbsBStages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(bar_bfull + s, kLbsBStage);
+        ptx::bulk_g2s(sB + (size_t)s * kLbsBStage, a_img + (size_t)(blk_begin + i) * kLbsBStage, kLbsBStage,
+                      bar_bfull + s);
       }
-      // generic-proxy stores -> visible to the tensor core (async proxy), then publish the stage
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar_bfull + sb);
-      // both converter warps are done with the raw slot before it is refilled
-      asm volatile("bar.sync 1, 64;" ::: "memory");
-      if (issuer && i + kLbsRStages < nblk) load_raw(i + kLbsRStages);
     }
   } else if (warp == kLbsWarpMma) {
     // ===== MMA issuer: one B stage feeds the blend MMAs of BOTH vertex tiles =====
@@ -326,6 +281,23 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const float* __restrict__ A,
   if (warp == kLbsWarpMma) ptx::tmem_dealloc(tmem_base, kLbsTmemCols);
 }
 
+// fp32 A [n,24,12] -> tf32 hi|lo operand image (stand-alone k3 entry point only).
+__global__ void __launch_bounds__(256)
+k_pack_a(const float* __restrict__ A, long long n, uint32_t* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * (kJ * 12)) return;
+  const long long b = idx / (kJ * 12);
+  const int r = int(idx - b * (kJ * 12)), jj = r / 12, e = r % 12;
+  const float v = A[idx];
+  const uint32_t hi = f32_to_tf32_rn(v);
+  const uint32_t lo = f32_to_tf32_rn(__fsub_rn(v, __uint_as_float(hi)));
+  const long long blk = b / kLbsBlock;
+  const int row = int(b % kLbsBlock) * 12 + e;
+  uint32_t* im = img + blk * (long long)(kLbsK * kLbsN);
+  im[(size_t)(jj >> 2) * (kLbsN * 4) + row * 4 + (jj & 3)] = hi;
+  im[(size_t)((24 + jj) >> 2) * (kLbsN * 4) + row * 4 + ((24 + jj) & 3)] = lo;
+}
+
 // Grid shape: x = vertex tile pair (fastest), y = body-block group.  The group count is chosen so
 // the CTA count lands just under a whole number of waves (one CTA per SM).
 inline int lbs_tc_blocks_per_cta(int cta_x, int nblocks, int num_sms) {
@@ -343,7 +315,7 @@ inline int lbs_tc_blocks_per_cta(int cta_x, int nblocks, int num_sms) {
 }
 
 inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float* vposed,
-                                 const float* A, long long n, float* verts,
+                                 const uint32_t* a_img, long long n, float* verts,
                                  const float* joints_in, const float* cam, float* kp2d,
                                  cudaStream_t s) {
   if (n == 0) return cudaSuccess;
@@ -353,7 +325,7 @@ inline cudaError_t launch_lbs_tc(const DeviceModel& m, int num_sms, const float*
   const int bpc = lbs_tc_blocks_per_cta(cta_x, nblocks, num_sms);
   const dim3 grid((unsigned)cta_x, (unsigned)((nblocks + bpc - 1) / bpc));
   k_lbs_tc<<<grid, kLbsTcThreads, kLbsSmemBytes, s>>>(
-      m.w_tf32, A, vposed, n, nblocks, bpc, m.V, m.VP, verts,
+      m.w_tf32, reinterpret_cast<const uint8_t*>(a_img), vposed, n, nblocks, bpc, m.V, m.VP, verts,
       joints_in, cam, kp2d);
   return cudaGetLastError();
 }

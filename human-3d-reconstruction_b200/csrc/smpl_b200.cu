@@ -108,7 +108,7 @@ struct BlobBuilder {
 // ---- workspace carving -----------------------------------------------------------------
 struct Workspace {
   size_t coef = 0, A = 0, vposed = 0, joints = 0;
-  size_t coef_hi = 0, coef_lo = 0, coef_tf32 = 0;
+  size_t coef_hi = 0, coef_lo = 0, coef_tf32 = 0, a_tf32 = 0;
   size_t total = 0;
 };
 
@@ -154,10 +154,12 @@ Workspace carve(const SmplB200Model* m, long long n, const Plan& p) {
   w.vposed = take((chunked ? (size_t)m->chunk : nn) * 3 * (size_t)m->d.VP * sizeof(float));
   w.joints = take(nn * kJ * 3 * sizeof(float));
   const size_t coef_blocks = (nn + kCoefBlock - 1) / kCoefBlock;
+  const size_t lbs_blocks = (nn + kLbsBlock - 1) / kLbsBlock;
   if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
     w.coef_hi = take(coef_blocks * kCoefBlock * kCoefK * 2);
   if (p.prec == SMPLB200_PREC_BF16X3) w.coef_lo = take(coef_blocks * kCoefBlock * kCoefK * 2);
   if (p.prec == SMPLB200_PREC_TF32) w.coef_tf32 = take(coef_blocks * kCoefBlock * kCoefK * 4);
+  if (p.lbs == SMPLB200_LBS_TC) w.a_tf32 = take(lbs_blocks * kLbsBlock * 12 * kLbsK * 4);
   w.total = off;
   return w;
 }
@@ -229,6 +231,10 @@ size_t coef_image_bytes(long long n, uint32_t prec) {
   if (prec == SMPLB200_PREC_BF16X3) return 2 * align_up(one * 2, 256);
   if (prec == SMPLB200_PREC_TF32) return align_up(one * 4, 256);
   return 0;
+}
+size_t a_image_bytes(long long n) {
+  const size_t blocks = ((size_t)std::max<long long>(n, 1) + kLbsBlock - 1) / kLbsBlock;
+  return align_up(blocks * kLbsBlock * 12 * kLbsK * 4, 256);
 }
 
 }  // namespace
@@ -542,13 +548,12 @@ int smplb200_blendshapes(const SmplB200Model* model, const float* coef, int64_t 
 size_t smplb200_lbs_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags) {
   Plan p;
   if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
-  return 0;   // no skinning path needs scratch (the tcgen05 path splits A inside the kernel)
+  return p.lbs == SMPLB200_LBS_TC ? a_image_bytes(n) : 0;
 }
 
 int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A, int64_t n,
                  float* vertices, const float* joints_in, const float* cam, float* kp2d,
                  void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
-  (void)workspace; (void)workspace_bytes;
   if (!model || n < 0 || (n > 0 && (!vposed || !A || !vertices))) return SMPLB200_ERR_INVALID_ARG;
   if ((kp2d != nullptr) && (!cam || !joints_in)) return SMPLB200_ERR_INVALID_ARG;
   if (!aligned16(A) || !aligned16(vposed)) return SMPLB200_ERR_ALIGNMENT;
@@ -559,7 +564,14 @@ int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A
   if (guard.err != cudaSuccess) return cuda_fail(guard.err);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (p.lbs == SMPLB200_LBS_TC) {
-    CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, A, n, vertices, joints_in, cam, kp2d, s));
+    const size_t need = a_image_bytes(n);
+    if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+      return SMPLB200_ERR_WORKSPACE;
+    uint32_t* img = static_cast<uint32_t*>(workspace);
+    const long long total = n * (kJ * 12);
+    k_pack_a<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, n, img);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, img, n, vertices, joints_in, cam, kp2d, s));
     return SMPLB200_OK;
   }
   return launch_lbs_fma(model, p.lbs == SMPLB200_LBS_DENSE, vposed, A, n, vertices, joints_in, cam,
@@ -605,6 +617,7 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
     out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.coef_hi);
   if (p.prec == SMPLB200_PREC_BF16X3) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.coef_lo);
   if (p.prec == SMPLB200_PREC_TF32) out.coef_tf32 = reinterpret_cast<uint32_t*>(ws + w.coef_tf32);
+  if (p.lbs == SMPLB200_LBS_TC) out.a_tf32 = reinterpret_cast<uint32_t*>(ws + w.a_tf32);
   int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
   if (st) return st;
 
@@ -623,7 +636,8 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
                              out.coef_bf16_hi ? out.coef_bf16_hi + cb : nullptr,
                              out.coef_bf16_lo ? out.coef_bf16_lo + cb : nullptr,
                              out.coef_tf32 ? out.coef_tf32 + cb : nullptr, nc, vposed, s));
-      CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, A + (size_t)c0 * kJ * 12, nc,
+      const size_t ab = (size_t)(c0 / kLbsBlock) * kLbsBlock * 12 * kLbsK;  // elements into A' images
+      CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, out.a_tf32 + ab, nc,
                            vertices + (size_t)c0 * V * 3,
                            proj_in_lbs ? jbuf + (size_t)c0 * kJ * 3 : nullptr,
                            proj_in_lbs ? cam + (size_t)c0 * 3 : nullptr,
@@ -640,7 +654,7 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
 
   // k3 (+k4 when joints are kinematic)
   if (p.lbs == SMPLB200_LBS_TC)
-    CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, A, n, vertices,
+    CU_TRY(launch_lbs_tc(model->d, model->num_sms, vposed, out.a_tf32, n, vertices,
                          proj_in_lbs ? jbuf : nullptr, proj_in_lbs ? cam : nullptr,
                          proj_in_lbs ? kp2d : nullptr, s));
   else

@@ -152,9 +152,8 @@ int smplb200_blendshapes(const SmplB200Model* model, const float* coef, int64_t 
                          uint32_t flags, void* stream);
 
 /* k3 (+k4): linear blend skinning with the weak-perspective projection in its epilogue.
- * `joints_in`/`cam`/`kp2d` may be NULL together (no projection).  No skinning path needs
- * scratch today (`smplb200_lbs_workspace_bytes` returns 0; `workspace` may be NULL); the
- * parameters are kept so a future path can ask for some without an ABI change.               */
+ * `joints_in`/`cam`/`kp2d` may be NULL together (no projection).  SMPLB200_LBS_TC needs
+ * `smplb200_lbs_workspace_bytes` of scratch for the tf32 hi|lo image of A.                   */
 size_t smplb200_lbs_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags);
 int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A, int64_t n,
                  float* vertices, const float* joints_in, const float* cam, float* kp2d,
