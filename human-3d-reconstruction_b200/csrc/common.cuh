@@ -36,6 +36,4 @@ struct DeviceModel {
   const uint32_t* w_tf32;              // [VP][48] skinning-weight rows, tf32 W_hi(24) | W_lo(24)
 };
 
-__device__ __forceinline__ float ld_nc(const float* p) { return __ldg(p); }
-
 }  // namespace smplb200
