@@ -19,6 +19,7 @@
 #include "k_blend_fma.cuh"
 #include "k_lbs_fma.cuh"
 #include "k_blend_tc.cuh"
+#include "k_blend_tc2.cuh"
 #include "k_lbs_tc.cuh"
 #include "k_decode.cuh"
 
@@ -28,6 +29,7 @@ struct SmplB200Model {
   DeviceModel d;
   int device = 0;
   int num_sms = 0;
+  int k1_variant = 1;   // tensor-core blendshape kernel: 1 = 1-SM MMA (multicast pairs), 2 = 2-SM MMA
   int chunk = 0;        // bodies per k1->k3 pass (tensor-core paths); 0 = whole batch in one pass
   void* blob = nullptr;
   size_t blob_bytes = 0;
@@ -38,6 +40,7 @@ namespace {
 thread_local int tl_last_cuda_error = 0;
 
 constexpr int kDefaultChunk = 0;
+constexpr int kDefaultK1Variant = 1;
 
 inline int cuda_fail(cudaError_t e) {
   tl_last_cuda_error = (int)e;
@@ -220,8 +223,19 @@ cudaError_t configure_tc_kernels() {
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
+  if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
+  if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
+  if ((e = blend_tc2_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_lbs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)kLbsSmemBytes);
+}
+
+// k1 tensor-core variant: 1 = 1-SM MMA + multicast pairs, 2 = 2-SM (cta_group::2) MMA
+cudaError_t launch_blend_tc_any(const SmplB200Model* m, uint32_t prec, const uint16_t* chi,
+                                const uint16_t* clo, const uint32_t* ctf, long long n, float* vposed,
+                                cudaStream_t s) {
+  if (m->k1_variant == 2) return launch_blend_tc2(m->d, m->num_sms, prec, chi, clo, ctf, n, vposed, s);
+  return launch_blend_tc(m->d, m->num_sms, prec, chi, clo, ctf, n, vposed, s);
 }
 
 size_t coef_image_bytes(long long n, uint32_t prec) {
@@ -438,6 +452,7 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     DeviceModel& d = m->d;
     d.V = V; d.VP = VP; d.NB = NB; d.KB = KB; d.NC = NC;
     d.max_nnz = max_nnz; d.max_depth = max_depth; d.jreg_nnz = (int)jval.size();
+    { const char* t = std::getenv("SMPLB200_K1"); m->k1_variant = (t && std::atoi(t) == 2) ? 2 : kDefaultK1Variant; }
     {  // bodies per k1->k3 pass: keeps the vposed intermediate L2-resident (multiple of 128)
       const char* t = std::getenv("SMPLB200_CHUNK");
       int c = t ? std::atoi(t) : kDefaultChunk;
@@ -541,7 +556,7 @@ int smplb200_blendshapes(const SmplB200Model* model, const float* coef, int64_t 
   const long long total = n * kCoefK;
   k_pack_coef<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(coef, n, hi, lo, tf);
   CU_TRY(cudaGetLastError());
-  CU_TRY(launch_blend_tc(model->d, model->num_sms, p.prec, hi, lo, tf, n, vposed, s));
+  CU_TRY(launch_blend_tc_any(model, p.prec, hi, lo, tf, n, vposed, s));
   return SMPLB200_OK;
 }
 
@@ -632,7 +647,7 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
     for (long long c0 = 0; c0 < n; c0 += C) {
       const long long nc = std::min<long long>(C, n - c0);
       const size_t cb = (size_t)(c0 / kCoefBlock) * kCoefBlock * kCoefK;   // elements into coef images
-      CU_TRY(launch_blend_tc(model->d, model->num_sms, p.prec,
+      CU_TRY(launch_blend_tc_any(model, p.prec,
                              out.coef_bf16_hi ? out.coef_bf16_hi + cb : nullptr,
                              out.coef_bf16_lo ? out.coef_bf16_lo + cb : nullptr,
                              out.coef_tf32 ? out.coef_tf32 + cb : nullptr, nc, vposed, s));
@@ -648,8 +663,8 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
   if (p.prec == SMPLB200_PREC_FP32)
     st = launch_blend_fma(model, coef, n, vposed, s);
   else
-    CU_TRY(launch_blend_tc(model->d, model->num_sms, p.prec, out.coef_bf16_hi, out.coef_bf16_lo,
-                           out.coef_tf32, n, vposed, s));
+    CU_TRY(launch_blend_tc_any(model, p.prec, out.coef_bf16_hi, out.coef_bf16_lo, out.coef_tf32, n,
+                               vposed, s));
   if (st) return st;
 
   // k3 (+k4 when joints are kinematic)
