@@ -6,7 +6,7 @@
 // Why tensor cores for a "memory-bound" op: dense 24-joint fp32 blending is FMA-bound on the CUDA
 // cores (4.1 Mflop per body needs ~97 TFLOP/s at 60% of HBM), and even
 // the <=4-nnz form is bound by the shared-memory crossbar (48 gathered floats per vertex-body).
-// As an MMA the blend is M = 128 vertices (TMEM lanes), N = 12 * 16 bodies, K = 24 joints, and
+// As an MMA the blend is M = 128 vertices (TMEM lanes), N = 12 * 8 bodies, K = 24 joints, and
 // costs ~0.42 clk per vertex-body per SM for ANY weight matrix -- no sparsity assumption.
 //
 // fp32 fidelity comes from the 3xTF32 split (both operands split exactly into tf32 hi + lo):
@@ -15,16 +15,16 @@
 // the same order as an fp32 FMA chain.  W' = [W_hi | W_lo] rows of a 128-vertex tile are RESIDENT
 // IN TENSOR MEMORY as the MMA A operand (no shared-memory re-reads); A' = [A_hi | A_lo] per
 // 8-body block (written by k2) is the B operand.  Both A' and the block's planar vposed rows
-// stream through bulk-TMA / mbarrier rings with their own producer warps (A': 2 stages from L2;
-// vposed: 4 stages from HBM).  The kernel is bound by L2 throughput (~8 TB/s of operand re-reads +
-// vposed + vertex traffic; round-1 ablation: 73 us with MMAs, loads and stores all disabled), so
+// stream through bulk-TMA / mbarrier rings with their own producer warps (A': 4 stages from L2;
+// vposed: 4 stages from HBM, the 24 rows of a block issued by 24 lanes at once).  The kernel is
+// bound by SM<->L2 traffic (operand re-reads + vposed + vertices, ~8 TB/s), so
 // each CTA blends TWO adjacent vertex tiles per A' stage (2 x W' in TMEM, 4 accumulators): the A'
 // re-read traffic halves and every vposed TMA row is 1 KB.  The grid is tile-pair-fastest: the
 // CTAs resident at one time read and write adjacent row chunks of the same bodies (DRAM pages).
 //
 // Epilogue thread = vertex: reads its 12 blended entries per body from TMEM, the planar vposed
-// coordinates (from the shared-memory ring, conflict-free), applies the 3x4 transform with FMAs, transposes through a
-// per-warp shared-memory row and emits coalesced stores.  k4 (weak-perspective projection,
+// coordinates (from the shared-memory ring, conflict-free), applies the 3x4 transform with FMAs,
+// transposes four bodies at a time through a per-warp shared-memory tile and emits coalesced stores.  k4 (weak-perspective projection,
 // SURVEY.md A.8) rides in the epilogue of the CTAs that own vertex tile 0.
 #pragma once
 #include "common.cuh"
@@ -34,7 +34,7 @@
 namespace smplb200 {
 
 constexpr int kLbsTiles = 2;                             // vertex tiles per CTA sharing one B stage
-constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 2;   // warp 3 idle; epilogue = warps 4..19
+constexpr int kLbsWarpTmaV = 0, kLbsWarpMma = 1, kLbsWarpTmaB = 2;   // warp 3 unused; epilogue = warps 4..19
 constexpr int kLbsEpiWarp0 = 4;
 constexpr int kLbsEpiWarps = 8 * kLbsTiles;              // per tile: two per TMEM lane quarter, 4 bodies each
 constexpr int kLbsTcThreads = (kLbsEpiWarp0 + kLbsEpiWarps) * 32;    // 640

@@ -246,6 +246,20 @@ def test_other_model_shapes(dev, num_verts, num_betas):
         assert_close(k, ref_k, atol=2e-6, what="kp2d")
 
 
+def test_k1_two_sm_variant_is_bit_identical(dev, models, monkeypatch):
+    """The opt-in 2-SM (cta_group::2) blendshape kernel must equal the default 1-SM kernel bit for bit."""
+    n = 700
+    betas, pose, cam = synthetic.make_inputs(n, 71)
+    args = to_dev(dev, betas, pose, cam)
+    for precision in ("bf16x3", "bf16", "tf32"):
+        monkeypatch.delenv("SMPLB200_K1", raising=False)
+        ref = SMPL(models["sparse"], precision=precision, lbs="tc").to(dev)(*args)
+        monkeypatch.setenv("SMPLB200_K1", "2")          # read when the per-device handle is created
+        out = SMPL(models["sparse"], precision=precision, lbs="tc").to(dev)(*args)
+        assert torch.equal(out[0], ref[0]), precision
+    monkeypatch.delenv("SMPLB200_K1", raising=False)
+
+
 def test_cuda_graph_replay_matches_eager(dev, models):
     from human_3d_reconstruction_b200 import GraphedSMPL
     for n, kw in ((64, dict(precision="fp32", lbs="fma")), (300, dict(precision="bf16x3", lbs="tc"))):
