@@ -12,9 +12,8 @@
 //     (round-1a ncu: tc pipe 65% busy for 21% math).  From TMEM the only shared-memory traffic
 //     per MMA is the B operand (64 B/clk).
 //   * a block of 128 bodies is the "B" operand (N = 128: 64 clk of tensor time per MMA, enough
-//     to hide the ~50 clk the single issuing thread needs per tcgen05.mma), streamed two k-steps
-//     (8 KB per part) per stage through a 10-12 deep bulk-TMA/mbarrier ring from the K-major
-//     operand images k2 writes.
+//     to hide the ~40 clk the single issuing thread needs per tcgen05.mma), streamed one K half
+//     per stage through a bulk-TMA/mbarrier ring from the K-major operand images k2 writes.
 //   * an epilogue thread owns one planar column for 128 bodies, so each store instruction of a
 //     warp is one fully coalesced 128-byte segment of the planar vposed[b, plane, v] layout.
 //
@@ -50,29 +49,21 @@ struct BlendTcCfg {
   static constexpr bool kTf32 = PREC == SMPLB200_PREC_TF32;
   static constexpr int kElem = kTf32 ? 4 : 2;
   static constexpr int kParts = PREC == SMPLB200_PREC_BF16X3 ? 2 : 1;   // hi (+ lo) operands
+  static constexpr int kStages = 3;                                      // ring of K-half stages
   static constexpr int kKSteps = kCoefK * kElem / 32;                    // 14 (bf16) or 28 (tf32)
-  // The coef operand streams in SMALL stages (2 MMA k-steps = 4 sixteen-byte K chunks = 8 KB per
-  // part) through a DEEP ring: a bulk copy from L2 takes ~1.5-2 us regardless of size, so what
-  // keeps the tensor pipe fed is the number of stages in flight, not their size (with 3 stages of
-  // 29-57 KB the producer delivered one stage per ~0.6 us and the MMA thread starved 40% of the time).
-  static constexpr int kStageKSteps = 2;
-  static constexpr int kStagesPerUnit = kKSteps / kStageKSteps;          // 7 (bf16) or 14 (tf32)
-  static constexpr uint32_t kBStagePart = kStageKSteps * 2 * kCoefBlock * 16;   // 8,192 B
-  static constexpr uint32_t kBStage = kBStagePart * kParts;
-  static constexpr int kStages = kParts == 2 ? 10 : 12;                  // ring depth: 160 KB / 96 KB
+  static constexpr int kKHalf = kKSteps / 2;                             // MMA k-steps per stage
   static constexpr int kAColsPart = kCoefK * kElem / 4;                  // TMEM columns: 112 / 224
   static constexpr int kAWords = kAColsPart;                             // 32-bit words per basis row
   static constexpr uint32_t kBBytesPart = kCoefK * kCoefBlock * kElem;   // one coef image (block)
+  static constexpr uint32_t kBHalf = kBBytesPart / 2;                    // its first / second K half
+  static constexpr uint32_t kBStage = kBHalf * kParts;
   static constexpr uint32_t kBarOffset = kStages * kBStage;
-  static constexpr uint32_t kSmemBytes = kBarOffset + 512;
+  static constexpr uint32_t kSmemBytes = kBarOffset + 256;
   static constexpr uint32_t kLboB = kCoefBlock * 16, kSbo = 128;
   static constexpr uint32_t kIdesc =
       ptx::make_idesc(kTf32 ? ptx::kFmtTF32 : ptx::kFmtBF16, 128, kCoefBlock);
-  // legacy half-K constants (used by the 2-SM experiment, k_blend_tc2.cuh)
-  static constexpr int kKHalf = kKSteps / 2;
-  static constexpr uint32_t kBHalf = kBBytesPart / 2;
   static_assert(kTcAccCols + kAColsPart * kParts <= kTcTmemCols, "TMEM budget");
-  static_assert(kKSteps % kStageKSteps == 0, "whole stages");
+  static_assert(kKSteps % 2 == 0, "K halves");
 };
 
 template <uint32_t PREC>
@@ -119,23 +110,21 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
   const uint32_t tmem_a = tmem_base + kTcAccCols;   // A operand columns follow the accumulators
 
   if (warp == kWarpTma) {
-    // ===== bulk-TMA producer: coef images of the body blocks, 2 k-steps per stage.  This CTA
+    // ===== bulk-TMA producer: coef images of the body blocks, one K half per stage.  This CTA
     // fetches HALF of the stage and multicasts it to both CTAs of the pair. =====
     if (lane == 0) {
       constexpr uint32_t kMy = C::kBStage / 2;          // bytes this CTA fetches per stage
-      const int nst = nunits * C::kStagesPerUnit;
-      for (int i = 0; i < nst; ++i) {
+      for (int i = 0; i < 2 * nunits; ++i) {
         const int s = i % C::kStages;
-        const int unit = i / C::kStagesPerUnit, sub = i - unit * C::kStagesPerUnit;
-        const int blk = (int)((u0 + unit) % nblocks);
+        const int blk = (int)((u0 + (i >> 1)) % nblocks);
         ptx::mbar_wait(bar_empty + s, ((i / C::kStages) & 1) ^ 1);   // both CTAs' MMAs retired
         ptx::mbar_arrive_expect_tx(bar_full + s, C::kBStage);
         uint8_t* dst = sB + (size_t)s * C::kBStage;
-        const size_t src = (size_t)blk * C::kBBytesPart + (size_t)sub * C::kBStagePart;
-        if (C::kParts == 2) {     // stage = [hi piece | lo piece]: rank 0 -> hi, rank 1 -> lo
-          ptx::bulk_g2s_multicast(dst + crank * C::kBStagePart, (crank ? coef_lo : coef_hi) + src,
-                                  C::kBStagePart, bar_full + s, (uint16_t)3);
-        } else {                  // single image: each rank fetches half of the bytes
+        const size_t src = (size_t)blk * C::kBBytesPart + (size_t)(i & 1) * C::kBHalf;
+        if (C::kParts == 2) {     // stage = [hi half-K image | lo half-K image]: rank 0 -> hi, rank 1 -> lo
+          ptx::bulk_g2s_multicast(dst + crank * C::kBHalf, (crank ? coef_lo : coef_hi) + src, C::kBHalf,
+                                  bar_full + s, (uint16_t)3);
+        } else {                  // single image: each rank fetches half of its bytes
           ptx::bulk_g2s_multicast(dst + crank * kMy, coef_hi + src + crank * kMy, kMy, bar_full + s,
                                   (uint16_t)3);
         }
@@ -157,18 +146,19 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
         ptx::mbar_wait(bar_tempty + a, ((i / kTcAccBufs) & 1) ^ 1);
         const uint32_t d_tmem = tmem_base + a * kCoefBlock;
         uint32_t acc = 0;
-        for (int sub = 0; sub < C::kStagesPerUnit; ++sub) {
-          const int st = i * C::kStagesPerUnit + sub, s = st % C::kStages;
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+          const int st = 2 * i + kh, s = st % C::kStages;
           ptx::mbar_wait(bar_full + s, (st / C::kStages) & 1);
           ptx::tc_fence_after();
           const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * C::kBStage);
           constexpr int kGroups = C::kParts == 2 ? 3 : 1;   // (hi,hi) [, (hi,lo), (lo,hi)]
 #pragma unroll
           for (int g = 0; g < kGroups; ++g) {
-            const uint32_t ap = tmem_a + (g == 2 ? C::kAColsPart : 0) + sub * C::kStageKSteps * 8;
-            const uint32_t bp = b_addr + (g == 1 ? C::kBStagePart : 0);
+            const uint32_t ap = tmem_a + (g == 2 ? C::kAColsPart : 0) + kh * C::kKHalf * 8;
+            const uint32_t bp = b_addr + (g == 1 ? C::kBHalf : 0);
 #pragma unroll
-            for (int ks = 0; ks < C::kStageKSteps; ++ks) {
+            for (int ks = 0; ks < C::kKHalf; ++ks) {
               const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * C::kLboB, C::kLboB, C::kSbo);
               if (C::kTf32) ptx::mma_tf32_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
               else ptx::mma_bf16_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
