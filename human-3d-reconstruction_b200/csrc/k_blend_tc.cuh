@@ -131,8 +131,11 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
       }
     }
   } else if (warp == kWarpMma) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop convergently and ONE elected lane issues.
+    // Keeping control flow warp-uniform lets the descriptors live in uniform registers; issued from
+    // a divergent `lane == 0` branch every tcgen05.mma cost ~15 SASS instructions (ELECT + 3x
+    // R2UR.BROADCAST + predicate shuffling, ~50 clk), i.e. ~2100 of the 2688 clk a unit's MMAs take. =====
+    {
       long long cur_tile = -1;
       uint32_t a_phase = 0;
       for (int i = 0; i < nunits; ++i) {
@@ -145,7 +148,6 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
         }
         ptx::mbar_wait(bar_tempty + a, ((i / kTcAccBufs) & 1) ^ 1);
         const uint32_t d_tmem = tmem_base + a * kCoefBlock;
-        uint32_t acc = 0;
 #pragma unroll
         for (int kh = 0; kh < 2; ++kh) {
           const int st = 2 * i + kh, s = st % C::kStages;
@@ -153,21 +155,24 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
           ptx::tc_fence_after();
           const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * C::kBStage);
           constexpr int kGroups = C::kParts == 2 ? 3 : 1;   // (hi,hi) [, (hi,lo), (lo,hi)]
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int g = 0; g < kGroups; ++g) {
-            const uint32_t ap = tmem_a + (g == 2 ? C::kAColsPart : 0) + kh * C::kKHalf * 8;
-            const uint32_t bp = b_addr + (g == 1 ? C::kBHalf : 0);
+            for (int g = 0; g < kGroups; ++g) {
+              const uint32_t ap = tmem_a + (g == 2 ? C::kAColsPart : 0) + kh * C::kKHalf * 8;
+              const uint32_t bp = b_addr + (g == 1 ? C::kBHalf : 0);
 #pragma unroll
-            for (int ks = 0; ks < C::kKHalf; ++ks) {
-              const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * C::kLboB, C::kLboB, C::kSbo);
-              if (C::kTf32) ptx::mma_tf32_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
-              else ptx::mma_bf16_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
-              acc = 1;
+              for (int ks = 0; ks < C::kKHalf; ++ks) {
+                const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * C::kLboB, C::kLboB, C::kSbo);
+                const uint32_t acc = (kh | g | ks) != 0;
+                if (C::kTf32) ptx::mma_tf32_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
+                else ptx::mma_bf16_ts(d_tmem, ap + ks * 8, bd, C::kIdesc, acc);
+              }
             }
+            ptx::tc_commit_multicast(bar_empty + s, (uint16_t)3);   // tell BOTH producers: stage consumed here
+            if (kh == 1) ptx::tc_commit(bar_tfull + a);             // accumulator ready for the epilogue
           }
-          ptx::tc_commit_multicast(bar_empty + s, (uint16_t)3);   // tell BOTH producers: stage consumed here
+          __syncwarp();
         }
-        ptx::tc_commit(bar_tfull + a);   // accumulator ready for the epilogue
       }
     }
   } else {
