@@ -34,6 +34,11 @@ struct DeviceModel {
   const uint32_t* basis_rows_bf16_lo;  // same, low part of the 2-term bf16 split
   const uint32_t* basis_rows_tf32;     // [NC][224] tf32
   const uint32_t* w_tf32;              // [VP][48] skinning-weight rows, tf32 W_hi(24) | W_lo(24)
+  // backward pass (k_backward.cuh)
+  const int* wcsr_ptr;                 // [J+1] skinning weights as CSR over JOINTS (transpose of ELL)
+  const int* wcsr_idx;                 // [nnz] vertex index, ascending within a joint
+  const float* wcsr_val;               // [nnz]
+  const float* dense_jreg;             // [VP, J] joint regressor rows (regressed-joint gradient)
 };
 
 }  // namespace smplb200

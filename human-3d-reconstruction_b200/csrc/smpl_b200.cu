@@ -22,6 +22,7 @@
 #include "k_blend_tc2.cuh"
 #include "k_lbs_tc.cuh"
 #include "k_decode.cuh"
+#include "k_backward.cuh"
 
 using namespace smplb200;
 
@@ -31,6 +32,7 @@ struct SmplB200Model {
   int num_sms = 0;
   int k1_variant = 1;   // tensor-core blendshape kernel: 1 = 1-SM MMA (multicast pairs), 2 = 2-SM MMA
   int chunk = 0;        // bodies per k1->k3 pass (tensor-core paths); 0 = whole batch in one pass
+  bool lbs_bwd_staged = false;   // backward skinning kernel stages a body's g_v + vposed in smem
   void* blob = nullptr;
   size_t blob_bytes = 0;
 };
@@ -226,6 +228,8 @@ cudaError_t configure_tc_kernels() {
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_blend_bwd_fma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)kBbSmemBytes)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_lbs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)kLbsSmemBytes);
 }
@@ -379,6 +383,20 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
       jptr[j + 1] = (int)jidx.size();
     }
     if (jidx.empty()) { jidx.push_back(0); jval.push_back(0.f); }
+    // ---- backward pass: skinning weights as CSR over joints, dense joint-regressor rows
+    std::vector<int> wptr(kJ + 1, 0), widx;
+    std::vector<float> wval;
+    for (int j = 0; j < kJ; ++j) {
+      for (int v = 0; v < V; ++v) {
+        const float wv = desc->weights[(size_t)v * kJ + j];
+        if (wv != 0.f) { widx.push_back(v); wval.push_back(wv); }
+      }
+      wptr[j + 1] = (int)widx.size();
+    }
+    if (widx.empty()) { widx.push_back(0); wval.push_back(0.f); }
+    std::vector<float> dense_jreg((size_t)VP * kJ, 0.f);
+    for (int v = 0; v < V; ++v)
+      for (int j = 0; j < kJ; ++j) dense_jreg[(size_t)v * kJ + j] = desc->j_regressor[(size_t)v * kJ + j];
 
     // ---- tensor-core A operand of k1: basis^T rows [planar column][K], resident in TMEM
     std::vector<uint16_t> bhi((size_t)NC * kCoefK, 0), blo((size_t)NC * kCoefK, 0);
@@ -434,6 +452,10 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     const size_t o_blo = bb.add(blo.data(), blo.size() * 2);
     const size_t o_btf = bb.add(btf.data(), btf.size() * 4);
     const size_t o_wtf = bb.add(wtf.data(), wtf.size() * 4);
+    const size_t o_wp = bb.add(wptr.data(), wptr.size() * 4);
+    const size_t o_wi = bb.add(widx.data(), widx.size() * 4);
+    const size_t o_wv = bb.add(wval.data(), wval.size() * 4);
+    const size_t o_djr = bb.add(dense_jreg.data(), dense_jreg.size() * 4);
 
     DeviceGuard guard(desc->device);
     if (guard.err != cudaSuccess) { delete m; return cuda_fail(guard.err); }
@@ -445,6 +467,14 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     e = configure_tc_kernels();
     if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
 
+    {  // backward skinning kernel: shared-memory staging when one body's g_v + vposed fit
+      const size_t need = lbs_bwd_smem_bytes(V, VP);
+      if (need + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {
+        e = cudaFuncSetAttribute(k_lbs_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
+        m->lbs_bwd_staged = true;
+      }
+    }
     m->blob_bytes = bb.bytes.size();
     m->device = desc->device;
     m->num_sms = prop.multiProcessorCount;
@@ -473,6 +503,10 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     d.basis_rows_bf16_lo = reinterpret_cast<const uint32_t*>(base + o_blo);
     d.basis_rows_tf32 = reinterpret_cast<const uint32_t*>(base + o_btf);
     d.w_tf32 = reinterpret_cast<const uint32_t*>(base + o_wtf);
+    d.wcsr_ptr = reinterpret_cast<const int*>(base + o_wp);
+    d.wcsr_idx = reinterpret_cast<const int*>(base + o_wi);
+    d.wcsr_val = reinterpret_cast<const float*>(base + o_wv);
+    d.dense_jreg = reinterpret_cast<const float*>(base + o_djr);
     *out_model = m;
     return SMPLB200_OK;
   } catch (const std::bad_alloc&) {
@@ -682,6 +716,132 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
   if (p.regressed && (joints || kp2d)) st = launch_regress(model, vertices, n, jbuf, cam, kp2d, s);
   return st;
 }
+
+}  // extern "C"
+
+// ---- backward ------------------------------------------------------------------------------
+namespace {
+struct BwdWorkspace {
+  Workspace fwd;                 // recomputed forward intermediates (coef / operand images, A, vposed)
+  size_t g_vposed = 0, g_A = 0, part = 0;
+  int slices = 1;
+  size_t total = 0;
+};
+
+BwdWorkspace carve_bwd(const SmplB200Model* m, long long n, const Plan& p, bool vertex_path) {
+  BwdWorkspace w;
+  if (!vertex_path) { w.total = 256; return w; }
+  Plan pf = p;
+  pf.lbs = SMPLB200_LBS_FMA;      // no skinning in the recompute: no A' image needed
+  w.fwd = carve(m, n, pf);
+  size_t off = w.fwd.total;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t nn = (size_t)std::max<long long>(n, 1);
+  const long long body_tiles = (long long)((nn + kBbBodies - 1) / kBbBodies);
+  const int nchunks = m->d.NC / kBbCols;
+  long long s = (2LL * m->num_sms + body_tiles - 1) / body_tiles;
+  w.slices = (int)std::max<long long>(1, std::min<long long>(s, std::min(kBbMaxSlices, nchunks)));
+  w.g_vposed = take(nn * 3 * (size_t)m->d.VP * sizeof(float));
+  w.g_A = take(nn * kJ * 12 * sizeof(float));
+  w.part = take((size_t)w.slices * nn * kCoefK * sizeof(float));
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" {
+
+size_t smplb200_backward_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags,
+                                         int vertex_path) {
+  Plan p;
+  if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  return carve_bwd(model, n, p, vertex_path != 0).total;
+}
+
+int smplb200_backward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags, int vertex_path) {
+  Plan p;
+  if (!model || n <= 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  return vertex_path ? 5 : 1;     // k2, k1, kb3, kb1, kb2  |  kb2 alone
+}
+
+int smplb200_backward(const SmplB200Model* model, const float* betas, const float* pose,
+                      const float* cam, int64_t n, const float* joints_fwd,
+                      const float* g_vertices, const float* g_joints, const float* g_kp2d,
+                      float* g_betas, float* g_pose, float* g_cam,
+                      void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!model || n < 0) return SMPLB200_ERR_INVALID_ARG;
+  if (n == 0) return SMPLB200_OK;
+  if (!betas || !pose || !g_betas || !g_pose) return SMPLB200_ERR_INVALID_ARG;
+  if ((g_kp2d || g_cam) && !cam) return SMPLB200_ERR_INVALID_ARG;
+  Plan p;
+  if (!resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
+  if (p.regressed && g_kp2d && !joints_fwd) return SMPLB200_ERR_INVALID_ARG;
+  const bool vertex_path = g_vertices != nullptr || (p.regressed && (g_joints || g_kp2d));
+  const BwdWorkspace w = carve_bwd(model, n, p, vertex_path);
+  if (vertex_path &&
+      (!workspace || workspace_bytes < w.total || (reinterpret_cast<uintptr_t>(workspace) & 255u)))
+    return SMPLB200_ERR_WORKSPACE;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+
+  ChainBwdArgs cb{};
+  cb.betas = betas; cb.pose = pose; cb.cam = cam;
+  cb.g_joints = g_joints; cb.g_kp2d = g_kp2d; cb.joints_fwd = joints_fwd;
+  cb.g_betas = g_betas; cb.g_pose = g_pose; cb.g_cam = g_cam;
+  cb.rotate_base = p.rotate_base ? 1 : 0;
+  cb.regressed = p.regressed ? 1 : 0;
+  cb.slices = w.slices;
+
+  if (vertex_path) {
+    float* coef = reinterpret_cast<float*>(ws + w.fwd.coef);
+    float* A = reinterpret_cast<float*>(ws + w.fwd.A);
+    float* vposed = reinterpret_cast<float*>(ws + w.fwd.vposed);
+    float* g_vposed = reinterpret_cast<float*>(ws + w.g_vposed);
+    float* g_A = reinterpret_cast<float*>(ws + w.g_A);
+    float* part = reinterpret_cast<float*>(ws + w.part);
+    // recompute k2 + k1 (same kernels and precision as the forward)
+    ChainOut out{};
+    out.A = A;
+    if (p.prec == SMPLB200_PREC_FP32) out.coef = coef;
+    if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
+      out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_hi);
+    if (p.prec == SMPLB200_PREC_BF16X3) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_lo);
+    if (p.prec == SMPLB200_PREC_TF32) out.coef_tf32 = reinterpret_cast<uint32_t*>(ws + w.fwd.coef_tf32);
+    int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
+    if (st) return st;
+    if (p.prec == SMPLB200_PREC_FP32) st = launch_blend_fma(model, coef, n, vposed, s);
+    else CU_TRY(launch_blend_tc_any(model, p.prec, out.coef_bf16_hi, out.coef_bf16_lo, out.coef_tf32, n, vposed, s));
+    if (st) return st;
+    // kb3
+    LbsBwdArgs la{};
+    la.vposed = vposed; la.A = A; la.g_verts = g_vertices;
+    la.g_joints = g_joints; la.g_kp2d = g_kp2d; la.cam = cam;
+    la.g_vposed = g_vposed; la.g_A = g_A; la.regressed = p.regressed ? 1 : 0;
+    const unsigned grid = (unsigned)std::min<long long>(n, 4LL * model->num_sms);
+    if (model->lbs_bwd_staged)
+      k_lbs_bwd<true><<<std::min<unsigned>(grid, (unsigned)model->num_sms), kLbsBwdThreads,
+                        lbs_bwd_smem_bytes(model->d.V, model->d.VP), s>>>(model->d, la, n);
+    else
+      k_lbs_bwd<false><<<grid, kLbsBwdThreads, 0, s>>>(model->d, la, n);
+    CU_TRY(cudaGetLastError());
+    // kb1
+    dim3 g1((unsigned)w.slices, (unsigned)((n + kBbBodies - 1) / kBbBodies));
+    k_blend_bwd_fma<<<g1, kBbThreads, kBbSmemBytes, s>>>(model->d, g_vposed, n, w.slices, part);
+    CU_TRY(cudaGetLastError());
+    cb.g_A = g_A;
+    cb.g_coef_part = part;
+  }
+  const unsigned grid = (unsigned)((n + kChainWarps - 1) / kChainWarps);
+  k_chain_bwd<<<grid, kChainWarps * 32, 0, s>>>(model->d, cb, n);
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int32_t num_classes,
                            int32_t height, int32_t width, const float* const* heads,

@@ -11,8 +11,11 @@ Model tensors are registered buffers so ``nn.DataParallel`` (reference
 src/lib/trains/trainer.py:176) replicates them; the packed device-side model (one
 ``SmplB200Model*`` per device) is created lazily from the buffers on first use.
 
-Forward-only (SURVEY.md §8b "Autograd"): requesting gradients raises.  CUDA-only: a CPU tensor
-raises -- there is no CPU path in the product.
+Differentiable: when an input requires grad the call goes through ``_SMPLFunction`` whose
+backward is ``smplb200_backward`` (hand-written kernels, csrc/k_backward.cuh) -- what the reference
+trainer needs to put a loss on the layer's outputs (reference src/lib/trains/trainer.py:31-37,
+102-104).  Outputs that do not reach the loss cost nothing: without a vertex gradient the backward
+is one small kernel.  CUDA-only: a CPU tensor raises -- there is no CPU path in the product.
 """
 from __future__ import annotations
 
@@ -45,6 +48,50 @@ def _check_in(name, t, n, width, device):
     if t.dim() != 2 or t.shape[0] != n or t.shape[1] != width:
         raise ValueError(f"{name} must have shape [{n}, {width}], got {tuple(t.shape)}")
     return t.contiguous()
+
+
+class _SMPLFunction(torch.autograd.Function):
+    """autograd node: forward = smplb200_forward, backward = smplb200_backward (first order only)."""
+
+    @staticmethod
+    def forward(ctx, layer, flags, betas, pose, cam):
+        outs = layer._forward_impl(betas, pose, cam, flags)
+        ctx.layer, ctx.flags, ctx.has_cam = layer, flags, cam is not None
+        ctx.set_materialize_grads(False)      # an output that does not reach the loss stays None
+        ctx.save_for_backward(betas, pose, cam, outs[1])
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_verts, g_joints, g_kp2d=None):
+        betas, pose, cam, joints = ctx.saved_tensors
+        layer, flags = ctx.layer, ctx.flags
+        device, n = betas.device, int(betas.shape[0])
+        h = layer.handle(device)
+
+        def prep(g):
+            return None if g is None else g.to(torch.float32).contiguous()
+
+        g_verts, g_joints, g_kp2d = prep(g_verts), prep(g_joints), prep(g_kp2d)
+        regressed = bool(flags & capi.JOINTS_REGRESSED)
+        vertex_path = g_verts is not None or (regressed and (g_joints is not None or g_kp2d is not None))
+        with torch.cuda.device(device):
+            g_betas = torch.empty_like(betas)
+            g_pose = torch.empty_like(pose)
+            g_cam = torch.empty_like(cam) if cam is not None else None
+            if n > 0:
+                wsb = int(capi.lib().smplb200_backward_workspace_bytes(h.ptr, n, flags, int(vertex_path)))
+                if wsb == 0:
+                    raise RuntimeError("smplb200_backward_workspace_bytes rejected the flag combination")
+                ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+                capi.check(capi.lib().smplb200_backward(
+                    h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(joints),
+                    _ptr(g_verts), _ptr(g_joints), _ptr(g_kp2d),
+                    _ptr(g_betas), _ptr(g_pose), _ptr(g_cam),
+                    _ptr(ws), wsb, flags, _stream_ptr(device)), "smplb200_backward")
+        need = ctx.needs_input_grad   # (layer, flags, betas, pose, cam)
+        return (None, None, g_betas if need[2] else None, g_pose if need[3] else None,
+                g_cam if (ctx.has_cam and need[4]) else None)
 
 
 class SMPL(nn.Module):
@@ -113,10 +160,6 @@ class SMPL(nn.Module):
         """
         if not isinstance(betas, torch.Tensor) or betas.device.type != "cuda":
             raise RuntimeError("SMPL (B200) needs CUDA tensors; there is no CPU fallback")
-        if torch.is_grad_enabled() and any(
-                isinstance(t, torch.Tensor) and t.requires_grad for t in (betas, pose, cam)):
-            raise RuntimeError("SMPL (B200) is forward-only: wrap the call in torch.no_grad() "
-                               "or detach the inputs (backward is out of scope, SURVEY.md §8f)")
         device = betas.device
         n = int(betas.shape[0])
         betas = _check_in("betas", betas, n, self.num_betas, device)
@@ -124,6 +167,12 @@ class SMPL(nn.Module):
         if cam is not None:
             cam = _check_in("cam", cam, n, 3, device)
         flags = self.flags if flags is None else int(flags)
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (betas, pose, cam)):
+            return _SMPLFunction.apply(self, flags, betas, pose, cam)
+        return self._forward_impl(betas, pose, cam, flags)
+
+    def _forward_impl(self, betas, pose, cam, flags):
+        device, n = betas.device, int(betas.shape[0])
         h = self.handle(device)
         with torch.cuda.device(device):
             verts = torch.empty((n, self.num_verts, 3), dtype=torch.float32, device=device)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SMPLB200_VERSION 100 /* 0.1.0 */
+#define SMPLB200_VERSION 110 /* 0.1.1: + backward */
 
 /* ---- status codes ---------------------------------------------------------------------- */
 enum {
@@ -162,6 +162,28 @@ int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A
 /* joints regressed from skinned vertices (SMPLB200_JOINTS_REGRESSED) + optional projection. */
 int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, int64_t n,
                             float* joints, const float* cam, float* kp2d, void* stream);
+
+/* ---- the backward pass (what the reference trainer needs next) -------------- */
+/* (g_betas[N,NB], g_pose[N,3J], g_cam[N,3]) <- upstream gradients of the forward outputs
+ * (g_vertices[N,V,3], g_joints[N,J,3], g_kp2d[N,J,2]; each may be NULL = zero), for the same
+ * betas/pose/cam and `flags` as the forward call.  Replaces what autograd derives for the eager
+ * layer inside the reference's training step (reference src/lib/trains/trainer.py:31-37 builds the
+ * loss, :102-104 call loss.backward()).  Intermediates are recomputed, nothing is saved by the
+ * forward.  `joints_fwd` (the forward's joints output) is read only with SMPLB200_JOINTS_REGRESSED
+ * and g_kp2d.  `g_cam` may be NULL; it requires `cam`.  The vertex path (g_vertices given, or
+ * regressed joints with g_joints/g_kp2d) needs `smplb200_backward_workspace_bytes(..., 1)` of
+ * 256-byte aligned scratch; without it (`vertex_path` = 0) the workspace may be NULL.
+ * Gradients are summed in a fixed order (no atomics): bitwise reproducible.                      */
+size_t smplb200_backward_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags,
+                                         int vertex_path);
+int smplb200_backward(const SmplB200Model* model, const float* betas, const float* pose,
+                      const float* cam, int64_t n, const float* joints_fwd,
+                      const float* g_vertices, const float* g_joints, const float* g_kp2d,
+                      float* g_betas, float* g_pose, float* g_cam,
+                      void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+/* Kernel launches one backward call issues (bench accounting).                                 */
+int smplb200_backward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags,
+                                   int vertex_path);
 
 /* ---- the producer of the per-person vectors ------------------------ */
 /* Fused NMS + top-K + head gather, one launch:
