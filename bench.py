@@ -426,6 +426,57 @@ def main():
                 "gpu_us": dt_dec * 1e6, "images_per_s": Bi / dt_dec,
                 "cpu_reference_port_us": dt_cpu * 1e6, "cpu_kind": "port (oracle/decode_ref.py, pinned bit-exact to the reference functions)",
                 "decode_plus_smpl_1024_bodies_us": dt_pipe * 1e6, "people_per_s": Bi * Kp / dt_pipe}
+            # ---- next §8(f) row: the backward pass (a trainer-shaped loss through the autograd node) --
+            from oracle.smpl_ref import smpl_forward as oracle_forward
+            nt = 128
+            lay_t = SMPL(model, precision="auto", lbs="auto").to(dev)
+            arrs = synthetic.make_inputs(nt, 9)
+            bt, pt, ct = (torch.from_numpy(x).to(dev).requires_grad_() for x in arrs)
+
+            def loss_of(outs, with_verts):
+                v, j, k = outs
+                l = k.abs().mean() + j.pow(2).mean()
+                return l + v.pow(2).mean() if with_verts else l
+
+            def train_step(with_verts):
+                bt.grad = pt.grad = ct.grad = None
+                loss_of(lay_t(bt, pt, ct), with_verts).backward()
+
+            bw = {}
+            for name, wv in (("loss_on_joints_kp2d", False), ("loss_on_vertices_joints_kp2d", True)):
+                for _ in range(3):
+                    train_step(wv)
+                dt_t = time_loop(lambda: train_step(wv), 20, torch) / 20
+                cb, cp, cc = (torch.from_numpy(x).requires_grad_() for x in arrs)
+                t0 = time.perf_counter()
+                loss_of(oracle_forward(model, cb, cp, cc), wv).backward()
+                dt_c = time.perf_counter() - t0
+                bw[name] = {"gpu_fwd_bwd_us": dt_t * 1e6, "cpu_autograd_port_us": dt_c * 1e6}
+            # the backward call alone at the headline batch (vertex path, device-resident gradients)
+            hb = lay_t.handle(dev)
+            lib_ = capi.lib()
+            wsb = int(lib_.smplb200_backward_workspace_bytes(hb.ptr, n, lay_t.flags, 1))
+            wsb_t = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            gv_, gj_, gk_ = (torch.randn(n, d0, d1, device=dev) for d0, d1 in ((6890, 3), (24, 3), (24, 2)))
+            gb_, gp_, gc_ = torch.empty_like(tb), torch.empty_like(tp), torch.empty_like(tc)
+            jf_ = torch.empty(n, 24, 3, device=dev)
+            sp_ = torch.cuda.current_stream(dev).cuda_stream
+
+            def bwd_call():
+                capi.check(lib_.smplb200_backward(
+                    hb.ptr, tb.data_ptr(), tp.data_ptr(), tc.data_ptr(), n, jf_.data_ptr(), gv_.data_ptr(),
+                    gj_.data_ptr(), gk_.data_ptr(), gb_.data_ptr(), gp_.data_ptr(), gc_.data_ptr(),
+                    wsb_t.data_ptr(), wsb, lay_t.flags, sp_), "smplb200_backward")
+
+            for _ in range(3):
+                bwd_call()
+            dt_b = time_loop(bwd_call, 10, torch) / 10
+            next_rows["backward"] = {
+                "workload": f"trainer-shaped loss at {nt} bodies through the autograd node; smplb200_backward alone at {n} bodies",
+                f"train_step_{nt}_bodies": bw,
+                f"backward_call_{n}_bodies_us": dt_b * 1e6, "backward_bodies_per_s": n / dt_b,
+                "launches_per_backward": int(lib_.smplb200_backward_launch_count(hb.ptr, n, lay_t.flags, 1)),
+                "cpu_kind": "port (torch autograd of oracle/smpl_ref.py, fp32, one call)"}
         t_kern_end = time.time()
 
     clocks = sampler.summary(t_wall0, t_wall1) if sampler else None

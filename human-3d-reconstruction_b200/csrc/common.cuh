@@ -39,6 +39,8 @@ struct DeviceModel {
   const int* wcsr_idx;                 // [nnz] vertex index, ascending within a joint
   const float* wcsr_val;               // [nnz]
   const float* dense_jreg;             // [VP, J] joint regressor rows (regressed-joint gradient)
+  const uint32_t* bwd_basis_tf32_hi;   // [NC/32][8][224][4] K-major tiles of basis[k, col] (k_blend_bwd_tc)
+  const uint32_t* bwd_basis_tf32_lo;   // same, low part of the 2-term tf32 split
 };
 
 }  // namespace smplb200

@@ -23,6 +23,7 @@
 #include "k_lbs_tc.cuh"
 #include "k_decode.cuh"
 #include "k_backward.cuh"
+#include "k_blend_bwd_tc.cuh"
 
 using namespace smplb200;
 
@@ -228,6 +229,8 @@ cudaError_t configure_tc_kernels() {
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
+  if ((e = blend_bwd_tc_set_smem<false>()) != cudaSuccess) return e;
+  if ((e = blend_bwd_tc_set_smem<true>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_blend_bwd_fma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kBbSmemBytes)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_lbs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -394,6 +397,19 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
       wptr[j + 1] = (int)widx.size();
     }
     if (widx.empty()) { widx.push_back(0); wval.push_back(0.f); }
+    // basis[k, col] as the B operand of the tensor-core blendshape backward: per K-step of 32
+    // planar columns one tile [8 chunks][224 rows k][4 cols], tf32 hi | lo (rows >= NB+207 are 0)
+    std::vector<uint32_t> gbh((size_t)NC * kCoefK, 0), gbl((size_t)NC * kCoefK, 0);
+    for (int ks = 0; ks < NC / 32; ++ks)
+      for (int c = 0; c < 8; ++c)
+        for (int r = 0; r < NB + kP; ++r)
+          for (int e = 0; e < 4; ++e) {
+            const float x = basis[(size_t)r * NC + ks * 32 + c * 4 + e];
+            const uint32_t hi = host_tf32(x);
+            const size_t idx = (((size_t)ks * 8 + c) * kCoefK + r) * 4 + e;
+            gbh[idx] = hi;
+            gbl[idx] = host_tf32(x - bits_to_f32(hi));
+          }
     std::vector<float> dense_jreg((size_t)VP * kJ, 0.f);
     for (int v = 0; v < V; ++v)
       for (int j = 0; j < kJ; ++j) dense_jreg[(size_t)v * kJ + j] = desc->j_regressor[(size_t)v * kJ + j];
@@ -456,6 +472,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     const size_t o_wi = bb.add(widx.data(), widx.size() * 4);
     const size_t o_wv = bb.add(wval.data(), wval.size() * 4);
     const size_t o_djr = bb.add(dense_jreg.data(), dense_jreg.size() * 4);
+    const size_t o_gbh = bb.add(gbh.data(), gbh.size() * 4);
+    const size_t o_gbl = bb.add(gbl.data(), gbl.size() * 4);
 
     DeviceGuard guard(desc->device);
     if (guard.err != cudaSuccess) { delete m; return cuda_fail(guard.err); }
@@ -507,6 +525,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     d.wcsr_idx = reinterpret_cast<const int*>(base + o_wi);
     d.wcsr_val = reinterpret_cast<const float*>(base + o_wv);
     d.dense_jreg = reinterpret_cast<const float*>(base + o_djr);
+    d.bwd_basis_tf32_hi = reinterpret_cast<const uint32_t*>(base + o_gbh);
+    d.bwd_basis_tf32_lo = reinterpret_cast<const uint32_t*>(base + o_gbl);
     *out_model = m;
     return SMPLB200_OK;
   } catch (const std::bad_alloc&) {
@@ -737,10 +757,12 @@ BwdWorkspace carve_bwd(const SmplB200Model* m, long long n, const Plan& p, bool 
   size_t off = w.fwd.total;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t nn = (size_t)std::max<long long>(n, 1);
-  const long long body_tiles = (long long)((nn + kBbBodies - 1) / kBbBodies);
-  const int nchunks = m->d.NC / kBbCols;
-  long long s = (2LL * m->num_sms + body_tiles - 1) / body_tiles;
-  w.slices = (int)std::max<long long>(1, std::min<long long>(s, std::min(kBbMaxSlices, nchunks)));
+  // column slices of the blendshape backward: enough CTAs for ~2 per SM, at most 81
+  const bool tc = p.prec != SMPLB200_PREC_FP32;
+  const long long body_tiles = (long long)(tc ? (nn + kBwdTcBodies - 1) / kBwdTcBodies : (nn + kBbBodies - 1) / kBbBodies);
+  const int nunits = tc ? m->d.NC / kBwdTcStepCols : m->d.NC / kBbCols;
+  long long s = tc ? (2LL * m->num_sms) / body_tiles : (2LL * m->num_sms + body_tiles - 1) / body_tiles;
+  w.slices = (int)std::max<long long>(1, std::min<long long>(s, std::min(kBbMaxSlices, nunits)));
   w.g_vposed = take(nn * 3 * (size_t)m->d.VP * sizeof(float));
   w.g_A = take(nn * kJ * 12 * sizeof(float));
   w.part = take((size_t)w.slices * nn * kCoefK * sizeof(float));
@@ -827,9 +849,13 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
       k_lbs_bwd<false><<<grid, kLbsBwdThreads, 0, s>>>(model->d, la, n);
     CU_TRY(cudaGetLastError());
     // kb1
-    dim3 g1((unsigned)w.slices, (unsigned)((n + kBbBodies - 1) / kBbBodies));
-    k_blend_bwd_fma<<<g1, kBbThreads, kBbSmemBytes, s>>>(model->d, g_vposed, n, w.slices, part);
-    CU_TRY(cudaGetLastError());
+    if (p.prec == SMPLB200_PREC_FP32) {
+      dim3 g1((unsigned)w.slices, (unsigned)((n + kBbBodies - 1) / kBbBodies));
+      k_blend_bwd_fma<<<g1, kBbThreads, kBbSmemBytes, s>>>(model->d, g_vposed, n, w.slices, part);
+      CU_TRY(cudaGetLastError());
+    } else {   // tcgen05: 3xTF32 for the fp32-class modes, 1xTF32 for the reduced-precision ones
+      CU_TRY(launch_blend_bwd_tc(model->d, p.prec == SMPLB200_PREC_BF16X3, g_vposed, n, w.slices, part, s));
+    }
     cb.g_A = g_A;
     cb.g_coef_part = part;
   }

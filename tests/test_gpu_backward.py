@@ -119,6 +119,24 @@ def test_backward_batch_sizes_and_auto_precision(dev, n):
     assert_grads(got, ref, f"n={n}")
 
 
+@pytest.mark.parametrize("precision,rtol", [("bf16x3", GRAD_RTOL), ("tf32", 3e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("n", [5, 130])
+def test_backward_tensor_core_blendshape_gradient(dev, models, precision, rtol, n):
+    """tcgen05 blendshape backward: 3xTF32 for bf16x3 (fp32-class bound), 1xTF32 for tf32 / bf16
+    (stated looser bounds: the recomputed vposed and the g_coef operands are reduced precision)."""
+    m = models["sparse"] if n == 5 else synthetic.make_model(6, num_verts=2000)
+    V = 6890 if n == 5 else 2000
+    b, p, c = synthetic.make_inputs(n, 17)
+    ups = upstream(n, V, 12)
+    layer = SMPL(m, precision=precision).to(dev)
+    got = gpu_grads(layer, dev, b, p, c, ups)
+    ref = oracle_grads(m, b, p, c, ups)
+    for name, g, r in zip(("g_betas", "g_pose", "g_cam"), got, ref):
+        g, r = g.cpu().double(), r.double()
+        err, scale = (g - r).abs().max().item(), r.abs().max().item()
+        assert err <= rtol * scale + GRAD_ATOL, f"{precision} n={n}: {name} err {err:.3e} scale {scale:.3e}"
+
+
 def test_backward_unstaged_large_mesh(dev):
     """V = 10000: one body's g_v + vposed exceed shared memory -> the non-staged skinning kernel."""
     m = synthetic.make_model(4, num_verts=10000)
