@@ -466,7 +466,7 @@ def main():
                 capi.check(lib_.smplb200_backward(
                     hb.ptr, tb.data_ptr(), tp.data_ptr(), tc.data_ptr(), n, jf_.data_ptr(), gv_.data_ptr(),
                     gj_.data_ptr(), gk_.data_ptr(), gb_.data_ptr(), gp_.data_ptr(), gc_.data_ptr(),
-                    wsb_t.data_ptr(), wsb, lay_t.flags, sp_), "smplb200_backward")
+                    None, 0, wsb_t.data_ptr(), wsb, lay_t.flags, sp_), "smplb200_backward")
 
             for _ in range(3):
                 bwd_call()
@@ -475,7 +475,7 @@ def main():
                 "workload": f"trainer-shaped loss at {nt} bodies through the autograd node; smplb200_backward alone at {n} bodies",
                 f"train_step_{nt}_bodies": bw,
                 f"backward_call_{n}_bodies_us": dt_b * 1e6, "backward_bodies_per_s": n / dt_b,
-                "launches_per_backward": int(lib_.smplb200_backward_launch_count(hb.ptr, n, lay_t.flags, 1)),
+                "launches_per_backward": int(lib_.smplb200_backward_launch_count(hb.ptr, n, lay_t.flags, 1, 0)),
                 "cpu_kind": "port (torch autograd of oracle/smpl_ref.py, fp32, one call)"}
         t_kern_end = time.time()
 

@@ -71,8 +71,9 @@ SYMBOLS = {
     "smplb200_lbs": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _u32, _vp]),
     "smplb200_regress_joints": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "smplb200_backward_workspace_bytes": (_sz, [_vp, _i64, _u32, _int]),
-    "smplb200_backward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _u32, _vp]),
-    "smplb200_backward_launch_count": (_int, [_vp, _i64, _u32, _int]),
+    "smplb200_backward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
+                                 _u32, _vp]),
+    "smplb200_backward_launch_count": (_int, [_vp, _i64, _u32, _int, _int]),
     "smplb200_decode_gather": (_int, [C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp,
                                       C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "smplb200_strerror": (C.c_char_p, [_int]),

@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "k_chain.cuh"
+#include "ptx.cuh"
 
 namespace smplb200 {
 
@@ -41,24 +42,43 @@ struct LbsBwdArgs {
 };
 
 inline size_t lbs_bwd_smem_bytes(int V, int VP) {
-  return ((size_t)3 * VP + (size_t)((3 * V + 3) / 4 * 4)) * sizeof(float);
+  // vposed planes | g_v slab (+ up to 15 B of alignment slack on either side of the bulk copy)
+  return ((size_t)3 * VP + (size_t)((3 * V + 3) / 4 * 4) + 8) * sizeof(float);
 }
 
 template <bool STAGED>
 __global__ void __launch_bounds__(kLbsBwdThreads, 1)
 k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
-  extern __shared__ __align__(16) float smem_bw[];
+  extern __shared__ __align__(128) float smem_bw[];
   __shared__ float s_A[kJ * 12];
   __shared__ float s_gj[kJ * 3];
+  __shared__ __align__(8) uint64_t s_bar;
   float* s_vp = smem_bw;                 // [3][VP]
-  float* s_g = smem_bw + 3 * m.VP;       // [V][3]
+  float* s_gbuf = smem_bw + 3 * m.VP;    // 16-byte aligned landing zone of the g_v slab
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = m.V, VP = m.VP;
+  if (STAGED) {
+    if (tid == 0) { ptx::mbar_init(&s_bar, 1); ptx::fence_barrier_init(); }
+    __syncthreads();
+  }
+  uint32_t phase = 0;
 
   for (long long b = blockIdx.x; b < n; b += gridDim.x) {
     __syncthreads();                     // the previous body's phase 2 is done with shared memory
     const float* gv = a.g_verts ? a.g_verts + (size_t)b * V * 3 : nullptr;
     const float* vp = a.vposed + (size_t)b * 3 * VP;
+    // the body's g_v slab starts at a 4-byte aligned address: copy the enclosing 16-byte granules
+    const uint32_t shift = gv ? (uint32_t)(reinterpret_cast<uintptr_t>(gv) & 15u) : 0u;
+    const float* s_g = s_gbuf + shift / 4;
+    if (STAGED && tid == 0) {
+      // one thread stages the whole body with bulk-TMA copies: no load instructions, no registers
+      const uint32_t vp_bytes = 3u * (uint32_t)VP * 4u;
+      const uint32_t g_bytes = gv ? ((shift + (uint32_t)V * 12u + 15u) & ~15u) : 0u;
+      ptx::fence_proxy_async();          // the previous body's generic-proxy accesses come first
+      ptx::mbar_arrive_expect_tx(&s_bar, vp_bytes + g_bytes);
+      ptx::bulk_g2s_split(s_vp, vp, vp_bytes, &s_bar);
+      if (gv) ptx::bulk_g2s_split(s_gbuf, reinterpret_cast<const uint8_t*>(gv) - shift, g_bytes, &s_bar);
+    }
     if (tid < kJ * 12) s_A[tid] = __ldg(a.A + (size_t)b * (kJ * 12) + tid);
     if (tid >= 320 && tid < 320 + kJ * 3) {
       // effective joint gradient that flows into the VERTICES (regressed joints only):
@@ -71,45 +91,45 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
       }
       s_gj[i] = v;
     }
-    if (STAGED) {
-      const float4* src = reinterpret_cast<const float4*>(vp);
-      float4* dst = reinterpret_cast<float4*>(s_vp);
-      for (int i = tid; i < 3 * VP / 4; i += kLbsBwdThreads) dst[i] = __ldg(src + i);
-      if (!a.regressed)
-        for (int i = tid; i < 3 * V; i += kLbsBwdThreads) s_g[i] = gv ? __ldg(gv + i) : 0.f;
-    }
+    if (STAGED && !gv)
+      for (int i = tid; i < 3 * V; i += kLbsBwdThreads) s_gbuf[i] = 0.f;
     __syncthreads();
-    // upstream gradient of vertex v, including the regressed-joint term  J_regressor[v,:] . g_joint
-    auto g_direct = [&](int v, float g[3]) {
-      g[0] = gv ? __ldg(gv + 3 * v) : 0.f;
-      g[1] = gv ? __ldg(gv + 3 * v + 1) : 0.f;
-      g[2] = gv ? __ldg(gv + 3 * v + 2) : 0.f;
-      if (a.regressed) {
-        const float* jr = m.dense_jreg + (size_t)v * kJ;
-        for (int j = 0; j < kJ; ++j) {
-          const float r = __ldg(jr + j);
-          if (r != 0.f) {
-            g[0] = fmaf(r, s_gj[3 * j], g[0]); g[1] = fmaf(r, s_gj[3 * j + 1], g[1]);
-            g[2] = fmaf(r, s_gj[3 * j + 2], g[2]);
-          }
+    // regressed joints: g_v += J_regressor[v,:] . g_joint
+    auto add_regressed = [&](int v, float g[3]) {
+      const float* jr = m.dense_jreg + (size_t)v * kJ;
+      for (int j = 0; j < kJ; ++j) {
+        const float r = __ldg(jr + j);
+        if (r != 0.f) {
+          g[0] = fmaf(r, s_gj[3 * j], g[0]); g[1] = fmaf(r, s_gj[3 * j + 1], g[1]);
+          g[2] = fmaf(r, s_gj[3 * j + 2], g[2]);
         }
       }
     };
-    if (STAGED && a.regressed) {
-      for (int v = tid; v < V; v += kLbsBwdThreads) {
-        float g[3];
-        g_direct(v, g);
-        s_g[3 * v] = g[0]; s_g[3 * v + 1] = g[1]; s_g[3 * v + 2] = g[2];
+    if (STAGED) {
+      ptx::mbar_wait(&s_bar, phase);
+      phase ^= 1;
+      if (a.regressed) {
+        float* sg = s_gbuf + shift / 4;
+        for (int v = tid; v < V; v += kLbsBwdThreads) {
+          float g[3] = {sg[3 * v], sg[3 * v + 1], sg[3 * v + 2]};
+          add_regressed(v, g);
+          sg[3 * v] = g[0]; sg[3 * v + 1] = g[1]; sg[3 * v + 2] = g[2];
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
     auto g_of = [&](int v, float g[3]) {
       if (STAGED) { g[0] = s_g[3 * v]; g[1] = s_g[3 * v + 1]; g[2] = s_g[3 * v + 2]; }
-      else g_direct(v, g);
+      else {
+        g[0] = gv ? __ldg(gv + 3 * v) : 0.f; g[1] = gv ? __ldg(gv + 3 * v + 1) : 0.f;
+        g[2] = gv ? __ldg(gv + 3 * v + 2) : 0.f;
+        if (a.regressed) add_regressed(v, g);
+      }
     };
     auto vp_of = [&](int c, int v) -> float { return STAGED ? s_vp[c * VP + v] : __ldg(vp + (size_t)c * VP + v); };
 
     // ---- phase 1: g_vposed_v = T_R(v)^T g_v with T_R = sum_j w_vj Rw_j
+#pragma unroll 3
     for (int v = tid; v < VP; v += kLbsBwdThreads) {
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       if (v < V) {
@@ -151,24 +171,38 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
     }
 
     // ---- phase 2: g_A[j] = sum_{v in skin(j)} w_vj * g_v (x) [vposed_v, 1]   (warp j)
+    // Lane l takes entries beg + l, + 32, ...; four entries are fetched per trip so the index /
+    // weight loads (L2) and the shared-memory gathers of four entries are in flight together.
     {
       const int beg = __ldg(m.wcsr_ptr + warp), end = __ldg(m.wcsr_ptr + warp + 1);
       float acc[12];
 #pragma unroll
       for (int e = 0; e < 12; ++e) acc[e] = 0.f;
-      for (int i = beg + lane; i < end; i += 32) {
-        const int v = __ldg(m.wcsr_idx + i);
-        const float w = __ldg(m.wcsr_val + i);
-        float g[3];
-        g_of(v, g);
-        const float p0 = vp_of(0, v), p1 = vp_of(1, v), p2 = vp_of(2, v);
+      for (int i0 = beg + lane; i0 < end; i0 += 4 * 32) {
+        int vi[4]; float wi[4];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float wg = w * g[r];
-          acc[4 * r] = fmaf(wg, p0, acc[4 * r]);
-          acc[4 * r + 1] = fmaf(wg, p1, acc[4 * r + 1]);
-          acc[4 * r + 2] = fmaf(wg, p2, acc[4 * r + 2]);
-          acc[4 * r + 3] += wg;
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 32 * u;
+          const bool ok = i < end;
+          vi[u] = ok ? __ldg(m.wcsr_idx + i) : 0;
+          wi[u] = ok ? __ldg(m.wcsr_val + i) : 0.f;
+        }
+        float gg[4][3], pp[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          g_of(vi[u], gg[u]);
+          pp[u][0] = vp_of(0, vi[u]); pp[u][1] = vp_of(1, vi[u]); pp[u][2] = vp_of(2, vi[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {     // entries in ascending order: same sum order as one-at-a-time
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float wg = wi[u] * gg[u][r];
+            acc[4 * r] = fmaf(wg, pp[u][0], acc[4 * r]);
+            acc[4 * r + 1] = fmaf(wg, pp[u][1], acc[4 * r + 1]);
+            acc[4 * r + 2] = fmaf(wg, pp[u][2], acc[4 * r + 2]);
+            acc[4 * r + 3] += wg;
+          }
         }
       }
 #pragma unroll
@@ -303,6 +337,7 @@ __device__ __forceinline__ void rodrigues_bwd(float tx, float ty, float tz, cons
 __global__ void __launch_bounds__(kChainWarps * 32)
 k_chain_bwd(DeviceModel m, ChainBwdArgs a, long long n) {
   __shared__ float s_c[kChainWarps][kJ][16];   // child -> parent: gRw(9) | gtw(3) | gJr(3)
+  __shared__ float s_gc[kChainWarps][kCoefK];  // g_coef of this body: the column slices added in order
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = (long long)blockIdx.x * kChainWarps + warp;
   if (b >= n) return;   // whole warp exits together
@@ -310,6 +345,22 @@ k_chain_bwd(DeviceModel m, ChainBwdArgs a, long long n) {
   const int j = lane < kJ ? lane : 0;
   const bool active = lane < kJ;
   const int NB = m.NB;
+
+  // g_coef = sum over the column slices of kb1's partials (coalesced, slice order, 7 sums per lane)
+  if (a.g_coef_part) {
+    float acc[kCoefK / 32];
+#pragma unroll
+    for (int t = 0; t < kCoefK / 32; ++t) acc[t] = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < a.slices; ++s) {
+      const float* p = a.g_coef_part + ((size_t)s * n + b) * kCoefK + lane;
+#pragma unroll
+      for (int t = 0; t < kCoefK / 32; ++t) acc[t] += __ldg(p + 32 * t);
+    }
+#pragma unroll
+    for (int t = 0; t < kCoefK / 32; ++t) s_gc[warp][lane + 32 * t] = acc[t];
+    __syncwarp();
+  }
 
   // ---- forward recompute (k_pose_chain)
   float th0 = 0.f, th1 = 0.f, th2 = 0.f;
@@ -414,11 +465,8 @@ k_chain_bwd(DeviceModel m, ChainBwdArgs a, long long n) {
 #pragma unroll
   for (int e = 0; e < 9; ++e) gR[e] = 0.f;
   if (active && j >= 1 && a.g_coef_part) {
-    for (int s = 0; s < a.slices; ++s) {
-      const float* p = a.g_coef_part + ((size_t)s * n + b) * kCoefK + NB + 9 * (j - 1);
 #pragma unroll
-      for (int e = 0; e < 9; ++e) gR[e] += __ldg(p + e);
-    }
+    for (int e = 0; e < 9; ++e) gR[e] = s_gc[warp][NB + 9 * (j - 1) + e];
   }
 
   // ---- chain, leaves to root
@@ -481,8 +529,7 @@ k_chain_bwd(DeviceModel m, ChainBwdArgs a, long long n) {
     if (lane == k) mine = v;
   }
   if (lane < NB) {
-    if (a.g_coef_part)
-      for (int s = 0; s < a.slices; ++s) mine += __ldg(a.g_coef_part + ((size_t)s * n + b) * kCoefK + lane);
+    if (a.g_coef_part) mine += s_gc[warp][lane];
     a.g_betas[b * NB + lane] = mine;
   }
   // ---- Rodrigues

@@ -54,6 +54,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity, 1000000u)) return;   // up to 1 ms asleep per attempt
   __trap();
 }
+// Orders this thread's earlier generic-proxy shared-memory accesses (made visible to it by a
+// barrier) before later async-proxy operations (bulk copies) on the same locations.
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // ---- bulk TMA: global -> shared, completion counted on an mbarrier --------------------------
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
                                          uint64_t* bar) {

@@ -748,7 +748,12 @@ struct BwdWorkspace {
   size_t total = 0;
 };
 
-BwdWorkspace carve_bwd(const SmplB200Model* m, long long n, const Plan& p, bool vertex_path) {
+// kb1 runs on tcgen05 unless the caller pinned the fp32 FMA path explicitly; under AUTO the
+// operands are split 3xTF32 (fp32-class accuracy) at every batch size.
+inline bool bwd_blend_tc(uint32_t flags) { return (flags & SMPLB200_PREC_MASK) != SMPLB200_PREC_FP32; }
+inline bool bwd_blend_x3(const Plan& p) { return p.prec == SMPLB200_PREC_FP32 || p.prec == SMPLB200_PREC_BF16X3; }
+
+BwdWorkspace carve_bwd(const SmplB200Model* m, long long n, const Plan& p, bool vertex_path, bool tc) {
   BwdWorkspace w;
   if (!vertex_path) { w.total = 256; return w; }
   Plan pf = p;
@@ -758,7 +763,6 @@ BwdWorkspace carve_bwd(const SmplB200Model* m, long long n, const Plan& p, bool 
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t nn = (size_t)std::max<long long>(n, 1);
   // column slices of the blendshape backward: enough CTAs for ~2 per SM, at most 81
-  const bool tc = p.prec != SMPLB200_PREC_FP32;
   const long long body_tiles = (long long)(tc ? (nn + kBwdTcBodies - 1) / kBwdTcBodies : (nn + kBbBodies - 1) / kBbBodies);
   const int nunits = tc ? m->d.NC / kBwdTcStepCols : m->d.NC / kBbCols;
   long long s = tc ? (2LL * m->num_sms) / body_tiles : (2LL * m->num_sms + body_tiles - 1) / body_tiles;
@@ -777,19 +781,22 @@ size_t smplb200_backward_workspace_bytes(const SmplB200Model* model, int64_t n, 
                                          int vertex_path) {
   Plan p;
   if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
-  return carve_bwd(model, n, p, vertex_path != 0).total;
+  return carve_bwd(model, n, p, vertex_path != 0, bwd_blend_tc(flags)).total;
 }
 
-int smplb200_backward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags, int vertex_path) {
+int smplb200_backward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags, int vertex_path,
+                                   int reuse_forward_workspace) {
   Plan p;
   if (!model || n <= 0 || !resolve_plan(model, n, flags, &p)) return 0;
-  return vertex_path ? 5 : 1;     // k2, k1, kb3, kb1, kb2  |  kb2 alone
+  if (!vertex_path) return 1;                                  // kb2 alone
+  return (reuse_forward_workspace && model->chunk == 0) ? 3 : 5;   // [k2, k1,] kb3, kb1, kb2
 }
 
 int smplb200_backward(const SmplB200Model* model, const float* betas, const float* pose,
                       const float* cam, int64_t n, const float* joints_fwd,
                       const float* g_vertices, const float* g_joints, const float* g_kp2d,
                       float* g_betas, float* g_pose, float* g_cam,
+                      const void* forward_workspace, size_t forward_workspace_bytes,
                       void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
   if (!model || n < 0) return SMPLB200_ERR_INVALID_ARG;
   if (n == 0) return SMPLB200_OK;
@@ -799,7 +806,8 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
   if (!resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
   if (p.regressed && g_kp2d && !joints_fwd) return SMPLB200_ERR_INVALID_ARG;
   const bool vertex_path = g_vertices != nullptr || (p.regressed && (g_joints || g_kp2d));
-  const BwdWorkspace w = carve_bwd(model, n, p, vertex_path);
+  const bool tc = bwd_blend_tc(flags);
+  const BwdWorkspace w = carve_bwd(model, n, p, vertex_path, tc);
   if (vertex_path &&
       (!workspace || workspace_bytes < w.total || (reinterpret_cast<uintptr_t>(workspace) & 255u)))
     return SMPLB200_ERR_WORKSPACE;
@@ -823,6 +831,15 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
     float* g_vposed = reinterpret_cast<float*>(ws + w.g_vposed);
     float* g_A = reinterpret_cast<float*>(ws + w.g_A);
     float* part = reinterpret_cast<float*>(ws + w.part);
+    int st = SMPLB200_OK;
+    const Workspace fw = carve(model, n, p);      // layout of the forward call's own workspace
+    if (forward_workspace && model->chunk == 0 && forward_workspace_bytes >= fw.total &&
+        (reinterpret_cast<uintptr_t>(forward_workspace) & 255u) == 0) {
+      // reuse the intermediates the forward left behind
+      const uint8_t* f = static_cast<const uint8_t*>(forward_workspace);
+      A = const_cast<float*>(reinterpret_cast<const float*>(f + fw.A));
+      vposed = const_cast<float*>(reinterpret_cast<const float*>(f + fw.vposed));
+    } else {
     // recompute k2 + k1 (same kernels and precision as the forward)
     ChainOut out{};
     out.A = A;
@@ -831,11 +848,12 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
       out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_hi);
     if (p.prec == SMPLB200_PREC_BF16X3) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_lo);
     if (p.prec == SMPLB200_PREC_TF32) out.coef_tf32 = reinterpret_cast<uint32_t*>(ws + w.fwd.coef_tf32);
-    int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
+    st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
     if (st) return st;
     if (p.prec == SMPLB200_PREC_FP32) st = launch_blend_fma(model, coef, n, vposed, s);
     else CU_TRY(launch_blend_tc_any(model, p.prec, out.coef_bf16_hi, out.coef_bf16_lo, out.coef_tf32, n, vposed, s));
     if (st) return st;
+    }
     // kb3
     LbsBwdArgs la{};
     la.vposed = vposed; la.A = A; la.g_verts = g_vertices;
@@ -849,12 +867,12 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
       k_lbs_bwd<false><<<grid, kLbsBwdThreads, 0, s>>>(model->d, la, n);
     CU_TRY(cudaGetLastError());
     // kb1
-    if (p.prec == SMPLB200_PREC_FP32) {
+    if (!tc) {
       dim3 g1((unsigned)w.slices, (unsigned)((n + kBbBodies - 1) / kBbBodies));
       k_blend_bwd_fma<<<g1, kBbThreads, kBbSmemBytes, s>>>(model->d, g_vposed, n, w.slices, part);
       CU_TRY(cudaGetLastError());
     } else {   // tcgen05: 3xTF32 for the fp32-class modes, 1xTF32 for the reduced-precision ones
-      CU_TRY(launch_blend_bwd_tc(model->d, p.prec == SMPLB200_PREC_BF16X3, g_vposed, n, w.slices, part, s));
+      CU_TRY(launch_blend_bwd_tc(model->d, bwd_blend_x3(p), g_vposed, n, w.slices, part, s));
     }
     cb.g_A = g_A;
     cb.g_coef_part = part;

@@ -55,7 +55,13 @@ class _SMPLFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, layer, flags, betas, pose, cam):
-        outs = layer._forward_impl(betas, pose, cam, flags)
+        keep = layer.save_forward_workspace
+        outs = layer._forward_impl(betas, pose, cam, flags, return_workspace=keep)
+        ctx.fwd_ws = None
+        if keep:
+            outs, ws = outs[:-1], outs[-1]
+            # kept alive for the backward (A and vposed are reused instead of recomputed) unless big
+            ctx.fwd_ws = ws if (ws is not None and ws.numel() <= layer.save_forward_workspace_max_bytes) else None
         ctx.layer, ctx.flags, ctx.has_cam = layer, flags, cam is not None
         ctx.set_materialize_grads(False)      # an output that does not reach the loss stays None
         ctx.save_for_backward(betas, pose, cam, outs[1])
@@ -84,11 +90,14 @@ class _SMPLFunction(torch.autograd.Function):
                 if wsb == 0:
                     raise RuntimeError("smplb200_backward_workspace_bytes rejected the flag combination")
                 ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+                fws = ctx.fwd_ws
                 capi.check(capi.lib().smplb200_backward(
                     h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(joints),
                     _ptr(g_verts), _ptr(g_joints), _ptr(g_kp2d),
                     _ptr(g_betas), _ptr(g_pose), _ptr(g_cam),
+                    _ptr(fws), 0 if fws is None else fws.numel(),
                     _ptr(ws), wsb, flags, _stream_ptr(device)), "smplb200_backward")
+        ctx.fwd_ws = None
         need = ctx.needs_input_grad   # (layer, flags, betas, pose, cam)
         return (None, None, g_betas if need[2] else None, g_pose if need[3] else None,
                 g_cam if (ctx.has_cam and need[4]) else None)
@@ -108,8 +117,13 @@ class SMPL(nn.Module):
       lbs: 'auto' | 'fma' | 'tc' | 'dense'  (skinning kernel)
     """
 
-    def __init__(self, model, precision="auto", joints="kinematic", rotate_base=False, lbs="auto"):
+    def __init__(self, model, precision="auto", joints="kinematic", rotate_base=False, lbs="auto",
+                 save_forward_workspace=True, save_forward_workspace_max_bytes=1 << 30):
         super().__init__()
+        # training: keep the forward's scratch (A, vposed: ~0.2 MB/body) for the backward instead of
+        # recomputing it, up to this many bytes per call
+        self.save_forward_workspace = bool(save_forward_workspace)
+        self.save_forward_workspace_max_bytes = int(save_forward_workspace_max_bytes)
         if isinstance(model, (str, bytes)):      # .npz / pickle, official SMPL layout or the eager layer's
             model = model_io.load_model(model)
         elif "kintree_table" in model or np.asarray(model["shapedirs"]).ndim == 3:
@@ -171,13 +185,14 @@ class SMPL(nn.Module):
             return _SMPLFunction.apply(self, flags, betas, pose, cam)
         return self._forward_impl(betas, pose, cam, flags)
 
-    def _forward_impl(self, betas, pose, cam, flags):
+    def _forward_impl(self, betas, pose, cam, flags, return_workspace=False):
         device, n = betas.device, int(betas.shape[0])
         h = self.handle(device)
         with torch.cuda.device(device):
             verts = torch.empty((n, self.num_verts, 3), dtype=torch.float32, device=device)
             joints = torch.empty((n, self.num_joints, 3), dtype=torch.float32, device=device)
             kp2d = None if cam is None else torch.empty((n, self.num_joints, 2), dtype=torch.float32, device=device)
+            ws = None
             if n > 0:
                 ws_bytes = h.workspace_bytes(n, flags)
                 if ws_bytes == 0:
@@ -186,7 +201,8 @@ class SMPL(nn.Module):
                 capi.check(capi.lib().smplb200_forward(
                     h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(verts), _ptr(joints), _ptr(kp2d),
                     _ptr(ws), ws_bytes, flags, _stream_ptr(device)), "smplb200_forward")
-        return (verts, joints) if cam is None else (verts, joints, kp2d)
+        outs = (verts, joints) if cam is None else (verts, joints, kp2d)
+        return outs + (ws,) if return_workspace else outs
 
     def launch_count(self, n: int, with_projection: bool, device=None) -> int:
         h = self.handle(device if device is not None else self.v_template.device)

@@ -173,6 +173,9 @@ int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, i
  * and g_kp2d.  `g_cam` may be NULL; it requires `cam`.  The vertex path (g_vertices given, or
  * regressed joints with g_joints/g_kp2d) needs `smplb200_backward_workspace_bytes(..., 1)` of
  * 256-byte aligned scratch; without it (`vertex_path` = 0) the workspace may be NULL.
+ * `forward_workspace` (optional, may be NULL): the workspace of the smplb200_forward call being
+ * differentiated (same n and flags, untouched since) -- its A and vposed intermediates are then
+ * reused instead of recomputed.  Ignored when the forward ran in chunks (SMPLB200_CHUNK).
  * Gradients are summed in a fixed order (no atomics): bitwise reproducible.                      */
 size_t smplb200_backward_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags,
                                          int vertex_path);
@@ -180,10 +183,11 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
                       const float* cam, int64_t n, const float* joints_fwd,
                       const float* g_vertices, const float* g_joints, const float* g_kp2d,
                       float* g_betas, float* g_pose, float* g_cam,
+                      const void* forward_workspace, size_t forward_workspace_bytes,
                       void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 /* Kernel launches one backward call issues (bench accounting).                                 */
 int smplb200_backward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags,
-                                   int vertex_path);
+                                   int vertex_path, int reuse_forward_workspace);
 
 /* ---- the producer of the per-person vectors ------------------------ */
 /* Fused NMS + top-K + head gather, one launch:

@@ -55,16 +55,18 @@ def main():
             capi.check(lib.smplb200_forward(h.ptr, b.data_ptr(), p.data_ptr(), c.data_ptr(), n, v.data_ptr(),
                                             j.data_ptr(), k.data_ptr(), wf.data_ptr(), wf.numel(), layer.flags, s), "fwd")
 
-        def bwd(vertex):
+        def bwd(vertex, reuse=False):
             capi.check(lib.smplb200_backward(h.ptr, b.data_ptr(), p.data_ptr(), c.data_ptr(), n, j.data_ptr(),
                                              gv.data_ptr() if vertex else None, gj.data_ptr(), gk.data_ptr(),
-                                             gb.data_ptr(), gp.data_ptr(), gc.data_ptr(), wb.data_ptr(), wb.numel(),
-                                             layer.flags, s), "bwd")
+                                             gb.data_ptr(), gp.data_ptr(), gc.data_ptr(),
+                                             wf.data_ptr() if reuse else None, wf.numel() if reuse else 0,
+                                             wb.data_ptr(), wb.numel(), layer.flags, s), "bwd")
         if a.once:
-            fwd(); bwd(True); bwd(False); torch.cuda.synchronize()
+            fwd(); bwd(True); bwd(True, True); bwd(False); torch.cuda.synchronize()
             continue
         print(json.dumps({"n": n, "forward_us": round(timed(fwd, a.iters, flush), 1),
                           "backward_vertex_path_us": round(timed(lambda: bwd(True), a.iters, flush), 1),
+                          "backward_vertex_path_reusing_forward_ws_us": round(timed(lambda: bwd(True, True), a.iters, flush), 1),
                           "backward_joints_only_us": round(timed(lambda: bwd(False), a.iters, flush), 1),
                           "backward_workspace_MB": round(wb.numel() / 2**20, 1)}), flush=True)
 

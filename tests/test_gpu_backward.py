@@ -173,6 +173,18 @@ def test_backward_is_bitwise_reproducible(dev, models):
     assert all(torch.equal(a[:16], b_) for a, b_ in zip(g1, g3))
 
 
+@pytest.mark.parametrize("n", [9, 300])
+def test_reusing_the_forward_workspace_changes_nothing(dev, models, n):
+    """A and vposed kept from the forward == A and vposed recomputed: bitwise equal gradients."""
+    m = models["sparse"] if n == 9 else synthetic.make_model(2, num_verts=1000)
+    V = 6890 if n == 9 else 1000
+    b, p, c = synthetic.make_inputs(n, 4)
+    ups = upstream(n, V, 14)
+    g_keep = gpu_grads(SMPL(m, save_forward_workspace=True).to(dev), dev, b, p, c, ups)
+    g_re = gpu_grads(SMPL(m, save_forward_workspace=False).to(dev), dev, b, p, c, ups)
+    assert all(torch.equal(x, y) for x, y in zip(g_keep, g_re))
+
+
 def test_training_style_loss(dev, models):
     """A loss shaped like an HMR trainer's (L1 on 2-D keypoints + L2 on 3-D joints + priors)."""
     m = models["sparse"]
@@ -207,15 +219,17 @@ def test_backward_errors_and_empty(dev, models):
     lib = capi.lib()
     # g_kp2d without cam
     st = lib.smplb200_backward(h.ptr, b.data_ptr(), p.data_ptr(), None, 2, None, None, None, gk.data_ptr(),
-                               gb.data_ptr(), gp.data_ptr(), None, None, 0, layer.flags, None)
+                               gb.data_ptr(), gp.data_ptr(), None, None, 0, None, 0, layer.flags, None)
     assert st == 1
     # vertex path without workspace
     gv = z(2, 6890, 3)
     st = lib.smplb200_backward(h.ptr, b.data_ptr(), p.data_ptr(), None, 2, None, gv.data_ptr(), None, None,
-                               gb.data_ptr(), gp.data_ptr(), None, None, 0, layer.flags, None)
+                               gb.data_ptr(), gp.data_ptr(), None, None, 0, None, 0, layer.flags, None)
     assert st == 3
     assert lib.smplb200_backward_workspace_bytes(h.ptr, 2, layer.flags, 1) > 2 * 3 * 6912 * 4
-    assert lib.smplb200_backward_launch_count(h.ptr, 2, layer.flags, 1) == 5
+    assert lib.smplb200_backward_launch_count(h.ptr, 2, layer.flags, 1, 0) == 5
+    assert lib.smplb200_backward_launch_count(h.ptr, 2, layer.flags, 1, 1) == 3
+    assert lib.smplb200_backward_launch_count(h.ptr, 2, layer.flags, 0, 0) == 1
     # empty batch
     tb, tp = z(0, 10).requires_grad_(), z(0, 72).requires_grad_()
     v, j = layer(tb, tp)
