@@ -36,8 +36,8 @@ struct DeviceModel {
   const uint32_t* w_tf32;              // [VP][48] skinning-weight rows, tf32 W_hi(24) | W_lo(24)
   // backward pass (k_backward.cuh)
   const int* wcsr_ptr;                 // [J+1] skinning weights as CSR over JOINTS (transpose of ELL)
-  const int* wcsr_idx;                 // [nnz] vertex index, ascending within a joint
-  const float* wcsr_val;               // [nnz]
+  const int* wcsr_idx;                 // [rounds*32] vertex index; lane l of a round has v % 32 == l (bank-conflict free)
+  const float* wcsr_val;               // [rounds*32] weight (0 for fillers)
   const float* dense_jreg;             // [VP, J] joint regressor rows (regressed-joint gradient)
   const uint32_t* bwd_basis_tf32_hi;   // [NC/32][8][224][4] K-major tiles of basis[k, col] (k_blend_bwd_tc)
   const uint32_t* bwd_basis_tf32_lo;   // same, low part of the 2-term tf32 split

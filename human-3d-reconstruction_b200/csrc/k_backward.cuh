@@ -50,7 +50,10 @@ template <bool STAGED>
 __global__ void __launch_bounds__(kLbsBwdThreads, 1)
 k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
   extern __shared__ __align__(128) float smem_bw[];
-  __shared__ float s_A[kJ * 12];
+  // The body's 24 transforms, one float4 per (joint, row), replicated 8x: lane l reads replica
+  // l % 8, which lives in bank quad l % 8 whatever the joint, so the per-vertex gather of A by
+  // joint index is bank-conflict free (unreplicated it cost ~10 wavefronts per LDS.128, round-1 ncu).
+  __shared__ float4 s_A8[kJ * 3 * 8];
   __shared__ float s_gj[kJ * 3];
   __shared__ __align__(8) uint64_t s_bar;
   float* s_vp = smem_bw;                 // [3][VP]
@@ -79,11 +82,12 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
       ptx::bulk_g2s_split(s_vp, vp, vp_bytes, &s_bar);
       if (gv) ptx::bulk_g2s_split(s_gbuf, reinterpret_cast<const uint8_t*>(gv) - shift, g_bytes, &s_bar);
     }
-    if (tid < kJ * 12) s_A[tid] = __ldg(a.A + (size_t)b * (kJ * 12) + tid);
-    if (tid >= 320 && tid < 320 + kJ * 3) {
+    if (tid < kJ * 3 * 8)
+      s_A8[tid] = __ldg(reinterpret_cast<const float4*>(a.A + (size_t)b * (kJ * 12)) + (tid >> 3));
+    if (tid >= 640 && tid < 640 + kJ * 3) {
       // effective joint gradient that flows into the VERTICES (regressed joints only):
       // g_joints + s * g_kp2d on x,y
-      const int i = tid - 320, j = i / 3, c = i - 3 * j;
+      const int i = tid - 640, j = i / 3, c = i - 3 * j;
       float v = 0.f;
       if (a.regressed) {
         if (a.g_joints) v = __ldg(a.g_joints + (size_t)b * (kJ * 3) + i);
@@ -105,18 +109,19 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
         }
       }
     };
-    if (STAGED) {
+    // Without the regressed-joint term phase 1 needs nothing from shared memory but A: it reads
+    // g_v straight from global (coalesced) WHILE the bulk copies land, and the wait moves to phase 2.
+    const bool early = STAGED && !a.regressed;
+    if (STAGED && !early) {
       ptx::mbar_wait(&s_bar, phase);
       phase ^= 1;
-      if (a.regressed) {
-        float* sg = s_gbuf + shift / 4;
-        for (int v = tid; v < V; v += kLbsBwdThreads) {
-          float g[3] = {sg[3 * v], sg[3 * v + 1], sg[3 * v + 2]};
-          add_regressed(v, g);
-          sg[3 * v] = g[0]; sg[3 * v + 1] = g[1]; sg[3 * v + 2] = g[2];
-        }
-        __syncthreads();
+      float* sg = s_gbuf + shift / 4;
+      for (int v = tid; v < V; v += kLbsBwdThreads) {
+        float g[3] = {sg[3 * v], sg[3 * v + 1], sg[3 * v + 2]};
+        add_regressed(v, g);
+        sg[3 * v] = g[0]; sg[3 * v + 1] = g[1]; sg[3 * v + 2] = g[2];
       }
+      __syncthreads();
     }
     auto g_of = [&](int v, float g[3]) {
       if (STAGED) { g[0] = s_g[3 * v]; g[1] = s_g[3 * v + 1]; g[2] = s_g[3 * v + 2]; }
@@ -134,7 +139,12 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       if (v < V) {
         float g[3];
-        g_of(v, g);
+        if (early) {
+          g[0] = gv ? __ldg(gv + 3 * v) : 0.f; g[1] = gv ? __ldg(gv + 3 * v + 1) : 0.f;
+          g[2] = gv ? __ldg(gv + 3 * v + 2) : 0.f;
+        } else {
+          g_of(v, g);
+        }
         float T[9];
 #pragma unroll
         for (int e = 0; e < 9; ++e) T[e] = 0.f;
@@ -144,22 +154,28 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
           const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
-            const float* Aj = s_A + ((jj >> (8 * s)) & 0xffu) * 12;
+            const float4* Aj = s_A8 + ((((jj >> (8 * s)) & 0xffu) * 3) << 3) + (lane & 7);
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) T[3 * r + c] = fmaf(ws[s], Aj[4 * r + c], T[3 * r + c]);
+            for (int r = 0; r < 3; ++r) {
+              const float4 row = Aj[r << 3];
+              T[3 * r] = fmaf(ws[s], row.x, T[3 * r]);
+              T[3 * r + 1] = fmaf(ws[s], row.y, T[3 * r + 1]);
+              T[3 * r + 2] = fmaf(ws[s], row.z, T[3 * r + 2]);
+            }
           }
         } else {
           const float* wr = m.dense_w + (size_t)v * kJ;
           for (int j = 0; j < kJ; ++j) {
             const float w = __ldg(wr + j);
             if (w == 0.f) continue;
-            const float* Aj = s_A + j * 12;
+            const float4* Aj = s_A8 + ((j * 3) << 3) + (lane & 7);
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) T[3 * r + c] = fmaf(w, Aj[4 * r + c], T[3 * r + c]);
+            for (int r = 0; r < 3; ++r) {
+              const float4 row = Aj[r << 3];
+              T[3 * r] = fmaf(w, row.x, T[3 * r]);
+              T[3 * r + 1] = fmaf(w, row.y, T[3 * r + 1]);
+              T[3 * r + 2] = fmaf(w, row.z, T[3 * r + 2]);
+            }
           }
         }
         o0 = fmaf(T[6], g[2], fmaf(T[3], g[1], T[0] * g[0]));
@@ -170,6 +186,10 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
       dst[0] = o0; dst[VP] = o1; dst[2 * (size_t)VP] = o2;
     }
 
+    if (early) {
+      ptx::mbar_wait(&s_bar, phase);
+      phase ^= 1;
+    }
     // ---- phase 2: g_A[j] = sum_{v in skin(j)} w_vj * g_v (x) [vposed_v, 1]   (warp j)
     // Lane l takes entries beg + l, + 32, ...; four entries are fetched per trip so the index /
     // weight loads (L2) and the shared-memory gathers of four entries are in flight together.

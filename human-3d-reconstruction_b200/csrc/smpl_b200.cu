@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -387,13 +388,25 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     }
     if (jidx.empty()) { jidx.push_back(0); jval.push_back(0.f); }
     // ---- backward pass: skinning weights as CSR over joints, dense joint-regressor rows
+    // Entries of a joint are laid out in ROUNDS of 32 (one per lane of the warp that reduces the
+    // joint); within a round lane l holds a vertex with v % 32 == l (or a zero-weight filler), so
+    // the 32 shared-memory gathers of a round hit 32 distinct banks (bank = v % 32 for the vposed
+    // planes, 3v + r % 32 for g_v).  Unordered lists cost ~3.5 wavefronts per gather (round-1 ncu).
     std::vector<int> wptr(kJ + 1, 0), widx;
     std::vector<float> wval;
     for (int j = 0; j < kJ; ++j) {
+      std::vector<std::vector<std::pair<int, float>>> bucket(32);
       for (int v = 0; v < V; ++v) {
         const float wv = desc->weights[(size_t)v * kJ + j];
-        if (wv != 0.f) { widx.push_back(v); wval.push_back(wv); }
+        if (wv != 0.f) bucket[v & 31].push_back({v, wv});
       }
+      size_t rounds = 0;
+      for (auto& bk : bucket) rounds = std::max(rounds, bk.size());
+      for (size_t r = 0; r < rounds; ++r)
+        for (int l = 0; l < 32; ++l) {
+          if (r < bucket[l].size()) { widx.push_back(bucket[l][r].first); wval.push_back(bucket[l][r].second); }
+          else { widx.push_back(std::min(l, V - 1)); wval.push_back(0.f); }
+        }
       wptr[j + 1] = (int)widx.size();
     }
     if (widx.empty()) { widx.push_back(0); wval.push_back(0.f); }

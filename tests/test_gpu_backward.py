@@ -137,6 +137,18 @@ def test_backward_tensor_core_blendshape_gradient(dev, models, precision, rtol, 
         assert err <= rtol * scale + GRAD_ATOL, f"{precision} n={n}: {name} err {err:.3e} scale {scale:.3e}"
 
 
+def test_backward_large_batch_default_path(dev):
+    """n = 520 under AUTO: tcgen05 recompute and tcgen05 blendshape backward, 4 persistent bodies per CTA."""
+    m = synthetic.make_model(8, num_verts=1500)
+    n = 520
+    b, p, c = synthetic.make_inputs(n, 29)
+    ups = upstream(n, 1500, 16)
+    layer = SMPL(m).to(dev)
+    got = gpu_grads(layer, dev, b, p, c, ups)
+    ref = oracle_grads(m, b, p, c, ups)
+    assert_grads(got, ref, "n=520 auto")
+
+
 def test_backward_unstaged_large_mesh(dev):
     """V = 10000: one body's g_v + vposed exceed shared memory -> the non-staged skinning kernel."""
     m = synthetic.make_model(4, num_verts=10000)
