@@ -440,7 +440,8 @@ def main():
 
             def train_step(with_verts):
                 bt.grad = pt.grad = ct.grad = None
-                loss_of(lay_t(bt, pt, ct), with_verts).backward()
+                with torch.enable_grad():
+                    loss_of(lay_t(bt, pt, ct), with_verts).backward()
 
             bw = {}
             for name, wv in (("loss_on_joints_kp2d", False), ("loss_on_vertices_joints_kp2d", True)):
@@ -449,7 +450,8 @@ def main():
                 dt_t = time_loop(lambda: train_step(wv), 20, torch) / 20
                 cb, cp, cc = (torch.from_numpy(x).requires_grad_() for x in arrs)
                 t0 = time.perf_counter()
-                loss_of(oracle_forward(model, cb, cp, cc), wv).backward()
+                with torch.enable_grad():
+                    loss_of(oracle_forward(model, cb, cp, cc), wv).backward()
                 dt_c = time.perf_counter() - t0
                 bw[name] = {"gpu_fwd_bwd_us": dt_t * 1e6, "cpu_autograd_port_us": dt_c * 1e6}
             # the backward call alone at the headline batch (vertex path, device-resident gradients)
