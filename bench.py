@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bodies-per-gpu", type=int, default=BODIES_PER_GPU)
+    ap.add_argument("--total-bodies", type=int, default=0,
+                    help="strong scaling: fix the whole job's batch (SURVEY C4: 65536) and shard it over the ranks")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16", "tf32", "bf16x3", "auto"],
                     help="blendshape MMA operands; bf16x3 (default) is the near-fp32 split-bf16 mode")
     ap.add_argument("--lbs", default="tc", choices=["fma", "tc", "dense", "auto"])
@@ -245,6 +247,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     n = args.bodies_per_gpu
+    strong = args.total_bodies > 0
+    if strong:      # contiguous shards of a fixed job
+        if args.total_bodies % world:
+            raise SystemExit("--total-bodies must be divisible by the number of ranks")
+        n = sharding.shard_bounds(args.total_bodies, world, 0)[1]
     peaks = load_peaks()
 
     model = synthetic.make_model(0, weights=args.weights)
@@ -346,7 +353,10 @@ def main():
 
         e2e_iters = max(10, min(args.steps, 200))
         e2e_val, h2d, d2h = e2e_rate(False, e2e_iters)
-        e2e_v_val, h2d_v, d2h_v = e2e_rate(True, max(3, min(args.steps, 10)))
+        if strong:      # scaling runs skip the side legs (vertex D2H, operand variants, next rows)
+            e2e_v_val, h2d_v, d2h_v = None, None, None
+        else:
+            e2e_v_val, h2d_v, d2h_v = e2e_rate(True, max(3, min(args.steps, 10)))
 
         # ---- per-kernel timing (rank 0) for the roofline ------------------------------------
         kernels = {}
@@ -385,7 +395,7 @@ def main():
                 kernels[name] = {"us": dt * 1e6, "gbs": byts * n / dt * 1e-9}
         # ---- other blendshape operand precisions, same workload (short loops) ---------------
         variants = {}
-        if rank == 0:
+        if rank == 0 and not strong:
             for prec in ("bf16x3", "bf16", "tf32", "fp32"):
                 if prec == args.precision:
                     continue
@@ -397,7 +407,7 @@ def main():
                 variants[prec] = {"bodies_per_s": n / dt, "us_per_step": dt * 1e6}
         # ---- next §8(f) row: fused decode -> gather producer at the configs[4] shape -----------
         next_rows = {}
-        if rank == 0:
+        if rank == 0 and not strong:
             from human_3d_reconstruction_b200 import decode_gather
             from oracle.decode_ref import decode_gather as decode_cpu
             Bi, Kp, Hm = 32, 32, 128
@@ -488,7 +498,35 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         bps, cores, times = cpu_oracle_throughput(model, 256, 3, 10, min_seconds=12.0)
+        cpu_model = ""
+        try:
+            with open("/proc/cpuinfo") as fh:
+                cpu_model = next((ln.split(":", 1)[1].strip() for ln in fh if ln.startswith("model name")), "")
+        except OSError:
+            pass
+        # single-body latency of the eager layer on the host (all threads, then one thread)
+        import torch as _t
+        from oracle.smpl_ref import smpl_forward as _oracle_fwd
+        b1_, p1_, c1_ = synthetic.make_inputs(1, 3)
+
+        def _lat():
+            for _ in range(3):
+                _oracle_fwd(model, b1_, p1_, c1_)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                _oracle_fwd(model, b1_, p1_, c1_)
+            return (time.perf_counter() - t0) / 20 * 1e6
+
+        with _t.no_grad():
+            lat_all = _lat()
+            nt_prev = _t.get_num_threads()
+            _t.set_num_threads(1)
+            lat_one = _lat()
+            _t.set_num_threads(nt_prev)
         cpu = {"value": bps, "unit": "bodies/s", "cores": cores, "kind": "port",
+               "cpu_model": cpu_model, "os_cpu_count": os.cpu_count(),
+               "affinity": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None,
+               "n1_latency_us": {"all_threads": lat_all, "one_thread": lat_one},
                "sample": f"oracle/smpl_ref.py fp32, 256-body calls (16 calls = the 4096-body workload), "
                          f"3 warm-up + {len(times)} timed calls (median), {sum(times):.1f} s of CPU work"}
 
@@ -513,7 +551,8 @@ def main():
         line = {
             "metric": "smpl_forward_bodies_per_sec", "value": value, "unit": "bodies/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": f"SMPL forward + 2D keypoint projection, batch {n} per GPU "

@@ -167,11 +167,17 @@ class SMPL(nn.Module):
         return h
 
     # -- the forward pass ------------------------------------------------------------------------
-    def forward(self, betas, pose, cam=None, *, flags=None):
+    def forward(self, betas, pose, cam=None, *, return_kp2d=None, flags=None):
         """betas[N,NB], pose[N,72] (axis-angle), cam[N,3]=(s,tx,ty) or None.
 
         Returns (vertices[N,V,3], joints[N,24,3]) and, when ``cam`` is given, kp2d[N,24,2].
+        ``return_kp2d`` (SURVEY.md §8b signature): None = follow ``cam``; True requires ``cam``;
+        False drops the projection even when ``cam`` is passed.
         """
+        if return_kp2d and cam is None:
+            raise ValueError("return_kp2d=True needs cam[N,3]")
+        if return_kp2d is False:
+            cam = None
         if not isinstance(betas, torch.Tensor) or betas.device.type != "cuda":
             raise RuntimeError("SMPL (B200) needs CUDA tensors; there is no CPU fallback")
         device = betas.device

@@ -222,6 +222,45 @@ def test_training_style_loss(dev, models):
     assert_grads((tb.grad, tp.grad, tc.grad), (rb.grad, rp.grad, rc.grad), "training loss")
 
 
+def test_train_step_is_cuda_graph_capturable(dev, models):
+    """forward + loss + backward captured once and replayed: no host sync, no allocation outside the
+    graph's pool, no stream-unsafe call anywhere in smplb200_forward / smplb200_backward."""
+    m = models["sparse"]
+    n = 16
+    layer = SMPL(m).to(dev)
+    b0, p0, c0 = synthetic.make_inputs(n, 31)
+    b1, p1, c1 = synthetic.make_inputs(n, 32)
+    sb, sp, sc = (torch.from_numpy(x).to(dev).requires_grad_() for x in (b0, p0, c0))
+
+    def step():
+        v, j, k = layer(sb, sp, sc)
+        (v.square().mean() + j.square().mean() + k.abs().mean()).backward()
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            sb.grad = sp.grad = sc.grad = None
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    sb.grad = sp.grad = sc.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    for arrs in ((b1, p1, c1), (b0, p0, c0)):
+        with torch.no_grad():
+            for t, a in zip((sb, sp, sc), arrs):
+                t.copy_(torch.from_numpy(a))
+        graph.replay()
+        torch.cuda.synchronize()
+        got = tuple(t.grad.clone() for t in (sb, sp, sc))
+        eb, ep, ec = (torch.from_numpy(a).to(dev).requires_grad_() for a in arrs)
+        v, j, k = layer(eb, ep, ec)
+        (v.square().mean() + j.square().mean() + k.abs().mean()).backward()
+        torch.cuda.synchronize()
+        assert all(torch.equal(g, e.grad) for g, e in zip(got, (eb, ep, ec)))
+
+
 def test_backward_errors_and_empty(dev, models):
     layer = SMPL(models["sparse"], precision="fp32").to(dev)
     h = layer.handle(dev)

@@ -275,6 +275,16 @@ def test_cuda_graph_replay_matches_eager(dev, models):
             assert torch.equal(v, ref[0]) and torch.equal(j, ref[1]) and torch.equal(k, ref[2])
 
 
+def test_return_kp2d_flag(dev, models):
+    layer = SMPL(models["sparse"]).to(dev)
+    b, p, c = to_dev(dev, *synthetic.make_inputs(3, 2))
+    with torch.no_grad():
+        assert len(layer(b, p, c)) == 3 and len(layer(b, p, c, return_kp2d=True)) == 3
+        assert len(layer(b, p, c, return_kp2d=False)) == 2 and len(layer(b, p)) == 2
+        with pytest.raises(ValueError):
+            layer(b, p, return_kp2d=True)
+
+
 def test_errors(dev, models):
     layer = SMPL(models["sparse"]).to(dev)
     b, p = torch.zeros(2, 10, device=dev), torch.zeros(2, 72, device=dev)
