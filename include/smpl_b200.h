@@ -176,7 +176,10 @@ int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, i
  * `forward_workspace` (optional, may be NULL): the workspace of the smplb200_forward call being
  * differentiated (same n and flags, untouched since) -- its A and vposed intermediates are then
  * reused instead of recomputed.  Ignored when the forward ran in chunks (SMPLB200_CHUNK).
- * Gradients are summed in a fixed order (no atomics): bitwise reproducible.                      */
+ * Gradients are summed in a fixed order (no atomics): bitwise reproducible.
+ * `g_vertices` is staged with 16-byte bulk copies: a body's [V,3] slab is read from the enclosing
+ * 16-byte granules, so up to 12 bytes on either side of it (inside the same allocation for any
+ * cudaMalloc / caching-allocator buffer, whose sizes are multiples of 256 bytes) are touched.      */
 size_t smplb200_backward_workspace_bytes(const SmplB200Model* model, int64_t n, uint32_t flags,
                                          int vertex_path);
 int smplb200_backward(const SmplB200Model* model, const float* betas, const float* pose,
