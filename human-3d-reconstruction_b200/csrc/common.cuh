@@ -41,6 +41,8 @@ struct DeviceModel {
   const float* dense_jreg;             // [VP, J] joint regressor rows (regressed-joint gradient)
   const uint32_t* bwd_basis_tf32_hi;   // [NC/32][8][224][4] K-major tiles of basis[k, col] (k_blend_bwd_tc)
   const uint32_t* bwd_basis_tf32_lo;   // same, low part of the 2-term tf32 split
+  const uint16_t* bwd_basis_bf16_hi;   // [NC/32][4][224][8] the same tiles in bf16 (hi | lo)
+  const uint16_t* bwd_basis_bf16_lo;
 };
 
 }  // namespace smplb200

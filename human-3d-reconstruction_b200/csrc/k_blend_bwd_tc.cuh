@@ -14,12 +14,13 @@
 //   * the accumulator D (224 fp32 columns) stays in TMEM for the CTA's whole column slice; the
 //     epilogue writes one [128, 224] partial per (slice, body block); kb2 adds the slices in order.
 //
-// Precision: 1xTF32 for SMPLB200_PREC_TF32 / _BF16, 3xTF32 (A_hi B_hi + A_lo B_hi + A_hi B_lo,
-// ~fp32 accuracy) for SMPLB200_PREC_BF16X3 / AUTO.
+// Precision: 1xTF32 for SMPLB200_PREC_TF32 / _BF16; split-bf16 (A_hi B_hi + A_lo B_hi + A_hi B_lo,
+// kind::f16, K = 16 per MMA: half the MMAs and half the basis bytes of 3xTF32, ~2^-16 relative) for
+// SMPLB200_PREC_BF16X3 / AUTO; 3xTF32 (~2^-21) for SMPLB200_PREC_FP32 at >= 256 bodies.
 //
-// Warp roles (320 threads): warp 0 = bulk-TMA producer of B, warp 1 = MMA issuer (warp-uniform,
-// one elected lane), warps 2..9 = two groups of four A-loader warps (TMEM lane quarter = warp % 4;
-// group g takes K-steps i = g mod 2, each thread keeps the NEXT K-step's line in flight while it
+// Warp roles (448 threads): warp 0 = bulk-TMA producer of B, warp 1 = MMA issuer (warp-uniform,
+// one elected lane), warps 2..13 = three groups of four A-loader warps (TMEM lane quarter = warp % 4;
+// group g takes K-steps i = g mod 3, each thread keeps the NEXT K-step's line in flight while it
 // converts the current one); warps 2..5 then run the epilogue.
 #pragma once
 #include "common.cuh"
@@ -28,32 +29,41 @@
 
 namespace smplb200 {
 
-constexpr int kBwdTcThreads = 320;
+constexpr int kBwdTcGroups = 3;              // loader groups (4 warps each)
+constexpr int kBwdTcThreads = (2 + 4 * kBwdTcGroups) * 32;   // 448
 constexpr int kBwdTcBodies = 128;
 constexpr int kBwdTcStepCols = 32;          // planar columns per K-step (4 MMAs of K = 8)
 constexpr uint32_t kBwdTcTile = 8u * kCoefK * 16u;   // one basis K-step tile: 28,672 B
 
-template <bool X3>
+enum : int { kBwdTf32 = 0, kBwdTf32x3 = 1, kBwdBf16x3 = 2 };
+
+template <int MODE>
 struct BlendBwdTcCfg {
-  static constexpr uint32_t kBStage = kBwdTcTile * (X3 ? 2u : 1u);
-  static constexpr int kStagesB = X3 ? 3 : 6;
-  static constexpr int kAStageCols = X3 ? 64 : 32;      // hi (| lo) tf32 columns per K-step
-  static constexpr int kStagesA = X3 ? 4 : 8;
+  static constexpr bool kBf16 = MODE == kBwdBf16x3;
+  static constexpr bool kSplit = MODE != kBwdTf32;                  // hi + lo parts of both operands
+  // one part of one K-step of B: tf32 [8 chunks][224][4] = 28,672 B, bf16 [4 chunks][224][8] = 14,336 B
+  static constexpr uint32_t kBPart = kBf16 ? kBwdTcTile / 2 : kBwdTcTile;
+  static constexpr uint32_t kBStage = kBPart * (kSplit ? 2u : 1u);
+  static constexpr int kStagesB = MODE == kBwdTf32x3 ? 3 : 6;
+  static constexpr int kAPartCols = kBf16 ? 16 : 32;                 // TMEM columns of one part of a K-step
+  static constexpr int kAStageCols = kAPartCols * (kSplit ? 2 : 1);
+  static constexpr int kStagesA = MODE == kBwdTf32x3 ? 4 : 8;
+  static constexpr int kMmaPerPart = kBf16 ? 2 : 4;                  // K = 16 bf16 / 8 tf32 per MMA, 32 columns
   static constexpr int kACol0 = kCoefK;                  // A stages follow the 224 accumulator columns
   static constexpr uint32_t kBarOffset = kStagesB * kBStage;
   static constexpr uint32_t kSmemBytes = kBarOffset + 512;
   static constexpr uint32_t kLbo = kCoefK * 16, kSbo = 128;
-  static constexpr uint32_t kIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kCoefK);
+  static constexpr uint32_t kIdesc = ptx::make_idesc(kBf16 ? ptx::kFmtBF16 : ptx::kFmtTF32, 128, kCoefK);
   static_assert(kACol0 + kStagesA * kAStageCols <= 512, "TMEM budget");
-  static_assert(kStagesA % 2 == 0, "a stage is always filled by the same loader group");
 };
 
-template <bool X3>
+template <int MODE>
 __global__ void __launch_bounds__(kBwdTcThreads, 1)
 k_blend_bwd_tc(const uint8_t* __restrict__ bimg_hi, const uint8_t* __restrict__ bimg_lo,
                const float* __restrict__ g_vposed, long long n, int NC, int slices,
                float* __restrict__ part /* [slices][n][224] */) {
-  using C = BlendBwdTcCfg<X3>;
+  using C = BlendBwdTcCfg<MODE>;
+  constexpr bool X3 = C::kSplit;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kBarOffset);
@@ -91,9 +101,9 @@ k_blend_bwd_tc(const uint8_t* __restrict__ bimg_hi, const uint8_t* __restrict__ 
         ptx::mbar_wait(b_empty + s, ((i / C::kStagesB) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(b_full + s, C::kBStage);
         uint8_t* dst = sB + (size_t)s * C::kBStage;
-        const size_t src = (size_t)(ks0 + i) * kBwdTcTile;
-        ptx::bulk_g2s(dst, bimg_hi + src, kBwdTcTile, b_full + s);
-        if (X3) ptx::bulk_g2s(dst + kBwdTcTile, bimg_lo + src, kBwdTcTile, b_full + s);
+        const size_t src = (size_t)(ks0 + i) * C::kBPart;
+        ptx::bulk_g2s(dst, bimg_hi + src, C::kBPart, b_full + s);
+        if (X3) ptx::bulk_g2s(dst + C::kBPart, bimg_lo + src, C::kBPart, b_full + s);
       }
     }
   } else if (warp == 1) {
@@ -109,12 +119,14 @@ k_blend_bwd_tc(const uint8_t* __restrict__ bimg_hi, const uint8_t* __restrict__ 
         constexpr int kGroups = X3 ? 3 : 1;          // (A_hi,B_hi) [, (A_lo,B_hi), (A_hi,B_lo)]
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
-          const uint32_t ap = a_addr + (g == 1 ? 32 : 0);
-          const uint32_t bp = b_addr + (g == 2 ? kBwdTcTile : 0);
+          const uint32_t ap = a_addr + (g == 1 ? C::kAPartCols : 0);
+          const uint32_t bp = b_addr + (g == 2 ? C::kBPart : 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
+          for (int kk = 0; kk < C::kMmaPerPart; ++kk) {
             const uint64_t bd = ptx::make_smem_desc(bp + kk * 2 * C::kLbo, C::kLbo, C::kSbo);
-            ptx::mma_tf32_ts(tmem_base, ap + kk * 8, bd, C::kIdesc, (uint32_t)((i | g | kk) != 0));
+            const uint32_t acc = (uint32_t)((i | g | kk) != 0);
+            if (C::kBf16) ptx::mma_bf16_ts(tmem_base, ap + kk * 8, bd, C::kIdesc, acc);
+            else ptx::mma_tf32_ts(tmem_base, ap + kk * 8, bd, C::kIdesc, acc);
           }
         }
         ptx::tc_commit(b_empty + sb);
@@ -138,27 +150,46 @@ k_blend_bwd_tc(const uint8_t* __restrict__ bimg_hi, const uint8_t* __restrict__ 
         dst[v] = valid ? __ldg(src + (size_t)i * 8 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     if (grp < nks) load(cur, grp);
-    for (int i = grp; i < nks; i += 2) {
-      if (i + 2 < nks) load(nxt, i + 2);
+    for (int i = grp; i < nks; i += kBwdTcGroups) {
+      if (i + kBwdTcGroups < nks) load(nxt, i + kBwdTcGroups);
       const int sa = i % C::kStagesA;
       ptx::mbar_wait(a_empty + sa, ((i / C::kStagesA) & 1) ^ 1);
       ptx::tc_fence_after();
       const uint32_t acol = tmem_base + lane_addr + C::kACol0 + sa * C::kAStageCols;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      if (C::kBf16) {
+        // 32 columns -> 16 words of packed bf16 pairs per part (element 2w in the low half)
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const float4 x = cur[4 * h + v];
+        for (int v = 0; v < 8; ++v) {
+          const float4 x = cur[v];
           const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[4 * v + e] = f32_to_tf32_rn(xs[e]);
-            if (X3) lo[4 * v + e] = f32_to_tf32_rn(xs[e] - __uint_as_float(hi[4 * v + e]));
+          for (int e = 0; e < 2; ++e) {
+            const uint16_t h0 = f32_to_bf16_rn(xs[2 * e]), h1 = f32_to_bf16_rn(xs[2 * e + 1]);
+            hi[2 * v + e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            lo[2 * v + e] = (uint32_t)f32_to_bf16_rn(xs[2 * e] - bf16_to_f32(h0)) |
+                            ((uint32_t)f32_to_bf16_rn(xs[2 * e + 1] - bf16_to_f32(h1)) << 16);
           }
         }
-        ptx::tmem_st16(acol + 16 * h, hi);
-        if (X3) ptx::tmem_st16(acol + 32 + 16 * h, lo);
+        ptx::tmem_st16(acol, hi);
+        ptx::tmem_st16(acol + 16, lo);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 x = cur[4 * h + v];
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[4 * v + e] = f32_to_tf32_rn(xs[e]);
+              if (X3) lo[4 * v + e] = f32_to_tf32_rn(xs[e] - __uint_as_float(hi[4 * v + e]));
+            }
+          }
+          ptx::tmem_st16(acol + 16 * h, hi);
+          if (X3) ptx::tmem_st16(acol + 32 + 16 * h, lo);
+        }
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -192,22 +223,26 @@ k_blend_bwd_tc(const uint8_t* __restrict__ bimg_hi, const uint8_t* __restrict__ 
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-template <bool X3>
+template <int MODE>
 inline cudaError_t blend_bwd_tc_set_smem() {
-  return cudaFuncSetAttribute(k_blend_bwd_tc<X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)BlendBwdTcCfg<X3>::kSmemBytes);
+  return cudaFuncSetAttribute(k_blend_bwd_tc<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)BlendBwdTcCfg<MODE>::kSmemBytes);
 }
 
-inline cudaError_t launch_blend_bwd_tc(const DeviceModel& m, bool x3, const float* g_vposed, long long n,
+inline cudaError_t launch_blend_bwd_tc(const DeviceModel& m, int mode, const float* g_vposed, long long n,
                                        int slices, float* part, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   dim3 grid((unsigned)slices, (unsigned)((n + kBwdTcBodies - 1) / kBwdTcBodies));
   const uint8_t* hi = reinterpret_cast<const uint8_t*>(m.bwd_basis_tf32_hi);
   const uint8_t* lo = reinterpret_cast<const uint8_t*>(m.bwd_basis_tf32_lo);
-  if (x3)
-    k_blend_bwd_tc<true><<<grid, kBwdTcThreads, BlendBwdTcCfg<true>::kSmemBytes, s>>>(hi, lo, g_vposed, n, m.NC, slices, part);
+  const uint8_t* bhi = reinterpret_cast<const uint8_t*>(m.bwd_basis_bf16_hi);
+  const uint8_t* blo = reinterpret_cast<const uint8_t*>(m.bwd_basis_bf16_lo);
+  if (mode == kBwdBf16x3)
+    k_blend_bwd_tc<kBwdBf16x3><<<grid, kBwdTcThreads, BlendBwdTcCfg<kBwdBf16x3>::kSmemBytes, s>>>(bhi, blo, g_vposed, n, m.NC, slices, part);
+  else if (mode == kBwdTf32x3)
+    k_blend_bwd_tc<kBwdTf32x3><<<grid, kBwdTcThreads, BlendBwdTcCfg<kBwdTf32x3>::kSmemBytes, s>>>(hi, lo, g_vposed, n, m.NC, slices, part);
   else
-    k_blend_bwd_tc<false><<<grid, kBwdTcThreads, BlendBwdTcCfg<false>::kSmemBytes, s>>>(hi, lo, g_vposed, n, m.NC, slices, part);
+    k_blend_bwd_tc<kBwdTf32><<<grid, kBwdTcThreads, BlendBwdTcCfg<kBwdTf32>::kSmemBytes, s>>>(hi, lo, g_vposed, n, m.NC, slices, part);
   return cudaGetLastError();
 }
 

@@ -230,8 +230,9 @@ cudaError_t configure_tc_kernels() {
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
   if ((e = blend_tc2_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
-  if ((e = blend_bwd_tc_set_smem<false>()) != cudaSuccess) return e;
-  if ((e = blend_bwd_tc_set_smem<true>()) != cudaSuccess) return e;
+  if ((e = blend_bwd_tc_set_smem<kBwdTf32>()) != cudaSuccess) return e;
+  if ((e = blend_bwd_tc_set_smem<kBwdTf32x3>()) != cudaSuccess) return e;
+  if ((e = blend_bwd_tc_set_smem<kBwdBf16x3>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_blend_bwd_fma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kBbSmemBytes)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_lbs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -413,6 +414,17 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     // basis[k, col] as the B operand of the tensor-core blendshape backward: per K-step of 32
     // planar columns one tile [8 chunks][224 rows k][4 cols], tf32 hi | lo (rows >= NB+207 are 0)
     std::vector<uint32_t> gbh((size_t)NC * kCoefK, 0), gbl((size_t)NC * kCoefK, 0);
+    std::vector<uint16_t> gbbh((size_t)NC * kCoefK, 0), gbbl((size_t)NC * kCoefK, 0);   // bf16: [ks][4][224][8]
+    for (int ks = 0; ks < NC / 32; ++ks)
+      for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < NB + kP; ++r)
+          for (int e = 0; e < 8; ++e) {
+            const float x = basis[(size_t)r * NC + ks * 32 + c * 8 + e];
+            const uint16_t hi = host_bf16(x);
+            const size_t idx = (((size_t)ks * 4 + c) * kCoefK + r) * 8 + e;
+            gbbh[idx] = hi;
+            gbbl[idx] = host_bf16(x - host_bf16_to_f32(hi));
+          }
     for (int ks = 0; ks < NC / 32; ++ks)
       for (int c = 0; c < 8; ++c)
         for (int r = 0; r < NB + kP; ++r)
@@ -487,6 +499,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     const size_t o_djr = bb.add(dense_jreg.data(), dense_jreg.size() * 4);
     const size_t o_gbh = bb.add(gbh.data(), gbh.size() * 4);
     const size_t o_gbl = bb.add(gbl.data(), gbl.size() * 4);
+    const size_t o_gbbh = bb.add(gbbh.data(), gbbh.size() * 2);
+    const size_t o_gbbl = bb.add(gbbl.data(), gbbl.size() * 2);
 
     DeviceGuard guard(desc->device);
     if (guard.err != cudaSuccess) { delete m; return cuda_fail(guard.err); }
@@ -540,6 +554,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     d.dense_jreg = reinterpret_cast<const float*>(base + o_djr);
     d.bwd_basis_tf32_hi = reinterpret_cast<const uint32_t*>(base + o_gbh);
     d.bwd_basis_tf32_lo = reinterpret_cast<const uint32_t*>(base + o_gbl);
+    d.bwd_basis_bf16_hi = reinterpret_cast<const uint16_t*>(base + o_gbbh);
+    d.bwd_basis_bf16_lo = reinterpret_cast<const uint16_t*>(base + o_gbbl);
     *out_model = m;
     return SMPLB200_OK;
   } catch (const std::bad_alloc&) {
@@ -761,10 +777,17 @@ struct BwdWorkspace {
   size_t total = 0;
 };
 
-// kb1 runs on tcgen05 unless the caller pinned the fp32 FMA path explicitly; under AUTO the
-// operands are split 3xTF32 (fp32-class accuracy) at every batch size.
-inline bool bwd_blend_tc(uint32_t flags) { return (flags & SMPLB200_PREC_MASK) != SMPLB200_PREC_FP32; }
-inline bool bwd_blend_x3(const Plan& p) { return p.prec == SMPLB200_PREC_FP32 || p.prec == SMPLB200_PREC_BF16X3; }
+// kb1 runs on tcgen05 except for an explicit SMPLB200_PREC_FP32 below the tensor-core batch size
+// (CUDA-core FMA kernel).  Operands: split bf16 under AUTO / BF16X3, 3xTF32 for explicit FP32 at
+// large batches, plain TF32 for the reduced-precision modes.
+inline bool bwd_blend_tc(uint32_t flags, long long n) {
+  return (flags & SMPLB200_PREC_MASK) != SMPLB200_PREC_FP32 || n >= SMPLB200_TC_MIN_BATCH;
+}
+inline int bwd_blend_mode(uint32_t flags, const Plan& p) {
+  if ((flags & SMPLB200_PREC_MASK) == SMPLB200_PREC_FP32) return kBwdTf32x3;
+  if (p.prec == SMPLB200_PREC_FP32 || p.prec == SMPLB200_PREC_BF16X3) return kBwdBf16x3;   // AUTO, BF16X3
+  return kBwdTf32;
+}
 
 BwdWorkspace carve_bwd(const SmplB200Model* m, long long n, const Plan& p, bool vertex_path, bool tc) {
   BwdWorkspace w;
@@ -794,7 +817,7 @@ size_t smplb200_backward_workspace_bytes(const SmplB200Model* model, int64_t n, 
                                          int vertex_path) {
   Plan p;
   if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
-  return carve_bwd(model, n, p, vertex_path != 0, bwd_blend_tc(flags)).total;
+  return carve_bwd(model, n, p, vertex_path != 0, bwd_blend_tc(flags, n)).total;
 }
 
 int smplb200_backward_launch_count(const SmplB200Model* model, int64_t n, uint32_t flags, int vertex_path,
@@ -819,7 +842,7 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
   if (!resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
   if (p.regressed && g_kp2d && !joints_fwd) return SMPLB200_ERR_INVALID_ARG;
   const bool vertex_path = g_vertices != nullptr || (p.regressed && (g_joints || g_kp2d));
-  const bool tc = bwd_blend_tc(flags);
+  const bool tc = bwd_blend_tc(flags, n);
   const BwdWorkspace w = carve_bwd(model, n, p, vertex_path, tc);
   if (vertex_path &&
       (!workspace || workspace_bytes < w.total || (reinterpret_cast<uintptr_t>(workspace) & 255u)))
@@ -885,7 +908,7 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
       k_blend_bwd_fma<<<g1, kBbThreads, kBbSmemBytes, s>>>(model->d, g_vposed, n, w.slices, part);
       CU_TRY(cudaGetLastError());
     } else {   // tcgen05: 3xTF32 for the fp32-class modes, 1xTF32 for the reduced-precision ones
-      CU_TRY(launch_blend_bwd_tc(model->d, bwd_blend_x3(p), g_vposed, n, w.slices, part, s));
+      CU_TRY(launch_blend_bwd_tc(model->d, bwd_blend_mode(flags, p), g_vposed, n, w.slices, part, s));
     }
     cb.g_A = g_A;
     cb.g_coef_part = part;

@@ -137,6 +137,18 @@ def test_backward_tensor_core_blendshape_gradient(dev, models, precision, rtol, 
         assert err <= rtol * scale + GRAD_ATOL, f"{precision} n={n}: {name} err {err:.3e} scale {scale:.3e}"
 
 
+def test_backward_explicit_fp32_large_batch_uses_3xtf32(dev):
+    """precision='fp32' at >= 256 bodies: FMA recompute, 3xTF32 tcgen05 blendshape gradient."""
+    m = synthetic.make_model(9, num_verts=1200)
+    n = 260
+    b, p, c = synthetic.make_inputs(n, 33)
+    ups = upstream(n, 1200, 18)
+    layer = SMPL(m, precision="fp32").to(dev)
+    got = gpu_grads(layer, dev, b, p, c, ups)
+    ref = oracle_grads(m, b, p, c, ups)
+    assert_grads(got, ref, "fp32 n=260")
+
+
 def test_backward_large_batch_default_path(dev):
     """n = 520 under AUTO: tcgen05 recompute and tcgen05 blendshape backward, 4 persistent bodies per CTA."""
     m = synthetic.make_model(8, num_verts=1500)
