@@ -133,7 +133,7 @@ bool resolve_plan(const SmplB200Model* m, long long n, uint32_t flags, Plan* p) 
     prec = n >= SMPLB200_TC_MIN_BATCH ? SMPLB200_PREC_BF16X3 : SMPLB200_PREC_FP32;
   uint32_t lbs = flags & SMPLB200_LBS_MASK;
   if (lbs == SMPLB200_LBS_AUTO)
-    lbs = n >= SMPLB200_TC_MIN_BATCH ? SMPLB200_LBS_TC : SMPLB200_LBS_FMA;
+    lbs = n >= SMPLB200_TC_LBS_MIN_BATCH ? SMPLB200_LBS_TC : SMPLB200_LBS_FMA;
   if (lbs == SMPLB200_LBS_FMA && m->d.max_nnz > 4) lbs = SMPLB200_LBS_DENSE;
   if (flags & ~(SMPLB200_PREC_MASK | SMPLB200_JOINTS_REGRESSED | SMPLB200_ROTATE_BASE |
                 SMPLB200_LBS_MASK))
@@ -780,8 +780,9 @@ struct BwdWorkspace {
 // kb1 runs on tcgen05 except for an explicit SMPLB200_PREC_FP32 below the tensor-core batch size
 // (CUDA-core FMA kernel).  Operands: split bf16 under AUTO / BF16X3, 3xTF32 for explicit FP32 at
 // large batches, plain TF32 for the reduced-precision modes.
+constexpr long long kBwdFp32TcMinBatch = 256;   // explicit FP32: CUDA-core FMA kernel below, 3xTF32 from here
 inline bool bwd_blend_tc(uint32_t flags, long long n) {
-  return (flags & SMPLB200_PREC_MASK) != SMPLB200_PREC_FP32 || n >= SMPLB200_TC_MIN_BATCH;
+  return (flags & SMPLB200_PREC_MASK) != SMPLB200_PREC_FP32 || n >= kBwdFp32TcMinBatch;
 }
 inline int bwd_blend_mode(uint32_t flags, const Plan& p) {
   if ((flags & SMPLB200_PREC_MASK) == SMPLB200_PREC_FP32) return kBwdTf32x3;

@@ -49,7 +49,7 @@ enum {
 
 /* ---- forward flags --------------------------------------------------------------------- */
 /* blendshape operand precision (accumulate and output are always fp32)                      */
-#define SMPLB200_PREC_AUTO   0u  /* FP32 FMA below SMPLB200_TC_MIN_BATCH bodies, BF16X3 above */
+#define SMPLB200_PREC_AUTO   0u  /* fastest path within 1e-5 m: FP32 FMA below SMPLB200_TC_MIN_BATCH bodies, BF16X3 from there */
 #define SMPLB200_PREC_FP32   1u  /* vectorised FMA kernel, k-ascending single accumulator     */
 #define SMPLB200_PREC_BF16   2u  /* tcgen05 kind::f16, bf16 operands                          */
 #define SMPLB200_PREC_TF32   3u  /* tcgen05 kind::tf32                                        */
@@ -61,13 +61,16 @@ enum {
 /* HMR's root pre-rotation by diag(1,-1,-1); default off                      */
 #define SMPLB200_ROTATE_BASE      (1u << 4)
 /* skinning path                                                                              */
-#define SMPLB200_LBS_AUTO   0u          /* tcgen05 blend at large N, FMA below               */
+#define SMPLB200_LBS_AUTO   0u          /* tcgen05 blend from SMPLB200_TC_LBS_MIN_BATCH bodies, FMA below */
 #define SMPLB200_LBS_FMA    (1u << 5)   /* CUDA-core kernel (ELL-sparse weights if <=4 nnz)  */
 #define SMPLB200_LBS_TC     (2u << 5)   /* 3xTF32 tcgen05 blend of the 24 joint transforms   */
 #define SMPLB200_LBS_DENSE  (3u << 5)   /* CUDA-core kernel, all 24 weights (debug/fallback) */
 #define SMPLB200_LBS_MASK   (3u << 5)
 
-#define SMPLB200_TC_MIN_BATCH 256
+/* Measured crossovers on B200 (profiles/r01_latency_crossover.txt, CUDA-graph replay): the tcgen05
+ * blendshape kernel beats the FMA one from 32 bodies, the tcgen05 skinning blend from 384.        */
+#define SMPLB200_TC_MIN_BATCH 32
+#define SMPLB200_TC_LBS_MIN_BATCH 384
 
 /* ---- model ----------------------------------------------------------------------------- */
 typedef struct SmplB200Model SmplB200Model;
