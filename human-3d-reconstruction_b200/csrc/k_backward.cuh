@@ -50,10 +50,11 @@ template <bool STAGED>
 __global__ void __launch_bounds__(kLbsBwdThreads, 1)
 k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
   extern __shared__ __align__(128) float smem_bw[];
-  // The body's 24 transforms, one float4 per (joint, row), replicated 8x: lane l reads replica
-  // l % 8, which lives in bank quad l % 8 whatever the joint, so the per-vertex gather of A by
-  // joint index is bank-conflict free (unreplicated it cost ~10 wavefronts per LDS.128, round-1 ncu).
-  __shared__ float4 s_A8[kJ * 3 * 8];
+  // The body's 24 transforms stored TRANSPOSED, [entry e][joint j]: the lanes of a warp gather by
+  // their own joint index, and with j fastest distinct joints are distinct banks and equal joints
+  // broadcast, so the 9 LDS.32 per slot are conflict free (row-major [j][12] read with LDS.128 cost
+  // ~10 wavefronts per load for random joints, round-1 ncu).
+  __shared__ float s_At[12 * kJ];
   __shared__ float s_gj[kJ * 3];
   __shared__ __align__(8) uint64_t s_bar;
   float* s_vp = smem_bw;                 // [3][VP]
@@ -82,8 +83,10 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
       ptx::bulk_g2s_split(s_vp, vp, vp_bytes, &s_bar);
       if (gv) ptx::bulk_g2s_split(s_gbuf, reinterpret_cast<const uint8_t*>(gv) - shift, g_bytes, &s_bar);
     }
-    if (tid < kJ * 3 * 8)
-      s_A8[tid] = __ldg(reinterpret_cast<const float4*>(a.A + (size_t)b * (kJ * 12)) + (tid >> 3));
+    if (tid < kJ * 12) {
+      const int j = tid / 12, e = tid - 12 * j;
+      s_At[e * kJ + j] = __ldg(a.A + (size_t)b * (kJ * 12) + tid);
+    }
     if (tid >= 640 && tid < 640 + kJ * 3) {
       // effective joint gradient that flows into the VERTICES (regressed joints only):
       // g_joints + s * g_kp2d on x,y
@@ -154,28 +157,22 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
           const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
-            const float4* Aj = s_A8 + ((((jj >> (8 * s)) & 0xffu) * 3) << 3) + (lane & 7);
+            const float* Aj = s_At + ((jj >> (8 * s)) & 0xffu);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const float4 row = Aj[r << 3];
-              T[3 * r] = fmaf(ws[s], row.x, T[3 * r]);
-              T[3 * r + 1] = fmaf(ws[s], row.y, T[3 * r + 1]);
-              T[3 * r + 2] = fmaf(ws[s], row.z, T[3 * r + 2]);
-            }
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) T[3 * r + c] = fmaf(ws[s], Aj[(4 * r + c) * kJ], T[3 * r + c]);
           }
         } else {
           const float* wr = m.dense_w + (size_t)v * kJ;
           for (int j = 0; j < kJ; ++j) {
             const float w = __ldg(wr + j);
             if (w == 0.f) continue;
-            const float4* Aj = s_A8 + ((j * 3) << 3) + (lane & 7);
+            const float* Aj = s_At + j;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-              const float4 row = Aj[r << 3];
-              T[3 * r] = fmaf(w, row.x, T[3 * r]);
-              T[3 * r + 1] = fmaf(w, row.y, T[3 * r + 1]);
-              T[3 * r + 2] = fmaf(w, row.z, T[3 * r + 2]);
-            }
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) T[3 * r + c] = fmaf(w, Aj[(4 * r + c) * kJ], T[3 * r + c]);
           }
         }
         o0 = fmaf(T[6], g[2], fmaf(T[3], g[1], T[0] * g[0]));

@@ -5,7 +5,10 @@
 // The per-vertex weights stay in registers for the whole CTA lifetime (ELL: <=4 (joint, weight)
 // pairs when the model is SMPL-sparse -- skipped terms are exact zeros; or all
 // 24 for arbitrary models).  Each body's 24 joint transforms (1152 B) are staged in shared
-// memory by coalesced float4 reads; vposed is planar so the three coordinate loads are fully
+// memory.  For the ELL path they are stored TRANSPOSED, [entry e][joint j]: the lanes of a warp
+// gather by their own joint index, and with j as the fastest index distinct joints are distinct
+// banks and equal joints broadcast -- 12 conflict-free LDS.32 per slot.  (Row-major [j][12] read
+// with LDS.128 cost ~10 wavefronts per load for random joints: 120 vs 48 per warp and body.) vposed is planar so the three coordinate loads are fully
 // coalesced; the xyz-interleaved output goes through a per-warp shared-memory transpose so each
 // warp emits three fully coalesced 128-byte stores covering 384 contiguous bytes (a body row is
 // only 8-byte aligned, 6890*3*4 = 82,680 B, so 16-byte vectors or TMA stores do not apply).
@@ -26,7 +29,7 @@ k_lbs_fma(DeviceModel m, const float* __restrict__ vposed, const float* __restri
           long long n, int bodies_per_cta, float* __restrict__ verts,
           const float* __restrict__ joints_in, const float* __restrict__ cam,
           float* __restrict__ kp2d) {
-  __shared__ __align__(16) float s_A[kLbsStage][kJ * 12];
+  __shared__ __align__(16) float s_A[kLbsStage][kJ * 12];   // DENSE: [j][12]; ELL: [e][24] (transposed)
   __shared__ __align__(16) float s_out[kLbsThreads / 32][96];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int v = blockIdx.x * kVertTile + tid;
@@ -50,10 +53,16 @@ k_lbs_fma(DeviceModel m, const float* __restrict__ vposed, const float* __restri
   for (long long bs = b_begin; bs < b_end; bs += kLbsStage) {
     const int nb = (int)min((long long)kLbsStage, b_end - bs);
     __syncthreads();
-    {
+    if (DENSE) {
       const float4* src = reinterpret_cast<const float4*>(A + bs * (kJ * 12));
       float4* dst = reinterpret_cast<float4*>(&s_A[0][0]);
       for (int i = tid; i < nb * (kJ * 3); i += kLbsThreads) dst[i] = __ldg(src + i);
+    } else {
+      const float* src = A + bs * (kJ * 12);
+      for (int i = tid; i < nb * (kJ * 12); i += kLbsThreads) {
+        const int bi = i / (kJ * 12), r = i - bi * (kJ * 12), j = r / 12, e = r - 12 * j;
+        s_A[bi][e * kJ + j] = __ldg(src + i);
+      }
     }
     __syncthreads();
     for (int bi = 0; bi < nb; ++bi) {
@@ -78,15 +87,9 @@ k_lbs_fma(DeviceModel m, const float* __restrict__ vposed, const float* __restri
       } else {
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          const int j = (jj >> (8 * s)) & 0xff;
-          const float4* a = reinterpret_cast<const float4*>(&s_A[bi][j * 12]);
-          const float4 r0 = a[0], r1 = a[1], r2 = a[2];
-          T[0] = fmaf(w[s], r0.x, T[0]); T[1] = fmaf(w[s], r0.y, T[1]);
-          T[2] = fmaf(w[s], r0.z, T[2]); T[3] = fmaf(w[s], r0.w, T[3]);
-          T[4] = fmaf(w[s], r1.x, T[4]); T[5] = fmaf(w[s], r1.y, T[5]);
-          T[6] = fmaf(w[s], r1.z, T[6]); T[7] = fmaf(w[s], r1.w, T[7]);
-          T[8] = fmaf(w[s], r2.x, T[8]); T[9] = fmaf(w[s], r2.y, T[9]);
-          T[10] = fmaf(w[s], r2.z, T[10]); T[11] = fmaf(w[s], r2.w, T[11]);
+          const float* a = &s_A[bi][(jj >> (8 * s)) & 0xff];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) T[e] = fmaf(w[s], a[e * kJ], T[e]);
         }
       }
       const float ox = fmaf(T[2], z, fmaf(T[1], y, fmaf(T[0], x, T[3])));
