@@ -316,6 +316,32 @@ def test_data_parallel_wrapper(dev, models):
     assert all(torch.equal(x, y) for x, y in zip(out, ref))
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two visible GPUs")
+def test_data_parallel_two_devices_forward_and_backward(models):
+    """nn.DataParallel across two GPUs, the way the reference trainer wraps its model
+    (trainer.py:176): per-device handles created from replica threads, scatter/gather autograd around
+    the layer's own autograd node.  Pinned FMA paths => bitwise equal to the single-device result."""
+    d0 = torch.device("cuda:0")
+    layer = SMPL(models["sparse"], precision="fp32", lbs="fma").to(d0)
+    dp = torch.nn.DataParallel(layer, device_ids=[0, 1])
+    n = 40
+    betas, pose, cam = synthetic.make_inputs(n, 43)
+    g = torch.Generator().manual_seed(7)
+    uv, uj, uk = torch.randn(n, 6890, 3, generator=g), torch.randn(n, 24, 3, generator=g), torch.randn(n, 24, 2, generator=g)
+
+    def run(module):
+        args = [torch.from_numpy(x).to(d0).requires_grad_() for x in (betas, pose, cam)]
+        v, j, k = module(*args)
+        ((v * uv.to(d0)).sum() + (j * uj.to(d0)).sum() + (k * uk.to(d0)).sum()).backward()
+        torch.cuda.synchronize()
+        return (v.detach(), j.detach(), k.detach()) + tuple(a.grad for a in args)
+
+    got, ref = run(dp), run(layer)
+    assert set(layer._handles) == {0, 1}, "one packed model handle per device"
+    for name, a, b in zip(("verts", "joints", "kp2d", "g_betas", "g_pose", "g_cam"), got, ref):
+        assert torch.equal(a, b), name
+
+
 # ------------------------------------------------------------------------------------------------
 # BASELINE.json full size (N = 4096): oracle parity (chunked) + size-independent properties
 # ------------------------------------------------------------------------------------------------
