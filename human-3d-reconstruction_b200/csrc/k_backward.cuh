@@ -3,12 +3,14 @@
 // so the layer can sit inside the reference trainer's loss (reference src/lib/trains/trainer.py:31-37
 // computes loss = model_with_loss(batch) and calls loss.backward() at :102-104).
 //
-// Reverse of the forward kernels, intermediates recomputed instead of saved (k2 + k1 run again; the
-// 83 KB/body vposed scratch is cheaper to rebuild than to keep alive across the network's backward):
+// Reverse of the forward kernels.  A and vposed are either recomputed (k2 + k1 run again) or, when the
+// caller kept the forward's workspace, read from it:
 //
 //   kb3  k_lbs_bwd        skinning:      g_vposed = T_R^T g_v         (thread per vertex)
 //                                        g_A[j]   = sum_v w_vj g_v (x) [vposed_v, 1]   (warp per joint)
-//   kb1  k_blend_bwd_fma  blendshapes:   g_coef   = g_vposed . basis^T   (split over column slices)
+//   kb1  blendshapes:     g_coef = g_vposed . basis^T, split over column slices:
+//        k_blend_bwd_tc   (k_blend_bwd_tc.cuh) tcgen05, the default;
+//        k_blend_bwd_fma  (here) CUDA cores, only for an explicit precision='fp32' below 256 bodies
 //   kb2  k_chain_bwd      chain + regressor + Rodrigues + projection, one warp per body
 //
 // The derivation is stated step by step in float64 numpy in oracle/smpl_backward_np.py and pinned
@@ -23,9 +25,10 @@ namespace smplb200 {
 
 // ---------------------------------------------------------------------------------------------
 // kb3: skinning backward, one CTA per body (persistent over bodies).
-//   STAGED: the body's upstream gradient g_v [V,3] and its vposed planes [3,VP] are staged once in
-//   shared memory (166 KB at V = 6890); phase 1 (thread = vertex) and phase 2 (warp = joint, lanes
-//   over that joint's skinned vertices) both read them from there, so HBM sees each once.
+//   STAGED: one thread bulk-TMA-stages the body's upstream gradient g_v [V,3] and its vposed planes
+//   [3,VP] into shared memory (166 KB at V = 6890).  Phase 1 (thread = vertex) runs while the copies
+//   land (it reads g_v from global, coalesced); phase 2 (warp = joint, lanes over that joint's
+//   skinned vertices) gathers from the staged copy.  Unstaged variant for meshes that do not fit.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLbsBwdThreads = 768;   // 24 warps: in phase 2 warp j owns joint j
 
