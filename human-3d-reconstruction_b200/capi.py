@@ -156,6 +156,7 @@ class ModelHandle:
         out = C.c_void_p()
         check(lib().smplb200_model_create(C.byref(desc), C.byref(out)), "smplb200_model_create")
         self.ptr = out
+        self._sizes = {}
         self.device = int(device)
         self.num_verts, self.num_joints, self.num_betas = V, J, NB
         self.padded_verts = int(lib().smplb200_padded_verts(out))
@@ -174,7 +175,19 @@ class ModelHandle:
             pass
 
     def workspace_bytes(self, n: int, flags: int) -> int:
-        return int(lib().smplb200_workspace_bytes(self.ptr, int(n), int(flags)))
+        key = (n, flags)
+        v = self._sizes.get(key)
+        if v is None:      # pure function of (n, flags): cached, the hot path makes no ctypes call for it
+            v = self._sizes[key] = int(lib().smplb200_workspace_bytes(self.ptr, int(n), int(flags)))
+        return v
+
+    def backward_workspace_bytes(self, n: int, flags: int, vertex_path: bool) -> int:
+        key = (n, flags, bool(vertex_path))
+        v = self._sizes.get(key)
+        if v is None:
+            v = self._sizes[key] = int(lib().smplb200_backward_workspace_bytes(
+                self.ptr, int(n), int(flags), int(bool(vertex_path))))
+        return v
 
     def host_staging_bytes(self, n: int, flags: int) -> int:
         return int(lib().smplb200_host_staging_bytes(self.ptr, int(n), int(flags)))

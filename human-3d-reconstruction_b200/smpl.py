@@ -81,22 +81,23 @@ class _SMPLFunction(torch.autograd.Function):
         g_verts, g_joints, g_kp2d = prep(g_verts), prep(g_joints), prep(g_kp2d)
         regressed = bool(flags & capi.JOINTS_REGRESSED)
         vertex_path = g_verts is not None or (regressed and (g_joints is not None or g_kp2d is not None))
-        with torch.cuda.device(device):
-            g_betas = torch.empty_like(betas)
-            g_pose = torch.empty_like(pose)
-            g_cam = torch.empty_like(cam) if cam is not None else None
-            if n > 0:
-                wsb = int(capi.lib().smplb200_backward_workspace_bytes(h.ptr, n, flags, int(vertex_path)))
-                if wsb == 0:
-                    raise RuntimeError("smplb200_backward_workspace_bytes rejected the flag combination")
-                ws = torch.empty(wsb, dtype=torch.uint8, device=device)
-                fws = ctx.fwd_ws
-                capi.check(capi.lib().smplb200_backward(
-                    h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(joints),
-                    _ptr(g_verts), _ptr(g_joints), _ptr(g_kp2d),
-                    _ptr(g_betas), _ptr(g_pose), _ptr(g_cam),
-                    _ptr(fws), 0 if fws is None else fws.numel(),
-                    _ptr(ws), wsb, flags, _stream_ptr(device)), "smplb200_backward")
+        # (no torch.cuda.device() switch: every allocation names its device and the library runs on
+        #  the handle's device whatever the caller's current one is)
+        g_betas = torch.empty_like(betas)
+        g_pose = torch.empty_like(pose)
+        g_cam = torch.empty_like(cam) if cam is not None else None
+        if n > 0:
+            wsb = h.backward_workspace_bytes(n, flags, vertex_path)
+            if wsb == 0:
+                raise RuntimeError("smplb200_backward_workspace_bytes rejected the flag combination")
+            ws = torch.empty(wsb, dtype=torch.uint8, device=device) if vertex_path else None
+            fws = ctx.fwd_ws
+            capi.check(capi.lib().smplb200_backward(
+                h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(joints),
+                _ptr(g_verts), _ptr(g_joints), _ptr(g_kp2d),
+                _ptr(g_betas), _ptr(g_pose), _ptr(g_cam),
+                _ptr(fws), 0 if fws is None else fws.numel(),
+                _ptr(ws), wsb if vertex_path else 0, flags, _stream_ptr(device)), "smplb200_backward")
         ctx.fwd_ws = None
         need = ctx.needs_input_grad   # (layer, flags, betas, pose, cam)
         return (None, None, g_betas if need[2] else None, g_pose if need[3] else None,
@@ -153,7 +154,8 @@ class SMPL(nn.Module):
         return d
 
     def handle(self, device) -> capi.ModelHandle:
-        device = torch.device(device)
+        if not isinstance(device, torch.device):
+            device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("SMPL (B200) runs on CUDA devices only; there is no CPU fallback")
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -194,19 +196,18 @@ class SMPL(nn.Module):
     def _forward_impl(self, betas, pose, cam, flags, return_workspace=False):
         device, n = betas.device, int(betas.shape[0])
         h = self.handle(device)
-        with torch.cuda.device(device):
-            verts = torch.empty((n, self.num_verts, 3), dtype=torch.float32, device=device)
-            joints = torch.empty((n, self.num_joints, 3), dtype=torch.float32, device=device)
-            kp2d = None if cam is None else torch.empty((n, self.num_joints, 2), dtype=torch.float32, device=device)
-            ws = None
-            if n > 0:
-                ws_bytes = h.workspace_bytes(n, flags)
-                if ws_bytes == 0:
-                    raise RuntimeError("smplb200_workspace_bytes rejected the flag combination")
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
-                capi.check(capi.lib().smplb200_forward(
-                    h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(verts), _ptr(joints), _ptr(kp2d),
-                    _ptr(ws), ws_bytes, flags, _stream_ptr(device)), "smplb200_forward")
+        verts = torch.empty((n, self.num_verts, 3), dtype=torch.float32, device=device)
+        joints = torch.empty((n, self.num_joints, 3), dtype=torch.float32, device=device)
+        kp2d = None if cam is None else torch.empty((n, self.num_joints, 2), dtype=torch.float32, device=device)
+        ws = None
+        if n > 0:
+            ws_bytes = h.workspace_bytes(n, flags)
+            if ws_bytes == 0:
+                raise RuntimeError("smplb200_workspace_bytes rejected the flag combination")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            capi.check(capi.lib().smplb200_forward(
+                h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(verts), _ptr(joints), _ptr(kp2d),
+                _ptr(ws), ws_bytes, flags, _stream_ptr(device)), "smplb200_forward")
         outs = (verts, joints) if cam is None else (verts, joints, kp2d)
         return outs + (ws,) if return_workspace else outs
 
