@@ -275,6 +275,25 @@ def test_train_step_is_cuda_graph_capturable(dev, models):
         assert all(torch.equal(g, e.grad) for g, e in zip(got, (eb, ep, ec)))
 
 
+def test_make_graphed_callables(dev, models):
+    """torch.cuda.make_graphed_callables (PyTorch's API for graphing one module of an eager training
+    loop) accepts the layer: forward and backward replay as two CUDA graphs, same gradients."""
+    m = models["sparse"]
+    n = 24
+    layer = SMPL(m, precision="fp32", lbs="fma").to(dev)
+    sample = tuple(torch.from_numpy(x).to(dev).requires_grad_() for x in synthetic.make_inputs(n, 51))
+    graphed = torch.cuda.make_graphed_callables(layer, sample)
+    arrs = synthetic.make_inputs(n, 52)
+    outs_g, outs_e = [], []
+    for mod, sink in ((graphed, outs_g), (layer, outs_e)):
+        b, p, c = (torch.from_numpy(x).to(dev).requires_grad_() for x in arrs)
+        v, j, k = mod(b, p, c)
+        (v.square().mean() + j.square().mean() + k.abs().mean()).backward()
+        torch.cuda.synchronize()
+        sink.extend([v.detach().clone(), j.detach().clone(), k.detach().clone(), b.grad, p.grad, c.grad])
+    assert all(torch.equal(a, b_) for a, b_ in zip(outs_g, outs_e))
+
+
 def test_backward_errors_and_empty(dev, models):
     layer = SMPL(models["sparse"], precision="fp32").to(dev)
     h = layer.handle(dev)
