@@ -128,8 +128,10 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       }
     }
   } else if (warp == kLbsWarpMma) {
-    // ===== MMA issuer: one B stage feeds the blend MMAs of BOTH vertex tiles =====
-    if (lane == 0 && nblk > 0) {
+    // ===== MMA issuer: one B stage feeds the blend MMAs of BOTH vertex tiles.  The whole warp runs
+    // the loop convergently and ONE elected lane issues (descriptors stay in uniform registers; from
+    // a divergent `lane == 0` branch every tcgen05.mma costs ~50 clk of issue, 18 per block). =====
+    if (nblk > 0) {
       constexpr uint32_t kLboB = kLbsN * 16, kSbo = 128;
       constexpr uint32_t kHalfB = 6 * kLboB;     // byte offset of the A_lo K half in the image
       ptx::mbar_wait(bar_w, 0);
@@ -139,23 +141,27 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         ptx::mbar_wait(bar_bfull + s, (i / kLbsBStages) & 1);
         ptx::tc_fence_after();
         const uint32_t b_addr = ptx::smem_u32(sB + (size_t)s * kLbsBStage);
-        for (int t = 0; t < ntile; ++t) {
-          const uint32_t d_tmem = tmem_base + (t * kLbsTcAcc + a) * kLbsN;
-          uint32_t acc = 0;
+        if (ptx::elect_one()) {
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {  // (W_hi,A_hi), (W_hi,A_lo), (W_lo,A_hi)
-            const uint32_t wp = tmem_w + t * kLbsK + (g == 2 ? 24 : 0);
-            const uint32_t bp = b_addr + (g == 1 ? kHalfB : 0);
+          for (int t = 0; t < kLbsTiles; ++t) {
+            if (t < ntile) {
+              const uint32_t d_tmem = tmem_base + (t * kLbsTcAcc + a) * kLbsN;
 #pragma unroll
-            for (int ks = 0; ks < 3; ++ks) {  // 24 joints = 3 tf32 k-steps of 8
-              const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * kLboB, kLboB, kSbo);
-              ptx::mma_tf32_ts(d_tmem, wp + ks * 8, bd, kLbsIdesc, acc);
-              acc = 1;
+              for (int g = 0; g < 3; ++g) {  // (W_hi,A_hi), (W_hi,A_lo), (W_lo,A_hi)
+                const uint32_t wp = tmem_w + t * kLbsK + (g == 2 ? 24 : 0);
+                const uint32_t bp = b_addr + (g == 1 ? kHalfB : 0);
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {  // 24 joints = 3 tf32 k-steps of 8
+                  const uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * kLboB, kLboB, kSbo);
+                  ptx::mma_tf32_ts(d_tmem, wp + ks * 8, bd, kLbsIdesc, (uint32_t)((g | ks) != 0));
+                }
+              }
             }
           }
+          ptx::tc_commit(bar_bempty + s);
+          ptx::tc_commit(bar_tfull + a);
         }
-        ptx::tc_commit(bar_bempty + s);
-        ptx::tc_commit(bar_tfull + a);
+        __syncwarp();
       }
     }
   } else if (warp >= kLbsEpiWarp0) {
