@@ -13,5 +13,7 @@ from . import capi  # noqa: F401
 from .smpl import SMPL, GraphedSMPL, HostRunner  # noqa: F401
 from . import sharding  # noqa: F401
 from .decode import decode_gather  # noqa: F401
+from .dcn import DCN, DCNv2, dcn_v2_conv  # noqa: F401
 
-__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "decode_gather", "capi", "synthetic", "sharding", "model_io"]
+__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "decode_gather", "DCN", "DCNv2", "dcn_v2_conv", "capi", "synthetic",
+           "sharding", "model_io"]

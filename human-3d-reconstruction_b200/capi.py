@@ -77,6 +77,8 @@ SYMBOLS = {
     "smplb200_backward_launch_count": (_int, [_vp, _i64, _u32, _int, _int]),
     "smplb200_decode_gather": (_int, [C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp,
                                       C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "smplb200_dcn_v2_workspace_bytes": (_sz, [C.c_int32, C.c_int32]),
+    "smplb200_dcn_v2_forward": (_int, [C.c_int32, _vp, _vp, _vp, _vp, _vp] + [C.c_int32] * 14 + [_vp, _vp, _sz, _vp]),
     "smplb200_strerror": (C.c_char_p, [_int]),
     "smplb200_version": (_int, []),
     "smplb200_last_cuda_error": (_int, []),

@@ -1,0 +1,252 @@
+// DCNv2 forward (modulated deformable 3x3 convolution) as ONE fused implicit GEMM on tcgen05 / TMEM.
+//
+// Replaces the reference's only native op for the forward direction:
+//   modulated_deformable_im2col_cuda  reference src/lib/models/DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:26-54,137-190
+//   + per-image THCudaBlas_SgemmBatched (bias via a ones-vector GEMM, then weight x columns)
+//                                     reference src/lib/models/DCNv2/src/cuda/dcn_v2_cuda.cu:43-173
+// The reference materialises the column buffer [B, Ci*9, Ho*Wo] in global memory (37.7 MB per image
+// at Ci = 256, 64x64) and reads it back in the GEMM.  Here the columns never exist in memory:
+//
+//   D[M = 128 output pixels (TMEM lanes), N = Co] += A[128 pixels, 32 k] * B[Co, 32 k]^T    per K-step
+//
+//   * A (the deformable samples) is produced by loader threads straight INTO TENSOR MEMORY: a thread
+//     owns one output pixel; per K-step (one tap, 32 input channels) it gathers 4 x 32 bilinear
+//     neighbours, blends them with the tap's weights, applies the modulation mask, splits the
+//     result into bf16 hi + lo and writes its TMEM lane with tcgen05.st.  Lanes of a warp are
+//     adjacent pixels, so each gather instruction touches a few adjacent sectors of one channel plane.
+//   * per pixel and tap the sampling geometry (4 plane offsets, 4 bilinear weights with the border
+//     rules folded in, mask) is computed ONCE into shared memory ([tap][value][pixel], conflict free)
+//     and reused for all Ci channels.
+//   * B (the weights) is re-tiled on the device before the launch (k_dcn_pack_w) into K-major bf16
+//     hi | lo tiles with K ordered tap-major (k' = tap * Ci + ci), one bulk-TMA copy per K-step.
+//   * split-bf16 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM): ~2^-16 relative, i.e. fp32-class
+//     results from the bf16 tensor pipe.
+//   * epilogue: thread = pixel reads its Co accumulators, adds the bias, and each warp store covers 32
+//     adjacent pixels of one output channel (128 bytes, coalesced) in the NCHW output.
+//
+// Warp roles (448 threads): warp 0 = bulk-TMA producer of the weight tiles, warp 1 = MMA issuer
+// (warp-uniform, one elected lane), warps 2..13 = three groups of four loader warps (TMEM lane
+// quarter = warp % 4; group g takes K-steps i = g mod 3); warps 2..5 run the epilogue.
+#pragma once
+#include "common.cuh"
+#include "k_chain.cuh"
+#include "ptx.cuh"
+
+namespace smplb200 {
+
+constexpr int kDcnGroups = 3;
+constexpr int kDcnThreads = (2 + 4 * kDcnGroups) * 32;      // 448
+constexpr int kDcnTaps = 9;
+constexpr int kDcnTapVals = 9;                               // 4 offsets, 4 weights, mask
+constexpr int kDcnStagesB = 4;
+constexpr int kDcnStagesA = 8;                               // 32 TMEM columns each (16 hi | 16 lo)
+constexpr int kDcnACol0 = 256;
+constexpr int kDcnMaxCo = 256;
+constexpr uint32_t kDcnTapBytes = kDcnTaps * kDcnTapVals * 128 * 4;   // 41,472
+
+struct DcnShape {
+  int B, Ci, H, W, Co, Ho, Wo;
+  int sh, sw, ph, pw, dh, dw;
+};
+
+inline uint32_t dcn_stage_bytes(int Co) { return 128u * (uint32_t)Co; }     // [hi|lo][4 chunks][Co][8 bf16]
+inline size_t dcn_smem_bytes(int Co) { return (size_t)kDcnStagesB * dcn_stage_bytes(Co) + kDcnTapBytes + 512; }
+inline size_t dcn_weight_image_bytes(int Ci, int Co) { return (size_t)kDcnTaps * (Ci / 32) * dcn_stage_bytes(Co); }
+
+// weight [Co, Ci, 3, 3] fp32 -> per K-step (tap, 32 channels) tile [hi|lo][4 chunks][Co rows][8 bf16]
+__global__ void __launch_bounds__(256)
+k_dcn_pack_w(const float* __restrict__ w, int Co, int Ci, uint16_t* __restrict__ img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Co * Ci * kDcnTaps) return;
+  const int tap = (int)(idx % kDcnTaps);
+  const int ci = (int)((idx / kDcnTaps) % Ci);
+  const int co = (int)(idx / ((long long)kDcnTaps * Ci));
+  const float x = w[idx];
+  const uint16_t hi = f32_to_bf16_rn(x);
+  const uint16_t lo = f32_to_bf16_rn(x - bf16_to_f32(hi));
+  const size_t ks = (size_t)tap * (Ci / 32) + ci / 32;
+  const int c = (ci % 32) / 8, e = ci % 8;
+  const size_t part = (size_t)4 * Co * 8;
+  const size_t base = ks * 2 * part + ((size_t)c * Co + co) * 8 + e;
+  img[base] = hi;
+  img[base + part] = lo;
+}
+
+__global__ void __launch_bounds__(kDcnThreads, 1)
+k_dcn_fwd(const float* __restrict__ input, const float* __restrict__ offset, const float* __restrict__ mask,
+          const uint8_t* __restrict__ wimg, const float* __restrict__ bias, DcnShape s, uint32_t idesc,
+          float* __restrict__ output) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t stage_bytes = 128u * (uint32_t)s.Co;
+  uint8_t* sB = smem;
+  float* sTap = reinterpret_cast<float*>(smem + kDcnStagesB * stage_bytes);    // [tap][val][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDcnStagesB * stage_bytes + kDcnTapBytes);
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = b_full + kDcnStagesB;
+  uint64_t* a_full = b_empty + kDcnStagesB;
+  uint64_t* a_empty = a_full + kDcnStagesA;
+  uint64_t* d_full = a_empty + kDcnStagesA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int steps_per_tap = s.Ci / 32;
+  const int nks = kDcnTaps * steps_per_tap;
+  const long long HoWo = (long long)s.Ho * s.Wo;
+  const long long P = (long long)s.B * HoWo;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kDcnStagesB; ++i) { ptx::mbar_init(b_full + i, 1); ptx::mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < kDcnStagesA; ++i) { ptx::mbar_init(a_full + i, 4); ptx::mbar_init(a_empty + i, 1); }
+    ptx::mbar_init(d_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== bulk-TMA producer: one weight tile (hi | lo) per K-step =====
+    if (lane == 0) {
+      for (int i = 0; i < nks; ++i) {
+        const int st = i % kDcnStagesB;
+        ptx::mbar_wait(b_empty + st, ((i / kDcnStagesB) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(b_full + st, stage_bytes);
+        ptx::bulk_g2s(sB + (size_t)st * stage_bytes, wimg + (size_t)i * stage_bytes, stage_bytes, b_full + st);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t lbo = (uint32_t)s.Co * 16u, part = 4u * lbo;
+    for (int i = 0; i < nks; ++i) {
+      const int sb = i % kDcnStagesB, sa = i % kDcnStagesA;
+      ptx::mbar_wait(b_full + sb, (i / kDcnStagesB) & 1);
+      ptx::mbar_wait(a_full + sa, (i / kDcnStagesA) & 1);
+      ptx::tc_fence_after();
+      const uint32_t b_addr = ptx::smem_u32(sB + (size_t)sb * stage_bytes);
+      const uint32_t a_addr = tmem_base + kDcnACol0 + sa * 32;
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {          // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo)
+          const uint32_t ap = a_addr + (g == 1 ? 16 : 0);
+          const uint32_t bp = b_addr + (g == 2 ? part : 0);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t bd = ptx::make_smem_desc(bp + kk * 2 * lbo, lbo, 128);
+            ptx::mma_bf16_ts(tmem_base, ap + kk * 8, bd, idesc, (uint32_t)((i | g | kk) != 0));
+          }
+        }
+        ptx::tc_commit(b_empty + sb);
+        ptx::tc_commit(a_empty + sa);
+        if (i == nks - 1) ptx::tc_commit(d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== loaders: thread = output pixel =====
+    const int lw = warp - 2, q = warp & 3, grp = lw >> 2;
+    const int px = q * 32 + lane;                         // pixel within the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const long long p = (long long)blockIdx.x * 128 + px;
+    const bool valid = p < P;
+    const long long b = valid ? p / HoWo : 0;
+    const int r = valid ? (int)(p - b * HoWo) : 0;
+    const int ho = r / s.Wo, wo = r - ho * s.Wo;
+
+    // --- sampling geometry of this pixel, taps t = grp, grp + 3, grp + 6 (each group a third)
+    for (int t = grp; t < kDcnTaps; t += kDcnGroups) {
+      float* dst = sTap + (size_t)t * kDcnTapVals * 128 + px;
+      int o[4] = {-1, -1, -1, -1};        // -1: neighbour outside the map (contributes exactly 0)
+      float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+      float mk = 0.f;
+      if (valid) {
+        const int i = t / 3, j = t - 3 * i;
+        const float* offp = offset + ((size_t)b * 2 * kDcnTaps + 2 * t) * HoWo + r;
+        const float off_h = __ldg(offp), off_w = __ldg(offp + HoWo);
+        const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + off_h;
+        const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + off_w;
+        if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {
+          mk = __ldg(mask + ((size_t)b * kDcnTaps + t) * HoWo + r);
+          const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+          const int h_high = h_low + 1, w_high = w_low + 1;
+          const float lh = h_im - (float)h_low, lwd = w_im - (float)w_low;
+          const float hh = 1.f - lh, hw = 1.f - lwd;
+          const bool t0 = h_low >= 0, t1 = h_high <= s.H - 1, l0 = w_low >= 0, l1 = w_high <= s.W - 1;
+          if (t0 && l0) { o[0] = h_low * s.W + w_low; wgt[0] = hh * hw; }
+          if (t0 && l1) { o[1] = h_low * s.W + w_high; wgt[1] = hh * lwd; }
+          if (t1 && l0) { o[2] = h_high * s.W + w_low; wgt[2] = lh * hw; }
+          if (t1 && l1) { o[3] = h_high * s.W + w_high; wgt[3] = lh * lwd; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dst[u * 128] = __int_as_float(o[u]);
+        dst[(4 + u) * 128] = wgt[u];
+      }
+      dst[8 * 128] = mk;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(4 * kDcnGroups * 32) : "memory");   // loader warps only
+
+    const float* img = input + (size_t)b * s.Ci * s.H * s.W;
+    const size_t HW = (size_t)s.H * s.W;
+    for (int i = grp; i < nks; i += kDcnGroups) {
+      const int t = i / steps_per_tap, cb = (i - t * steps_per_tap) * 32;
+      const float* tv = sTap + (size_t)t * kDcnTapVals * 128 + px;
+      const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
+                o3 = __float_as_int(tv[384]);
+      const float w0 = tv[512], w1 = tv[640], w2 = tv[768], w3 = tv[896], mk = tv[1024];
+      const float* pl = img + (size_t)cb * HW;
+      float val[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const float* c = pl + (size_t)u * HW;
+        // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
+        const float v0 = o0 >= 0 ? __ldg(c + o0) : 0.f, v1 = o1 >= 0 ? __ldg(c + o1) : 0.f;
+        const float v2 = o2 >= 0 ? __ldg(c + o2) : 0.f, v3 = o3 >= 0 ? __ldg(c + o3) : 0.f;
+        val[u] = (w0 * v0 + w1 * v1 + w2 * v2 + w3 * v3) * mk;
+      }
+      const int sa = i % kDcnStagesA;
+      ptx::mbar_wait(a_empty + sa, ((i / kDcnStagesA) & 1) ^ 1);
+      ptx::tc_fence_after();
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const uint16_t h0 = f32_to_bf16_rn(val[2 * u]), h1 = f32_to_bf16_rn(val[2 * u + 1]);
+        hi[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        lo[u] = (uint32_t)f32_to_bf16_rn(val[2 * u] - bf16_to_f32(h0)) |
+                ((uint32_t)f32_to_bf16_rn(val[2 * u + 1] - bf16_to_f32(h1)) << 16);
+      }
+      const uint32_t acol = tmem_base + lane_addr + kDcnACol0 + sa * 32;
+      ptx::tmem_st16(acol, hi);
+      ptx::tmem_st16(acol + 16, lo);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_full + sa);
+      __syncwarp();
+    }
+    if (lw < 4) {
+      // ===== epilogue: D[pixel, co] + bias -> output[b, co, ho, wo] =====
+      ptx::mbar_wait(d_full, 0);
+      ptx::tc_fence_after();
+      float* dst = output + (size_t)b * s.Co * HoWo + r;
+#pragma unroll 1
+      for (int c0 = 0; c0 < s.Co; c0 += 16) {
+        uint32_t d[16];
+        ptx::tmem_ld16(tmem_base + lane_addr + c0, d);
+        ptx::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u)
+            dst[(size_t)(c0 + u) * HoWo] = __uint_as_float(d[u]) + (bias ? __ldg(bias + c0 + u) : 0.f);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace smplb200

@@ -25,6 +25,7 @@
 #include "k_decode.cuh"
 #include "k_backward.cuh"
 #include "k_blend_bwd_tc.cuh"
+#include "k_dcn.cuh"
 
 using namespace smplb200;
 
@@ -955,6 +956,53 @@ int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int
     k_decode_gather<false><<<(unsigned)batch, kDecThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         heat, num_classes, height, width, k, dh, scores, reinterpret_cast<long long*>(inds), clses, ys, xs);
   }
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+size_t smplb200_dcn_v2_workspace_bytes(int32_t channels_in, int32_t channels_out) {
+  if (channels_in < 32 || channels_in % 32 || channels_out < 16 || channels_out % 16 || channels_out > kDcnMaxCo)
+    return 0;
+  return align_up(dcn_weight_image_bytes(channels_in, channels_out), 256);
+}
+
+int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* weight, const float* bias,
+                            const float* offset, const float* mask, int32_t batch, int32_t channels_in,
+                            int32_t height, int32_t width, int32_t channels_out,
+                            int32_t kernel_h, int32_t kernel_w, int32_t stride_h, int32_t stride_w,
+                            int32_t pad_h, int32_t pad_w, int32_t dilation_h, int32_t dilation_w,
+                            int32_t deformable_group, float* output,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (batch < 0 || channels_in < 1 || channels_out < 1 || height < 1 || width < 1 || stride_h < 1 ||
+      stride_w < 1 || pad_h < 0 || pad_w < 0 || dilation_h < 1 || dilation_w < 1 || kernel_h < 1 || kernel_w < 1)
+    return SMPLB200_ERR_INVALID_ARG;
+  if (kernel_h != 3 || kernel_w != 3 || deformable_group != 1) return SMPLB200_ERR_UNSUPPORTED;
+  const size_t need = smplb200_dcn_v2_workspace_bytes(channels_in, channels_out);
+  if (need == 0) return SMPLB200_ERR_UNSUPPORTED;
+  DcnShape sh{};
+  sh.B = batch; sh.Ci = channels_in; sh.H = height; sh.W = width; sh.Co = channels_out;
+  sh.sh = stride_h; sh.sw = stride_w; sh.ph = pad_h; sh.pw = pad_w; sh.dh = dilation_h; sh.dw = dilation_w;
+  sh.Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
+  sh.Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
+  if (sh.Ho < 1 || sh.Wo < 1) return SMPLB200_ERR_INVALID_ARG;
+  if ((long long)height * width > (1LL << 30)) return SMPLB200_ERR_UNSUPPORTED;   // plane offsets are int32
+  if (batch == 0) return SMPLB200_OK;
+  if (!input || !weight || !offset || !mask || !output) return SMPLB200_ERR_INVALID_ARG;
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return SMPLB200_ERR_WORKSPACE;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long welems = (long long)channels_out * channels_in * kDcnTaps;
+  k_dcn_pack_w<<<(unsigned)((welems + 255) / 256), 256, 0, s>>>(weight, channels_out, channels_in,
+                                                              static_cast<uint16_t*>(workspace));
+  CU_TRY(cudaGetLastError());
+  const size_t smem = dcn_smem_bytes(channels_out);
+  CU_TRY(cudaFuncSetAttribute(k_dcn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long pixels = (long long)batch * sh.Ho * sh.Wo;
+  const uint32_t idesc = ptx::make_idesc(ptx::kFmtBF16, 128, (uint32_t)channels_out);
+  k_dcn_fwd<<<(unsigned)((pixels + 127) / 128), kDcnThreads, smem, s>>>(
+      input, offset, mask, static_cast<const uint8_t*>(workspace), bias, sh, idesc, output);
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }

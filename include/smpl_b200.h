@@ -210,6 +210,28 @@ int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int
                            float* scores, int64_t* inds, int32_t* clses, float* ys, float* xs,
                            float* const* gathered, void* stream);
 
+/* ---- DCNv2 forward: the reference's one native op ------------------- */
+/* output[B,Co,Ho,Wo] = modulated deformable convolution of input[B,Ci,H,W] with weight[Co,Ci,kh,kw],
+ * offset[B,2*dg*kh*kw,Ho,Wo] (channel 2t = dh, 2t+1 = dw of tap t = i*kw + j), mask[B,dg*kh*kw,Ho,Wo]
+ * and bias[Co] (may be NULL).  Same arguments, in the same order, as the reference binding
+ * `dcn_v2_forward(input, weight, bias, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h,
+ * pad_w, dilation_h, dilation_w, deformable_group)` (reference src/lib/models/DCNv2/src/dcn_v2.h:9-39,
+ * src/vision.cpp:4-9), which replaces modulated_deformable_im2col_cuda + two batched SGEMMs
+ * (reference src/cuda/dcn_v2_cuda.cu:43-173).  One fused implicit-GEMM kernel, no column buffer.
+ * Built for what the reference network uses (reference src/lib/models/model.py:355: 3x3, one
+ * deformable group): kernel 3x3, deformable_group 1, Ci a multiple of 32, Co a multiple of 16 and
+ * <= 256; any stride / padding / dilation.  Anything else returns SMPLB200_ERR_UNSUPPORTED.
+ * `workspace`: smplb200_dcn_v2_workspace_bytes(ci, co) of 256-byte aligned device scratch (the
+ * re-tiled bf16 weight image, rebuilt every call because weights are trainable parameters).        */
+size_t smplb200_dcn_v2_workspace_bytes(int32_t channels_in, int32_t channels_out);
+int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* weight, const float* bias,
+                            const float* offset, const float* mask, int32_t batch, int32_t channels_in,
+                            int32_t height, int32_t width, int32_t channels_out,
+                            int32_t kernel_h, int32_t kernel_w, int32_t stride_h, int32_t stride_w,
+                            int32_t pad_h, int32_t pad_w, int32_t dilation_h, int32_t dilation_w,
+                            int32_t deformable_group, float* output,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------- */
 const char* smplb200_strerror(int status);
 int smplb200_version(void);
