@@ -489,6 +489,37 @@ def main():
                 f"backward_call_{n}_bodies_us": dt_b * 1e6, "backward_bodies_per_s": n / dt_b,
                 "launches_per_backward": int(lib_.smplb200_backward_launch_count(hb.ptr, n, lay_t.flags, 1, 0)),
                 "cpu_kind": "port (torch autograd of oracle/smpl_ref.py, fp32, one call)"}
+            # ---- next §8(f) row 4: the reference's one native op, DCNv2 forward, on the DLA-34 layers ----
+            from human_3d_reconstruction_b200 import dcn_v2_conv
+            from oracle.dcn_ref import dcn_v2_forward as dcn_cpu
+            dcn_layers = [(1, 512, 256, 16), (1, 256, 256, 32), (2, 256, 128, 32), (2, 128, 128, 64),
+                          (4, 128, 64, 64), (5, 64, 64, 128), (1, 256, 64, 32)]   # (count, Ci, Co, H=W)
+            gd = torch.Generator().manual_seed(317)
+            dcn_total, dcn_rows = 0.0, {}
+            for cnt, Ci_, Co_, Hd in dcn_layers:
+                xd = torch.randn(32, Ci_, Hd, Hd, generator=gd).to(dev)
+                wd = (torch.randn(Co_, Ci_, 3, 3, generator=gd) / (Ci_ * 9) ** 0.5).to(dev)
+                bd_ = torch.randn(Co_, generator=gd).to(dev)
+                od = (torch.randn(32, 18, Hd, Hd, generator=gd) * 2.0).to(dev)
+                md = torch.rand(32, 9, Hd, Hd, generator=gd).to(dev)
+                for _ in range(2):
+                    dcn_v2_conv(xd, od, md, wd, bd_)
+                dt_d = time_loop(lambda: dcn_v2_conv(xd, od, md, wd, bd_), 5, torch) / 5
+                dcn_rows[f"{Ci_}->{Co_}@{Hd}x{Hd}"] = dt_d * 1e6
+                dcn_total += cnt * dt_d
+                del xd, wd, od, md
+            xc = torch.randn(1, 64, 128, 128, generator=gd)
+            t0 = time.perf_counter()
+            dcn_cpu(xc, torch.randn(64, 64, 3, 3, generator=gd) / 24.0, torch.zeros(64),
+                    torch.randn(1, 18, 128, 128, generator=gd) * 2.0, torch.rand(1, 9, 128, 128, generator=gd))
+            dt_dc = time.perf_counter() - t0
+            next_rows["dcn_v2_forward"] = {
+                "workload": "the 16 DeformConv layers of the reference DLA-34 (7 distinct shapes), batch 32, 512x512 input, "
+                            "random offsets (sigma 2 px) and masks",
+                "layer_us": dcn_rows, "network_16_layers_ms": dcn_total * 1e3,
+                "cpu_reference_port_ms_per_image_one_64to64_128x128_layer": dt_dc * 1e3,
+                "cpu_kind": "port (oracle/dcn_ref.py, pinned against torchvision CPU deform_conv2d and the reference KAT)",
+                "bound": "L1/LSU gather rate (profiles/r01_dcn_ncu.json)"}
         t_kern_end = time.time()
 
     clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
