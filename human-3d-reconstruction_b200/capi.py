@@ -25,7 +25,8 @@ JOINTS_KINEMATIC, JOINTS_REGRESSED = 0, 1 << 3
 ROTATE_BASE = 1 << 4
 LBS_AUTO, LBS_FMA, LBS_TC, LBS_DENSE = 0, 1 << 5, 2 << 5, 3 << 5
 TC_MIN_BATCH = 32        # AUTO: tcgen05 (bf16x3) blendshapes from this many bodies
-TC_LBS_MIN_BATCH = 384   # AUTO: tcgen05 skinning blend from this many bodies
+TC_LBS_MIN_BATCH = 384
+DCN_INPUT_NHWC = 1   # AUTO: tcgen05 skinning blend from this many bodies
 COEF_K = 224
 
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32,
@@ -77,8 +78,8 @@ SYMBOLS = {
     "smplb200_backward_launch_count": (_int, [_vp, _i64, _u32, _int, _int]),
     "smplb200_decode_gather": (_int, [C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp,
                                       C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "smplb200_dcn_v2_workspace_bytes": (_sz, [C.c_int32, C.c_int32]),
-    "smplb200_dcn_v2_forward": (_int, [C.c_int32, _vp, _vp, _vp, _vp, _vp] + [C.c_int32] * 14 + [_vp, _vp, _sz, _vp]),
+    "smplb200_dcn_v2_workspace_bytes": (_sz, [C.c_int32] * 5 + [_u32]),
+    "smplb200_dcn_v2_forward": (_int, [C.c_int32, _vp, _vp, _vp, _vp, _vp] + [C.c_int32] * 14 + [_vp, _vp, _sz, _u32, _vp]),
     "smplb200_strerror": (C.c_char_p, [_int]),
     "smplb200_version": (_int, []),
     "smplb200_last_cuda_error": (_int, []),

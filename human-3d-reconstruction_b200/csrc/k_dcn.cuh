@@ -9,11 +9,15 @@
 //
 //   D[M = 128 output pixels (TMEM lanes), N = Co] += A[128 pixels, 32 k] * B[Co, 32 k]^T    per K-step
 //
-//   * A (the deformable samples) is produced by loader threads straight INTO TENSOR MEMORY: a thread
-//     owns one output pixel; per K-step (one tap, 32 input channels) it gathers 4 x 32 bilinear
-//     neighbours, blends them with the tap's weights, applies the modulation mask, splits the
-//     result into bf16 hi + lo and writes its TMEM lane with tcgen05.st.  Lanes of a warp are
-//     adjacent pixels, so each gather instruction touches a few adjacent sectors of one channel plane.
+//   * A (the deformable samples) is produced by loader warps straight INTO TENSOR MEMORY.  The input
+//     is read CHANNELS-LAST (a transposed copy made by k_nchw_to_nhwc, or the caller's own NHWC
+//     tensor): a bilinear neighbour of a pixel is then one contiguous 128-byte line per 32 channels,
+//     and 8 lanes fetch it with ONE 16-byte load each, so a warp instruction touches 4 full lines
+//     instead of ~20 scattered 32-byte sectors (first version, NCHW gathers: l1tex 65-78 % busy at
+//     ~20 sectors per load, profiles/r01_dcn_ncu.json).  Per K-step (one tap, 32 channels) a warp
+//     makes 8 rounds of 4 pixels x 8 lanes, blends the 4 neighbours with the tap's weights, applies
+//     the mask, transposes the 32 x 32 values through a private shared-memory tile so that lane =
+//     pixel, splits them into bf16 hi + lo and writes its TMEM lanes with tcgen05.st.
 //   * per pixel and tap the sampling geometry (4 plane offsets, 4 bilinear weights with the border
 //     rules folded in, mask) is computed ONCE into shared memory ([tap][value][pixel], conflict free)
 //     and reused for all Ci channels.
@@ -38,7 +42,7 @@ constexpr int kDcnGroups = 3;
 constexpr int kDcnThreads = (2 + 4 * kDcnGroups) * 32;      // 448
 constexpr int kDcnTaps = 9;
 constexpr int kDcnTapVals = 9;                               // 4 offsets, 4 weights, mask
-constexpr int kDcnStagesB = 4;
+constexpr int kDcnStagesB = 3;
 constexpr int kDcnStagesA = 8;                               // 32 TMEM columns each (16 hi | 16 lo)
 constexpr int kDcnACol0 = 256;
 constexpr int kDcnMaxCo = 256;
@@ -47,11 +51,46 @@ constexpr uint32_t kDcnTapBytes = kDcnTaps * kDcnTapVals * 128 * 4;   // 41,472
 struct DcnShape {
   int B, Ci, H, W, Co, Ho, Wo;
   int sh, sw, ph, pw, dh, dw;
+  int tiles_x, tiles_y;           // output tiles of kDcnTileW x kDcnTileH pixels per image
 };
 
+// A CTA's 128 output pixels form a 16 x 8 BLOCK, not a 128-pixel row segment: the input region its
+// 9 taps x 4 neighbours sample is then ~(16+8) x (8+10) pixels (~110 KB at Ci = 64) and stays in L1,
+// where a row segment samples ~(128+8) x 11 pixels (~380 KB) and re-fetched every line from L2
+// (first versions: 4.8 GB of L2->SM traffic for the 64->64 @128x128 layer, the whole run time).
+constexpr int kDcnTileW = 16, kDcnTileH = 8;
+
 inline uint32_t dcn_stage_bytes(int Co) { return 128u * (uint32_t)Co; }     // [hi|lo][4 chunks][Co][8 bf16]
-inline size_t dcn_smem_bytes(int Co) { return (size_t)kDcnStagesB * dcn_stage_bytes(Co) + kDcnTapBytes + 512; }
+constexpr int kDcnTileStride = 36;                           // floats per pixel row of a warp's transpose tile
+constexpr uint32_t kDcnTileBytes = 32 * kDcnTileStride * 4;   // 4,608 per loader warp
+inline size_t dcn_smem_bytes(int Co) {
+  return (size_t)kDcnStagesB * dcn_stage_bytes(Co) + kDcnTapBytes + (size_t)4 * kDcnGroups * kDcnTileBytes + 512;
+}
 inline size_t dcn_weight_image_bytes(int Ci, int Co) { return (size_t)kDcnTaps * (Ci / 32) * dcn_stage_bytes(Co); }
+
+// input [B, C, HW] -> [B, HW, C] (channels-last copy read by the loaders)
+__global__ void __launch_bounds__(256)
+k_nchw_to_nhwc(const float* __restrict__ in, int C, long long HW, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* src = in + (size_t)blockIdx.z * C * HW;
+  float* dst = out + (size_t)blockIdx.z * C * HW;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + 8 * k;
+    const long long p = p0 + tx;
+    tile[ty + 8 * k][tx] = (c < C && p < HW) ? __ldg(src + (size_t)c * HW + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long p = p0 + ty + 8 * k;
+    const int c = c0 + tx;
+    if (c < C && p < HW) dst[(size_t)p * C + c] = tile[tx][ty + 8 * k];
+  }
+}
 
 // weight [Co, Ci, 3, 3] fp32 -> per K-step (tap, 32 channels) tile [hi|lo][4 chunks][Co rows][8 bf16]
 __global__ void __launch_bounds__(256)
@@ -73,14 +112,16 @@ k_dcn_pack_w(const float* __restrict__ w, int Co, int Ci, uint16_t* __restrict__
 }
 
 __global__ void __launch_bounds__(kDcnThreads, 1)
-k_dcn_fwd(const float* __restrict__ input, const float* __restrict__ offset, const float* __restrict__ mask,
+k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ offset, const float* __restrict__ mask,
           const uint8_t* __restrict__ wimg, const float* __restrict__ bias, DcnShape s, uint32_t idesc,
           float* __restrict__ output) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t stage_bytes = 128u * (uint32_t)s.Co;
   uint8_t* sB = smem;
   float* sTap = reinterpret_cast<float*>(smem + kDcnStagesB * stage_bytes);    // [tap][val][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDcnStagesB * stage_bytes + kDcnTapBytes);
+  float* sTile = reinterpret_cast<float*>(smem + kDcnStagesB * stage_bytes + kDcnTapBytes);   // per loader warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDcnStagesB * stage_bytes + kDcnTapBytes +
+                                               4 * kDcnGroups * kDcnTileBytes);
   uint64_t* b_full = bars;
   uint64_t* b_empty = b_full + kDcnStagesB;
   uint64_t* a_full = b_empty + kDcnStagesB;
@@ -92,7 +133,6 @@ k_dcn_fwd(const float* __restrict__ input, const float* __restrict__ offset, con
   const int steps_per_tap = s.Ci / 32;
   const int nks = kDcnTaps * steps_per_tap;
   const long long HoWo = (long long)s.Ho * s.Wo;
-  const long long P = (long long)s.B * HoWo;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kDcnStagesB; ++i) { ptx::mbar_init(b_full + i, 1); ptx::mbar_init(b_empty + i, 1); }
@@ -148,11 +188,12 @@ k_dcn_fwd(const float* __restrict__ input, const float* __restrict__ offset, con
     const int lw = warp - 2, q = warp & 3, grp = lw >> 2;
     const int px = q * 32 + lane;                         // pixel within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const long long p = (long long)blockIdx.x * 128 + px;
-    const bool valid = p < P;
-    const long long b = valid ? p / HoWo : 0;
-    const int r = valid ? (int)(p - b * HoWo) : 0;
-    const int ho = r / s.Wo, wo = r - ho * s.Wo;
+    const int tiles_per_img = s.tiles_x * s.tiles_y;
+    const long long b = blockIdx.x / tiles_per_img;
+    const int tix = (int)(blockIdx.x - b * tiles_per_img);
+    const int ho = (tix / s.tiles_x) * kDcnTileH + px / kDcnTileW, wo = (tix % s.tiles_x) * kDcnTileW + px % kDcnTileW;
+    const bool valid = ho < s.Ho && wo < s.Wo;
+    const int r = valid ? ho * s.Wo + wo : 0;
 
     // --- sampling geometry of this pixel, taps t = grp, grp + 3, grp + 6 (each group a third)
     for (int t = grp; t < kDcnTaps; t += kDcnGroups) {
@@ -173,10 +214,11 @@ k_dcn_fwd(const float* __restrict__ input, const float* __restrict__ offset, con
           const float lh = h_im - (float)h_low, lwd = w_im - (float)w_low;
           const float hh = 1.f - lh, hw = 1.f - lwd;
           const bool t0 = h_low >= 0, t1 = h_high <= s.H - 1, l0 = w_low >= 0, l1 = w_high <= s.W - 1;
-          if (t0 && l0) { o[0] = h_low * s.W + w_low; wgt[0] = hh * hw; }
-          if (t0 && l1) { o[1] = h_low * s.W + w_high; wgt[1] = hh * lwd; }
-          if (t1 && l0) { o[2] = h_high * s.W + w_low; wgt[2] = lh * hw; }
-          if (t1 && l1) { o[3] = h_high * s.W + w_high; wgt[3] = lh * lwd; }
+          const int img0 = (int)b * s.H * s.W;        // NHWC pixel index of the image's first pixel
+          if (t0 && l0) { o[0] = img0 + h_low * s.W + w_low; wgt[0] = hh * hw; }
+          if (t0 && l1) { o[1] = img0 + h_low * s.W + w_high; wgt[1] = hh * lwd; }
+          if (t1 && l0) { o[2] = img0 + h_high * s.W + w_low; wgt[2] = lh * hw; }
+          if (t1 && l1) { o[3] = img0 + h_high * s.W + w_high; wgt[3] = lh * lwd; }
         }
       }
 #pragma unroll
@@ -188,24 +230,42 @@ k_dcn_fwd(const float* __restrict__ input, const float* __restrict__ offset, con
     }
     asm volatile("bar.sync 1, %0;" ::"n"(4 * kDcnGroups * 32) : "memory");   // loader warps only
 
-    const float* img = input + (size_t)b * s.Ci * s.H * s.W;
-    const size_t HW = (size_t)s.H * s.W;
+    float* tile = sTile + (size_t)lw * (32 * kDcnTileStride);
+    const int sub = lane & 7, pq = lane >> 3;             // 8 lanes per pixel, 4 pixels per round
     for (int i = grp; i < nks; i += kDcnGroups) {
       const int t = i / steps_per_tap, cb = (i - t * steps_per_tap) * 32;
-      const float* tv = sTap + (size_t)t * kDcnTapVals * 128 + px;
-      const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
-                o3 = __float_as_int(tv[384]);
-      const float w0 = tv[512], w1 = tv[640], w2 = tv[768], w3 = tv[896], mk = tv[1024];
-      const float* pl = img + (size_t)cb * HW;
+      const float* tvb = sTap + (size_t)t * kDcnTapVals * 128 + q * 32;
+      const float* cbase = input + cb + 4 * sub;
+      // ---- 8 rounds: pixel pw = 4*rd + pq of this warp, channels cb + 4*sub .. +3
+#pragma unroll
+      for (int rd = 0; rd < 8; ++rd) {
+        const int pw = 4 * rd + pq;
+        const float* tv = tvb + pw;
+        const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
+                  o3 = __float_as_int(tv[384]);
+        const float w0 = tv[512], w1 = tv[640], w2 = tv[768], w3 = tv[896], mk = tv[1024];
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 v0 = o0 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o0 * s.Ci)) : z;
+        const float4 v1 = o1 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o1 * s.Ci)) : z;
+        const float4 v2 = o2 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o2 * s.Ci)) : z;
+        const float4 v3 = o3 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o3 * s.Ci)) : z;
+        // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
+        float4 r4;
+        r4.x = (w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x) * mk;
+        r4.y = (w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y) * mk;
+        r4.z = (w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z) * mk;
+        r4.w = (w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w) * mk;
+        *reinterpret_cast<float4*>(tile + pw * kDcnTileStride + 4 * sub) = r4;
+      }
+      __syncwarp();
+      // ---- transpose: lane = pixel reads its 32 channels
       float val[32];
 #pragma unroll
-      for (int u = 0; u < 32; ++u) {
-        const float* c = pl + (size_t)u * HW;
-        // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
-        const float v0 = o0 >= 0 ? __ldg(c + o0) : 0.f, v1 = o1 >= 0 ? __ldg(c + o1) : 0.f;
-        const float v2 = o2 >= 0 ? __ldg(c + o2) : 0.f, v3 = o3 >= 0 ? __ldg(c + o3) : 0.f;
-        val[u] = (w0 * v0 + w1 * v1 + w2 * v2 + w3 * v3) * mk;
+      for (int k = 0; k < 8; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(tile + lane * kDcnTileStride + 4 * k);
+        val[4 * k] = x.x; val[4 * k + 1] = x.y; val[4 * k + 2] = x.z; val[4 * k + 3] = x.w;
       }
+      __syncwarp();
       const int sa = i % kDcnStagesA;
       ptx::mbar_wait(a_empty + sa, ((i / kDcnStagesA) & 1) ^ 1);
       ptx::tc_fence_after();

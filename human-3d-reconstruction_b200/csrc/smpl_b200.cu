@@ -960,10 +960,15 @@ int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int
   return SMPLB200_OK;
 }
 
-size_t smplb200_dcn_v2_workspace_bytes(int32_t channels_in, int32_t channels_out) {
-  if (channels_in < 32 || channels_in % 32 || channels_out < 16 || channels_out % 16 || channels_out > kDcnMaxCo)
+size_t smplb200_dcn_v2_workspace_bytes(int32_t batch, int32_t channels_in, int32_t height, int32_t width,
+                                       int32_t channels_out, uint32_t flags) {
+  if (channels_in < 32 || channels_in % 32 || channels_out < 16 || channels_out % 16 || channels_out > kDcnMaxCo ||
+      batch < 0 || height < 1 || width < 1 || (flags & ~SMPLB200_DCN_INPUT_NHWC))
     return 0;
-  return align_up(dcn_weight_image_bytes(channels_in, channels_out), 256);
+  size_t bytes = align_up(dcn_weight_image_bytes(channels_in, channels_out), 256);
+  if (!(flags & SMPLB200_DCN_INPUT_NHWC))
+    bytes += align_up((size_t)std::max(batch, 1) * channels_in * height * width * sizeof(float), 256);
+  return bytes;
 }
 
 int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* weight, const float* bias,
@@ -972,12 +977,13 @@ int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* wei
                             int32_t kernel_h, int32_t kernel_w, int32_t stride_h, int32_t stride_w,
                             int32_t pad_h, int32_t pad_w, int32_t dilation_h, int32_t dilation_w,
                             int32_t deformable_group, float* output,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+                            void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
   if (batch < 0 || channels_in < 1 || channels_out < 1 || height < 1 || width < 1 || stride_h < 1 ||
-      stride_w < 1 || pad_h < 0 || pad_w < 0 || dilation_h < 1 || dilation_w < 1 || kernel_h < 1 || kernel_w < 1)
+      stride_w < 1 || pad_h < 0 || pad_w < 0 || dilation_h < 1 || dilation_w < 1 || kernel_h < 1 || kernel_w < 1 ||
+      (flags & ~SMPLB200_DCN_INPUT_NHWC))
     return SMPLB200_ERR_INVALID_ARG;
   if (kernel_h != 3 || kernel_w != 3 || deformable_group != 1) return SMPLB200_ERR_UNSUPPORTED;
-  const size_t need = smplb200_dcn_v2_workspace_bytes(channels_in, channels_out);
+  const size_t need = smplb200_dcn_v2_workspace_bytes(batch, channels_in, height, width, channels_out, flags);
   if (need == 0) return SMPLB200_ERR_UNSUPPORTED;
   DcnShape sh{};
   sh.B = batch; sh.Ci = channels_in; sh.H = height; sh.W = width; sh.Co = channels_out;
@@ -985,24 +991,38 @@ int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* wei
   sh.Ho = (height + 2 * pad_h - (dilation_h * (kernel_h - 1) + 1)) / stride_h + 1;
   sh.Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
   if (sh.Ho < 1 || sh.Wo < 1) return SMPLB200_ERR_INVALID_ARG;
-  if ((long long)height * width > (1LL << 30)) return SMPLB200_ERR_UNSUPPORTED;   // plane offsets are int32
+  if ((long long)batch * height * width >= (1LL << 31)) return SMPLB200_ERR_UNSUPPORTED;   // pixel offsets are int32
   if (batch == 0) return SMPLB200_OK;
   if (!input || !weight || !offset || !mask || !output) return SMPLB200_ERR_INVALID_ARG;
   if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return SMPLB200_ERR_WORKSPACE;
+  if (!aligned16(input)) return SMPLB200_ERR_ALIGNMENT;
   DeviceGuard guard(device);
   if (guard.err != cudaSuccess) return cuda_fail(guard.err);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
   const long long welems = (long long)channels_out * channels_in * kDcnTaps;
   k_dcn_pack_w<<<(unsigned)((welems + 255) / 256), 256, 0, s>>>(weight, channels_out, channels_in,
-                                                              static_cast<uint16_t*>(workspace));
+                                                              reinterpret_cast<uint16_t*>(ws));
   CU_TRY(cudaGetLastError());
+  const float* nhwc = input;
+  if (!(flags & SMPLB200_DCN_INPUT_NHWC)) {
+    float* xt = reinterpret_cast<float*>(ws + align_up(dcn_weight_image_bytes(channels_in, channels_out), 256));
+    const long long HW = (long long)height * width;
+    dim3 g((unsigned)((HW + 31) / 32), (unsigned)(channels_in / 32), (unsigned)batch);
+    k_nchw_to_nhwc<<<g, 256, 0, s>>>(input, channels_in, HW, xt);
+    CU_TRY(cudaGetLastError());
+    nhwc = xt;
+  }
   const size_t smem = dcn_smem_bytes(channels_out);
   CU_TRY(cudaFuncSetAttribute(k_dcn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long pixels = (long long)batch * sh.Ho * sh.Wo;
+  sh.tiles_x = (sh.Wo + kDcnTileW - 1) / kDcnTileW;
+  sh.tiles_y = (sh.Ho + kDcnTileH - 1) / kDcnTileH;
+  const long long ctas = (long long)batch * sh.tiles_x * sh.tiles_y;
+  if (ctas >= (1LL << 31)) return SMPLB200_ERR_UNSUPPORTED;
   const uint32_t idesc = ptx::make_idesc(ptx::kFmtBF16, 128, (uint32_t)channels_out);
-  k_dcn_fwd<<<(unsigned)((pixels + 127) / 128), kDcnThreads, smem, s>>>(
-      input, offset, mask, static_cast<const uint8_t*>(workspace), bias, sh, idesc, output);
+  k_dcn_fwd<<<(unsigned)ctas, kDcnThreads, smem, s>>>(
+      nhwc, offset, mask, ws, bias, sh, idesc, output);
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }

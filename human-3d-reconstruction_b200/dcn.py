@@ -46,17 +46,26 @@ def dcn_v2_conv(input, offset, mask, weight, bias, stride=1, padding=1, dilation
     dg = int(deformable_groups)
     if tuple(offset.shape) != (B, 2 * dg * kh * kw, Ho, Wo) or tuple(mask.shape) != (B, dg * kh * kw, Ho, Wo):
         raise ValueError("offset / mask shapes do not match the output size and kernel")
-    input, offset, mask, weight = (t.contiguous() for t in (input, offset, mask, weight))
+    # a channels_last input is sampled in place (its memory IS [B,H,W,Ci]); anything else is copied
+    flags = 0
+    if not input.is_contiguous() and input.is_contiguous(memory_format=torch.channels_last):
+        flags = capi.DCN_INPUT_NHWC
+    else:
+        input = input.contiguous()
+    offset, mask, weight = (t.contiguous() for t in (offset, mask, weight))
     bias = None if bias is None else bias.contiguous()
     out = torch.empty((B, Co, Ho, Wo), dtype=torch.float32, device=dev)
     lib = capi.lib()
-    wsb = int(lib.smplb200_dcn_v2_workspace_bytes(Ci, Co))
-    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+    wsb = int(lib.smplb200_dcn_v2_workspace_bytes(B, Ci, H, W, Co, flags))
+    if wsb == 0:
+        raise RuntimeError("dcn_v2_conv (B200): unsupported shape (needs 3x3, Ci % 32 == 0, Co % 16 == 0, Co <= 256)")
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     capi.check(lib.smplb200_dcn_v2_forward(
         idx, input.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
         offset.data_ptr(), mask.data_ptr(), B, Ci, H, W, Co, kh, kw, sh, sw, ph, pw, dh, dw, dg,
-        out.data_ptr(), ws.data_ptr(), wsb, torch.cuda.current_stream(dev).cuda_stream), "smplb200_dcn_v2_forward")
+        out.data_ptr(), ws.data_ptr(), wsb, flags, torch.cuda.current_stream(dev).cuda_stream),
+        "smplb200_dcn_v2_forward")
     return out
 
 

@@ -221,16 +221,21 @@ int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int
  * Built for what the reference network uses (reference src/lib/models/model.py:355: 3x3, one
  * deformable group): kernel 3x3, deformable_group 1, Ci a multiple of 32, Co a multiple of 16 and
  * <= 256; any stride / padding / dilation.  Anything else returns SMPLB200_ERR_UNSUPPORTED.
- * `workspace`: smplb200_dcn_v2_workspace_bytes(ci, co) of 256-byte aligned device scratch (the
- * re-tiled bf16 weight image, rebuilt every call because weights are trainable parameters).        */
-size_t smplb200_dcn_v2_workspace_bytes(int32_t channels_in, int32_t channels_out);
+ * `flags`: 0, or SMPLB200_DCN_INPUT_NHWC when `input` is already channels-last ([B,H,W,Ci], e.g. a
+ * torch.channels_last tensor): the kernel samples a channels-last view (one contiguous 128-byte line
+ * per neighbour and 32 channels) and otherwise makes that copy itself.
+ * `workspace`: smplb200_dcn_v2_workspace_bytes(...) of 256-byte aligned device scratch (the re-tiled
+ * bf16 weight image, rebuilt every call because weights are trainable, + the channels-last copy).   */
+#define SMPLB200_DCN_INPUT_NHWC 1u
+size_t smplb200_dcn_v2_workspace_bytes(int32_t batch, int32_t channels_in, int32_t height, int32_t width,
+                                       int32_t channels_out, uint32_t flags);
 int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* weight, const float* bias,
                             const float* offset, const float* mask, int32_t batch, int32_t channels_in,
                             int32_t height, int32_t width, int32_t channels_out,
                             int32_t kernel_h, int32_t kernel_w, int32_t stride_h, int32_t stride_w,
                             int32_t pad_h, int32_t pad_w, int32_t dilation_h, int32_t dilation_w,
                             int32_t deformable_group, float* output,
-                            void* workspace, size_t workspace_bytes, void* stream);
+                            void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------- */
 const char* smplb200_strerror(int status);

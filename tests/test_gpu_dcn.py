@@ -103,6 +103,17 @@ def test_reference_known_answer_and_plain_convolution(dev):
     close(got, torch.nn.functional.conv2d(x.double(), w2.double(), b2.double(), padding=1), "plain conv")
 
 
+def test_channels_last_input_is_sampled_in_place(dev):
+    x, w, b, off, m = rand_case(2, 64, 32, 10, 9, 2.0, 21)
+    ref = dcn_v2_forward(x, w, b, off, m, dtype=torch.float64)
+    xd = x.to(dev)
+    with torch.no_grad():
+        a = dcn_v2_conv(xd, off.to(dev), m.to(dev), w.to(dev), b.to(dev))
+        c = dcn_v2_conv(xd.contiguous(memory_format=torch.channels_last), off.to(dev), m.to(dev), w.to(dev), b.to(dev))
+    close(a, ref, "NCHW input")
+    assert torch.equal(a, c), "the channels-last path must give the same bits"
+
+
 def test_modules(dev):
     torch.manual_seed(11)
     layer = DCN(64, 32, kernel_size=(3, 3), stride=1, padding=1, dilation=1, deformable_groups=1).to(dev)
@@ -124,13 +135,14 @@ def test_modules(dev):
 
 def test_errors_and_unsupported(dev):
     lib = capi.lib()
-    assert lib.smplb200_dcn_v2_workspace_bytes(48, 32) == 0          # Ci not a multiple of 32
-    assert lib.smplb200_dcn_v2_workspace_bytes(64, 512) == 0         # Co > 256
+    assert lib.smplb200_dcn_v2_workspace_bytes(1, 48, 4, 4, 32, 0) == 0          # Ci not a multiple of 32
+    assert lib.smplb200_dcn_v2_workspace_bytes(1, 64, 4, 4, 512, 0) == 0         # Co > 256
+    assert lib.smplb200_dcn_v2_workspace_bytes(2, 64, 8, 8, 32, 0) > lib.smplb200_dcn_v2_workspace_bytes(2, 64, 8, 8, 32, 1)
     z = lambda *s: torch.zeros(*s, device=dev)
     x, w, off, m, out = z(1, 32, 4, 4), z(16, 32, 3, 3), z(1, 18, 4, 4), z(1, 9, 4, 4), z(1, 16, 4, 4)
-    ws = torch.empty(lib.smplb200_dcn_v2_workspace_bytes(32, 16), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.smplb200_dcn_v2_workspace_bytes(1, 32, 4, 4, 16, 0), dtype=torch.uint8, device=dev)
     args = lambda dg, wsp, wsn: (0, x.data_ptr(), w.data_ptr(), None, off.data_ptr(), m.data_ptr(), 1, 32, 4, 4, 16,
-                                  3, 3, 1, 1, 1, 1, 1, 1, dg, out.data_ptr(), wsp, wsn, None)
+                                  3, 3, 1, 1, 1, 1, 1, 1, dg, out.data_ptr(), wsp, wsn, 0, None)
     assert lib.smplb200_dcn_v2_forward(*args(2, ws.data_ptr(), ws.numel())) == 2      # deformable groups
     assert lib.smplb200_dcn_v2_forward(*args(1, None, 0)) == 3                        # workspace
     assert lib.smplb200_dcn_v2_forward(*args(1, ws.data_ptr(), ws.numel())) == 0
