@@ -28,9 +28,9 @@
 //   * epilogue: thread = pixel reads its Co accumulators, adds the bias, and each warp store covers 32
 //     adjacent pixels of one output channel (128 bytes, coalesced) in the NCHW output.
 //
-// Warp roles (448 threads): warp 0 = bulk-TMA producer of the weight tiles, warp 1 = MMA issuer
-// (warp-uniform, one elected lane), warps 2..13 = three groups of four loader warps (TMEM lane
-// quarter = warp % 4; group g takes K-steps i = g mod 3); warps 2..5 run the epilogue.
+// Warp roles (576 threads): warp 0 = bulk-TMA producer of the weight tiles, warp 1 = MMA issuer
+// (warp-uniform, one elected lane), warps 2..17 = four groups of four loader warps (TMEM lane
+// quarter = warp % 4; group g takes K-steps i = g mod 4); warps 2..5 run the epilogue.
 #pragma once
 #include "common.cuh"
 #include "k_chain.cuh"
@@ -38,8 +38,8 @@
 
 namespace smplb200 {
 
-constexpr int kDcnGroups = 3;
-constexpr int kDcnThreads = (2 + 4 * kDcnGroups) * 32;      // 448
+constexpr int kDcnGroups = 4;
+constexpr int kDcnThreads = (2 + 4 * kDcnGroups) * 32;      // 576
 constexpr int kDcnTaps = 9;
 constexpr int kDcnTapVals = 9;                               // 4 offsets, 4 weights, mask
 constexpr int kDcnStagesB = 3;
@@ -236,26 +236,36 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
       const int t = i / steps_per_tap, cb = (i - t * steps_per_tap) * 32;
       const float* tvb = sTap + (size_t)t * kDcnTapVals * 128 + q * 32;
       const float* cbase = input + cb + 4 * sub;
-      // ---- 8 rounds: pixel pw = 4*rd + pq of this warp, channels cb + 4*sub .. +3
+      // ---- 8 rounds: pixel pw = 4*rd + pq of this warp, channels cb + 4*sub .. +3.  The rounds run in
+      // two batches of four: all 16 line loads of a batch are issued before the first blend, so four
+      // rounds of L1/L2 latency overlap (the kernel is latency-bound: ncu long_scoreboard on top).
 #pragma unroll
-      for (int rd = 0; rd < 8; ++rd) {
-        const int pw = 4 * rd + pq;
-        const float* tv = tvb + pw;
-        const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
-                  o3 = __float_as_int(tv[384]);
-        const float w0 = tv[512], w1 = tv[640], w2 = tv[768], w3 = tv[896], mk = tv[1024];
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 v0 = o0 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o0 * s.Ci)) : z;
-        const float4 v1 = o1 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o1 * s.Ci)) : z;
-        const float4 v2 = o2 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o2 * s.Ci)) : z;
-        const float4 v3 = o3 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o3 * s.Ci)) : z;
-        // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
-        float4 r4;
-        r4.x = (w0 * v0.x + w1 * v1.x + w2 * v2.x + w3 * v3.x) * mk;
-        r4.y = (w0 * v0.y + w1 * v1.y + w2 * v2.y + w3 * v3.y) * mk;
-        r4.z = (w0 * v0.z + w1 * v1.z + w2 * v2.z + w3 * v3.z) * mk;
-        r4.w = (w0 * v0.w + w1 * v1.w + w2 * v2.w + w3 * v3.w) * mk;
-        *reinterpret_cast<float4*>(tile + pw * kDcnTileStride + 4 * sub) = r4;
+      for (int half = 0; half < 2; ++half) {
+        float4 v[4][4];
+        float wv[4][5];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* tv = tvb + 4 * (4 * half + u) + pq;
+          const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
+                    o3 = __float_as_int(tv[384]);
+          wv[u][0] = tv[512]; wv[u][1] = tv[640]; wv[u][2] = tv[768]; wv[u][3] = tv[896]; wv[u][4] = tv[1024];
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u][0] = o0 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o0 * s.Ci)) : z;
+          v[u][1] = o1 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o1 * s.Ci)) : z;
+          v[u][2] = o2 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o2 * s.Ci)) : z;
+          v[u][3] = o3 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o3 * s.Ci)) : z;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pw = 4 * (4 * half + u) + pq;
+          // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
+          float4 r4;
+          r4.x = (wv[u][0] * v[u][0].x + wv[u][1] * v[u][1].x + wv[u][2] * v[u][2].x + wv[u][3] * v[u][3].x) * wv[u][4];
+          r4.y = (wv[u][0] * v[u][0].y + wv[u][1] * v[u][1].y + wv[u][2] * v[u][2].y + wv[u][3] * v[u][3].y) * wv[u][4];
+          r4.z = (wv[u][0] * v[u][0].z + wv[u][1] * v[u][1].z + wv[u][2] * v[u][2].z + wv[u][3] * v[u][3].z) * wv[u][4];
+          r4.w = (wv[u][0] * v[u][0].w + wv[u][1] * v[u][1].w + wv[u][2] * v[u][2].w + wv[u][3] * v[u][3].w) * wv[u][4];
+          *reinterpret_cast<float4*>(tile + pw * kDcnTileStride + 4 * sub) = r4;
+        }
       }
       __syncwarp();
       // ---- transpose: lane = pixel reads its 32 channels

@@ -62,7 +62,11 @@ def main():
                 torch.cuda.synchronize()
                 continue
             us = timed(lambda: dcn_v2_conv(x, off, m, w, b), a.iters)
-            row = {"layer": f"{Ci}->{Co} @ {H}x{W}", "count_in_network": cnt, "batch": B, "ours_us": round(us, 1)}
+            xcl = x.contiguous(memory_format=torch.channels_last)
+            us_cl = timed(lambda: dcn_v2_conv(xcl, off, m, w, b), a.iters)
+            row = {"layer": f"{Ci}->{Co} @ {H}x{W}", "count_in_network": cnt, "batch": B, "ours_us": round(us, 1),
+                   "ours_channels_last_input_us": round(us_cl, 1)}
+            tot_cl = globals().setdefault("_tot_cl", [0.0]); tot_cl[0] += cnt * us_cl
             flops = 2.0 * B * H * W * Co * Ci * 9
             bytes_ = 4.0 * (B * Ci * H * W + 27 * B * H * W + B * Co * H * W)
             row["tflops_fp32_equivalent"] = round(flops / us * 1e-6, 1)
@@ -79,7 +83,8 @@ def main():
             print(json.dumps(row), flush=True)
     if a.once:
         return
-    out = {"network_total_16_layers_us": round(tot_ours, 1), "torchvision_cuda_total_us": round(tot_tv, 1) if tot_tv else None}
+    out = {"network_total_16_layers_us": round(tot_ours, 1),
+           "network_total_channels_last_input_us": round(globals().get("_tot_cl", [0.0])[0], 1), "torchvision_cuda_total_us": round(tot_tv, 1) if tot_tv else None}
     # CPU port on a bounded sample: one image of the 64->64 @128x128 layer
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle.dcn_ref import dcn_v2_forward
