@@ -71,3 +71,26 @@ def test_dcn_module_forward_with_zero_initialised_offset_conv():
     got = dcn_forward(x, torch.zeros(27, 4, 3, 3), torch.zeros(27), w, b)
     ref = 0.5 * torch.nn.functional.conv2d(x, w, None, padding=1) + b.view(1, 3, 1, 1)
     assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_vs_torchvision_random_configurations():
+    """Random small shapes / strides / paddings / dilations / groups / offset scales (seeded)."""
+    rng = torch.Generator().manual_seed(2026)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=rng))
+    for _ in range(12):
+        dg = ri(1, 2)
+        B, Ci, Co = ri(1, 2), dg * ri(1, 3), ri(1, 5)
+        H, W = ri(3, 9), ri(3, 9)
+        stride, padding, dilation = ri(1, 2), ri(0, 2), ri(1, 2)
+        Ho = (H + 2 * padding - (dilation * 2 + 1)) // stride + 1
+        Wo = (W + 2 * padding - (dilation * 2 + 1)) // stride + 1
+        if Ho < 1 or Wo < 1:
+            continue
+        x = torch.randn(B, Ci, H, W, generator=rng, dtype=torch.float64)
+        w = torch.randn(Co, Ci, 3, 3, generator=rng, dtype=torch.float64)
+        b = torch.randn(Co, generator=rng, dtype=torch.float64)
+        off = torch.randn(B, dg * 18, Ho, Wo, generator=rng, dtype=torch.float64) * float(ri(0, 6))
+        m = torch.rand(B, dg * 9, Ho, Wo, generator=rng, dtype=torch.float64)
+        ref = deform_conv2d(x, off, w, b, stride=stride, padding=padding, dilation=dilation, mask=m)
+        got = dcn_v2_forward(x, w, b, off, m, stride, padding, dilation, dg, dtype=torch.float64)
+        assert torch.allclose(got, ref, rtol=1e-11, atol=1e-11), (B, Ci, Co, H, W, stride, padding, dilation, dg)
