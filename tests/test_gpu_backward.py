@@ -236,6 +236,40 @@ def test_training_style_loss(dev, models):
     assert_grads((tb.grad, tp.grad, tc.grad), (rb.grad, rp.grad, rc.grad), "training loss")
 
 
+def test_backward_full_size_properties(dev, models):
+    """BASELINE.json's batch (4096 bodies, tcgen05 everywhere): size-independent properties of the
+    gradient map, plus the float64 oracle on a slice of the batch."""
+    m = models["sparse"]
+    n = 4096
+    b, p, c = synthetic.make_inputs(n, 61)
+    layer = SMPL(m).to(dev)
+    g = torch.Generator().manual_seed(9)
+    uv, uj, uk = (torch.randn(n, d0, d1, generator=g).to(dev) for d0, d1 in ((6890, 3), (24, 3), (24, 2)))
+
+    def grads(scale_v, scale_j, scale_k):
+        tb, tp, tc = (torch.from_numpy(x).to(dev).requires_grad_() for x in (b, p, c))
+        v, j, k = layer(tb, tp, tc)
+        torch.autograd.backward([v, j, k], [uv * scale_v, uj * scale_j, uk * scale_k])
+        torch.cuda.synchronize()
+        return tb.grad, tp.grad, tc.grad
+
+    g1 = grads(1.0, 1.0, 1.0)
+    assert all(torch.isfinite(t).all() for t in g1)
+    # homogeneity: scaling every upstream gradient by a power of two scales every sum exactly
+    g2 = grads(2.0, 2.0, 2.0)
+    assert all(torch.equal(2.0 * a, b_) for a, b_ in zip(g1, g2))
+    # additivity over the outputs: g(v) + g(j) + g(k) == g(v, j, k) up to fp32 rounding
+    gv, gj, gk = grads(1.0, 0.0, 0.0), grads(0.0, 1.0, 0.0), grads(0.0, 0.0, 1.0)
+    for a, x, y, z in zip(g1, gv, gj, gk):
+        assert (a - (x + y + z)).abs().max().item() <= 1e-5 * a.abs().max().item()
+    # zero upstream -> zero gradient
+    assert all(t.abs().max().item() == 0.0 for t in grads(0.0, 0.0, 0.0))
+    # the oracle on the first 48 bodies (gradients are per body)
+    k_ = 48
+    ref = oracle_grads(m, b[:k_], p[:k_], c[:k_], [uv[:k_].cpu().numpy(), uj[:k_].cpu().numpy(), uk[:k_].cpu().numpy()])
+    assert_grads(tuple(t[:k_] for t in g1), ref, "N=4096, first 48 bodies")
+
+
 def test_train_step_is_cuda_graph_capturable(dev, models):
     """forward + loss + backward captured once and replayed: no host sync, no allocation outside the
     graph's pool, no stream-unsafe call anywhere in smplb200_forward / smplb200_backward."""
