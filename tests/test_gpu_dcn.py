@@ -103,6 +103,28 @@ def test_reference_known_answer_and_plain_convolution(dev):
     close(got, torch.nn.functional.conv2d(x.double(), w2.double(), b2.double(), padding=1), "plain conv")
 
 
+def test_network_layer_shape_and_linearity(dev):
+    """The network's largest DeformConv (64 -> 64 @ 128x128): oracle parity on a 2-image batch and the
+    size-independent properties of the operator: exact homogeneity in the input and in the mask (powers
+    of two), additivity in the input up to rounding, bias-only output for a zero mask."""
+    x, w, b, off, m = rand_case(2, 64, 64, 128, 128, 2.0, 77)
+    ref = dcn_v2_forward(x, w, b, off, m, dtype=torch.float64)
+    xd, wd, bd, od, md = (t.to(dev) for t in (x, w, b, off, m))
+    zb = torch.zeros_like(bd)
+    with torch.no_grad():
+        y = dcn_v2_conv(xd, od, md, wd, bd)
+        close(y, ref, "64->64 @128x128")
+        y0 = dcn_v2_conv(xd, od, md, wd, zb)
+        assert torch.equal(dcn_v2_conv(2.0 * xd, od, md, wd, zb), 2.0 * y0)
+        assert torch.equal(dcn_v2_conv(xd, od, 0.5 * md, wd, zb), 0.5 * y0)
+        x2 = torch.randn_like(xd)
+        ya = dcn_v2_conv(xd + x2, od, md, wd, zb)
+        yb = y0 + dcn_v2_conv(x2, od, md, wd, zb)
+        assert (ya - yb).abs().max().item() <= 1e-4 * ya.abs().max().item()
+        only_bias = dcn_v2_conv(xd, od, torch.zeros_like(md), wd, bd)
+        assert torch.equal(only_bias, bd.view(1, -1, 1, 1).expand_as(only_bias))
+
+
 def test_channels_last_input_is_sampled_in_place(dev):
     x, w, b, off, m = rand_case(2, 64, 32, 10, 9, 2.0, 21)
     ref = dcn_v2_forward(x, w, b, off, m, dtype=torch.float64)
