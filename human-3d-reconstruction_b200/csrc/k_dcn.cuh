@@ -28,9 +28,11 @@
 //   * epilogue: thread = pixel reads its Co accumulators, adds the bias, and each warp store covers 32
 //     adjacent pixels of one output channel (128 bytes, coalesced) in the NCHW output.
 //
-// Warp roles (576 threads): warp 0 = bulk-TMA producer of the weight tiles, warp 1 = MMA issuer
-// (warp-uniform, one elected lane), warps 2..17 = four groups of four loader warps (TMEM lane
-// quarter = warp % 4; group g takes K-steps i = g mod 4); warps 2..5 run the epilogue.
+// Warp roles (576 threads, persistent over tiles): warp 0 = bulk-TMA producer of the weight tiles,
+// warp 1 = MMA issuer (warp-uniform, one elected lane), warps 2..13 = three groups of four loader
+// warps (TMEM lane quarter = warp % 4; group g takes K-steps i = g mod 3), warps 14..17 = auxiliary
+// group: sampling geometry of the next tile (double-buffered table) and epilogue of the current one
+// (double-buffered accumulator when Co <= 128).
 #pragma once
 #include "common.cuh"
 #include "k_chain.cuh"
@@ -38,11 +40,12 @@
 
 namespace smplb200 {
 
-constexpr int kDcnGroups = 4;
-constexpr int kDcnThreads = (2 + 4 * kDcnGroups) * 32;      // 576
+constexpr int kDcnLoadGroups = 3;                            // loader groups of four warps: warps 2..13
+constexpr int kDcnAuxWarp0 = 2 + 4 * kDcnLoadGroups;         // warps 14..17: tap tables + epilogue
+constexpr int kDcnThreads = (kDcnAuxWarp0 + 4) * 32;         // 576
 constexpr int kDcnTaps = 9;
 constexpr int kDcnTapVals = 9;                               // 4 offsets, 4 weights, mask
-constexpr int kDcnStagesB = 3;
+constexpr int kDcnMaxStagesB = 3;                            // weight-tile ring (2 stages when Co > 128)
 constexpr int kDcnStagesA = 8;                               // 32 TMEM columns each (16 hi | 16 lo)
 constexpr int kDcnACol0 = 256;
 constexpr int kDcnMaxCo = 256;
@@ -63,8 +66,10 @@ constexpr int kDcnTileW = 16, kDcnTileH = 8;
 inline uint32_t dcn_stage_bytes(int Co) { return 128u * (uint32_t)Co; }     // [hi|lo][4 chunks][Co][8 bf16]
 constexpr int kDcnTileStride = 36;                           // floats per pixel row of a warp's transpose tile
 constexpr uint32_t kDcnTileBytes = 32 * kDcnTileStride * 4;   // 4,608 per loader warp
+inline int dcn_stages_b(int Co) { return Co > 128 ? 2 : kDcnMaxStagesB; }
 inline size_t dcn_smem_bytes(int Co) {
-  return (size_t)kDcnStagesB * dcn_stage_bytes(Co) + kDcnTapBytes + (size_t)4 * kDcnGroups * kDcnTileBytes + 512;
+  return (size_t)dcn_stages_b(Co) * dcn_stage_bytes(Co) + 2 * (size_t)kDcnTapBytes +
+         (size_t)4 * kDcnLoadGroups * kDcnTileBytes + 512;
 }
 inline size_t dcn_weight_image_bytes(int Ci, int Co) { return (size_t)kDcnTaps * (Ci / 32) * dcn_stage_bytes(Co); }
 
@@ -111,33 +116,46 @@ k_dcn_pack_w(const float* __restrict__ w, int Co, int Ci, uint16_t* __restrict__
   img[base + part] = lo;
 }
 
+// Persistent, warp-specialised: a CTA loops over output tiles (tile = blockIdx.x + n * gridDim.x);
+// the sampling geometry of tile n+1 and the epilogue of tile n are done by a dedicated auxiliary
+// warp group while the loader groups and the tensor pipe are already on tile n+1, so the per-tile
+// prologue / epilogue of the first (one CTA per tile) version -- ~20 % of its warp time sat at the
+// final barrier (ncu) -- overlaps the main loop, and TMEM / barriers are set up once per SM.
 __global__ void __launch_bounds__(kDcnThreads, 1)
-k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ offset, const float* __restrict__ mask,
-          const uint8_t* __restrict__ wimg, const float* __restrict__ bias, DcnShape s, uint32_t idesc,
-          float* __restrict__ output) {
+k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ offset,
+          const float* __restrict__ mask, const uint8_t* __restrict__ wimg, const float* __restrict__ bias,
+          DcnShape s, uint32_t idesc, int ntiles, int nstB, float* __restrict__ output) {
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t stage_bytes = 128u * (uint32_t)s.Co;
   uint8_t* sB = smem;
-  float* sTap = reinterpret_cast<float*>(smem + kDcnStagesB * stage_bytes);    // [tap][val][128]
-  float* sTile = reinterpret_cast<float*>(smem + kDcnStagesB * stage_bytes + kDcnTapBytes);   // per loader warp
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDcnStagesB * stage_bytes + kDcnTapBytes +
-                                               4 * kDcnGroups * kDcnTileBytes);
+  float* sTap = reinterpret_cast<float*>(smem + (size_t)nstB * stage_bytes);            // [2][tap][val][128]
+  float* sTile = reinterpret_cast<float*>(smem + (size_t)nstB * stage_bytes + 2 * kDcnTapBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nstB * stage_bytes + 2 * kDcnTapBytes +
+                                               4 * kDcnLoadGroups * kDcnTileBytes);
   uint64_t* b_full = bars;
-  uint64_t* b_empty = b_full + kDcnStagesB;
-  uint64_t* a_full = b_empty + kDcnStagesB;
+  uint64_t* b_empty = b_full + kDcnMaxStagesB;
+  uint64_t* a_full = b_empty + kDcnMaxStagesB;
   uint64_t* a_empty = a_full + kDcnStagesA;
-  uint64_t* d_full = a_empty + kDcnStagesA;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+  uint64_t* tap_full = a_empty + kDcnStagesA;     // [2] aux -> loaders
+  uint64_t* tap_empty = tap_full + 2;             // [2] loaders -> aux
+  uint64_t* d_full = tap_empty + 2;               // [2] MMA -> aux
+  uint64_t* d_empty = d_full + 2;                 // [2] aux -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int steps_per_tap = s.Ci / 32;
   const int nks = kDcnTaps * steps_per_tap;
   const long long HoWo = (long long)s.Ho * s.Wo;
+  const bool dbl = s.Co <= 128;                    // two accumulators fit next to the 8 A stages
+  const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kDcnStagesB; ++i) { ptx::mbar_init(b_full + i, 1); ptx::mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < kDcnMaxStagesB; ++i) { ptx::mbar_init(b_full + i, 1); ptx::mbar_init(b_empty + i, 1); }
     for (int i = 0; i < kDcnStagesA; ++i) { ptx::mbar_init(a_full + i, 4); ptx::mbar_init(a_empty + i, 1); }
-    ptx::mbar_init(d_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tap_full + i, 4); ptx::mbar_init(tap_empty + i, 4 * kDcnLoadGroups);
+      ptx::mbar_init(d_full + i, 1); ptx::mbar_init(d_empty + i, 4);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
@@ -147,164 +165,205 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== bulk-TMA producer: one weight tile (hi | lo) per K-step =====
+    // ===== bulk-TMA producer: one weight tile (hi | lo) per K-step, re-streamed (from L2) per tile =====
     if (lane == 0) {
-      for (int i = 0; i < nks; ++i) {
-        const int st = i % kDcnStagesB;
-        ptx::mbar_wait(b_empty + st, ((i / kDcnStagesB) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(b_full + st, stage_bytes);
-        ptx::bulk_g2s(sB + (size_t)st * stage_bytes, wimg + (size_t)i * stage_bytes, stage_bytes, b_full + st);
-      }
+      long long gi = 0;
+      for (int n = 0; n < my_tiles; ++n)
+        for (int i = 0; i < nks; ++i, ++gi) {
+          const int st = (int)(gi % nstB);
+          ptx::mbar_wait(b_empty + st, (uint32_t)((gi / nstB) & 1) ^ 1u);
+          ptx::mbar_arrive_expect_tx(b_full + st, stage_bytes);
+          ptx::bulk_g2s(sB + (size_t)st * stage_bytes, wimg + (size_t)i * stage_bytes, stage_bytes, b_full + st);
+        }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t lbo = (uint32_t)s.Co * 16u, part = 4u * lbo;
-    for (int i = 0; i < nks; ++i) {
-      const int sb = i % kDcnStagesB, sa = i % kDcnStagesA;
-      ptx::mbar_wait(b_full + sb, (i / kDcnStagesB) & 1);
-      ptx::mbar_wait(a_full + sa, (i / kDcnStagesA) & 1);
-      ptx::tc_fence_after();
-      const uint32_t b_addr = ptx::smem_u32(sB + (size_t)sb * stage_bytes);
-      const uint32_t a_addr = tmem_base + kDcnACol0 + sa * 32;
-      if (ptx::elect_one()) {
+    long long gi = 0;
+    for (int n = 0; n < my_tiles; ++n) {
+      const int db = dbl ? (n & 1) : 0;
+      const int use = dbl ? (n >> 1) : n;                      // how often this accumulator was used before
+      ptx::mbar_wait(d_empty + db, (uint32_t)(use & 1) ^ 1u);
+      const uint32_t d_addr = tmem_base + db * 128;
+      for (int i = 0; i < nks; ++i, ++gi) {
+        const int sb = (int)(gi % nstB), sa = (int)(gi % kDcnStagesA);
+        ptx::mbar_wait(b_full + sb, (uint32_t)((gi / nstB) & 1));
+        ptx::mbar_wait(a_full + sa, (uint32_t)((gi / kDcnStagesA) & 1));
+        ptx::tc_fence_after();
+        const uint32_t b_addr = ptx::smem_u32(sB + (size_t)sb * stage_bytes);
+        const uint32_t a_addr = tmem_base + kDcnACol0 + sa * 32;
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int g = 0; g < 3; ++g) {          // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo)
-          const uint32_t ap = a_addr + (g == 1 ? 16 : 0);
-          const uint32_t bp = b_addr + (g == 2 ? part : 0);
+          for (int g = 0; g < 3; ++g) {          // (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo)
+            const uint32_t ap = a_addr + (g == 1 ? 16 : 0);
+            const uint32_t bp = b_addr + (g == 2 ? part : 0);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const uint64_t bd = ptx::make_smem_desc(bp + kk * 2 * lbo, lbo, 128);
-            ptx::mma_bf16_ts(tmem_base, ap + kk * 8, bd, idesc, (uint32_t)((i | g | kk) != 0));
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint64_t bd = ptx::make_smem_desc(bp + kk * 2 * lbo, lbo, 128);
+              ptx::mma_bf16_ts(d_addr, ap + kk * 8, bd, idesc, (uint32_t)((i | g | kk) != 0));
+            }
+          }
+          ptx::tc_commit(b_empty + sb);
+          ptx::tc_commit(a_empty + sa);
+          if (i == nks - 1) ptx::tc_commit(d_full + db);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < kDcnAuxWarp0) {
+    // ===== loaders: 8 lanes fetch one neighbour line, transpose so that lane = pixel, write TMEM =====
+    const int lw = warp - 2, q = warp & 3, grp = lw >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float* tile = sTile + (size_t)lw * (32 * kDcnTileStride);
+    const int sub = lane & 7, pq = lane >> 3;             // 8 lanes per pixel, 4 pixels per round
+    long long gbase = 0;
+    for (int n = 0; n < my_tiles; ++n, gbase += nks) {
+      const int tb = n & 1;
+      ptx::mbar_wait(tap_full + tb, (uint32_t)((n >> 1) & 1));
+      const float* tap0 = sTap + (size_t)tb * (kDcnTapBytes / 4);
+      for (int i = grp; i < nks; i += kDcnLoadGroups) {
+        const long long gi = gbase + i;
+        const int t = i / steps_per_tap, cb = (i - t * steps_per_tap) * 32;
+        const float* tvb = tap0 + (size_t)t * kDcnTapVals * 128 + q * 32;
+        const float* cbase = input + cb + 4 * sub;
+        // 8 rounds (pixel pw = 4*rd + pq, channels cb + 4*sub .. +3) in two batches of four: all 16
+        // line loads of a batch are issued before the first blend, so four rounds of latency overlap
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 v[4][4];
+          float wv[4][5];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* tv = tvb + 4 * (4 * half + u) + pq;
+            const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
+                      o3 = __float_as_int(tv[384]);
+            wv[u][0] = tv[512]; wv[u][1] = tv[640]; wv[u][2] = tv[768]; wv[u][3] = tv[896]; wv[u][4] = tv[1024];
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            v[u][0] = o0 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o0 * s.Ci)) : z;
+            v[u][1] = o1 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o1 * s.Ci)) : z;
+            v[u][2] = o2 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o2 * s.Ci)) : z;
+            v[u][3] = o3 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o3 * s.Ci)) : z;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int pw = 4 * (4 * half + u) + pq;
+            // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
+            float4 r4;
+            r4.x = (wv[u][0] * v[u][0].x + wv[u][1] * v[u][1].x + wv[u][2] * v[u][2].x + wv[u][3] * v[u][3].x) * wv[u][4];
+            r4.y = (wv[u][0] * v[u][0].y + wv[u][1] * v[u][1].y + wv[u][2] * v[u][2].y + wv[u][3] * v[u][3].y) * wv[u][4];
+            r4.z = (wv[u][0] * v[u][0].z + wv[u][1] * v[u][1].z + wv[u][2] * v[u][2].z + wv[u][3] * v[u][3].z) * wv[u][4];
+            r4.w = (wv[u][0] * v[u][0].w + wv[u][1] * v[u][1].w + wv[u][2] * v[u][2].w + wv[u][3] * v[u][3].w) * wv[u][4];
+            *reinterpret_cast<float4*>(tile + pw * kDcnTileStride + 4 * sub) = r4;
           }
         }
-        ptx::tc_commit(b_empty + sb);
-        ptx::tc_commit(a_empty + sa);
-        if (i == nks - 1) ptx::tc_commit(d_full);
+        __syncwarp();
+        float val[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 x = *reinterpret_cast<const float4*>(tile + lane * kDcnTileStride + 4 * k);
+          val[4 * k] = x.x; val[4 * k + 1] = x.y; val[4 * k + 2] = x.z; val[4 * k + 3] = x.w;
+        }
+        __syncwarp();
+        const int sa = (int)(gi % kDcnStagesA);
+        ptx::mbar_wait(a_empty + sa, (uint32_t)((gi / kDcnStagesA) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const uint16_t h0 = f32_to_bf16_rn(val[2 * u]), h1 = f32_to_bf16_rn(val[2 * u + 1]);
+          hi[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          lo[u] = (uint32_t)f32_to_bf16_rn(val[2 * u] - bf16_to_f32(h0)) |
+                  ((uint32_t)f32_to_bf16_rn(val[2 * u + 1] - bf16_to_f32(h1)) << 16);
+        }
+        const uint32_t acol = tmem_base + lane_addr + kDcnACol0 + sa * 32;
+        ptx::tmem_st16(acol, hi);
+        ptx::tmem_st16(acol + 16, lo);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_full + sa);
+        __syncwarp();
       }
       __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tap_empty + tb);      // this warp is done with the tile's tap table
     }
   } else {
-    // ===== loaders: thread = output pixel =====
-    const int lw = warp - 2, q = warp & 3, grp = lw >> 2;
+    // ===== auxiliary group: sampling geometry of the NEXT tile, epilogue of the CURRENT one =====
+    const int q = warp & 3;
     const int px = q * 32 + lane;                         // pixel within the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int tiles_per_img = s.tiles_x * s.tiles_y;
-    const long long b = blockIdx.x / tiles_per_img;
-    const int tix = (int)(blockIdx.x - b * tiles_per_img);
-    const int ho = (tix / s.tiles_x) * kDcnTileH + px / kDcnTileW, wo = (tix % s.tiles_x) * kDcnTileW + px % kDcnTileW;
-    const bool valid = ho < s.Ho && wo < s.Wo;
-    const int r = valid ? ho * s.Wo + wo : 0;
-
-    // --- sampling geometry of this pixel, taps t = grp, grp + 3, grp + 6 (each group a third)
-    for (int t = grp; t < kDcnTaps; t += kDcnGroups) {
-      float* dst = sTap + (size_t)t * kDcnTapVals * 128 + px;
-      int o[4] = {-1, -1, -1, -1};        // -1: neighbour outside the map (contributes exactly 0)
-      float wgt[4] = {0.f, 0.f, 0.f, 0.f};
-      float mk = 0.f;
-      if (valid) {
-        const int i = t / 3, j = t - 3 * i;
-        const float* offp = offset + ((size_t)b * 2 * kDcnTaps + 2 * t) * HoWo + r;
-        const float off_h = __ldg(offp), off_w = __ldg(offp + HoWo);
-        const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + off_h;
-        const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + off_w;
-        if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {
-          mk = __ldg(mask + ((size_t)b * kDcnTaps + t) * HoWo + r);
-          const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-          const int h_high = h_low + 1, w_high = w_low + 1;
-          const float lh = h_im - (float)h_low, lwd = w_im - (float)w_low;
-          const float hh = 1.f - lh, hw = 1.f - lwd;
-          const bool t0 = h_low >= 0, t1 = h_high <= s.H - 1, l0 = w_low >= 0, l1 = w_high <= s.W - 1;
-          const int img0 = (int)b * s.H * s.W;        // NHWC pixel index of the image's first pixel
-          if (t0 && l0) { o[0] = img0 + h_low * s.W + w_low; wgt[0] = hh * hw; }
-          if (t0 && l1) { o[1] = img0 + h_low * s.W + w_high; wgt[1] = hh * lwd; }
-          if (t1 && l0) { o[2] = img0 + h_high * s.W + w_low; wgt[2] = lh * hw; }
-          if (t1 && l1) { o[3] = img0 + h_high * s.W + w_high; wgt[3] = lh * lwd; }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        dst[u * 128] = __int_as_float(o[u]);
-        dst[(4 + u) * 128] = wgt[u];
-      }
-      dst[8 * 128] = mk;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(4 * kDcnGroups * 32) : "memory");   // loader warps only
-
-    float* tile = sTile + (size_t)lw * (32 * kDcnTileStride);
-    const int sub = lane & 7, pq = lane >> 3;             // 8 lanes per pixel, 4 pixels per round
-    for (int i = grp; i < nks; i += kDcnGroups) {
-      const int t = i / steps_per_tap, cb = (i - t * steps_per_tap) * 32;
-      const float* tvb = sTap + (size_t)t * kDcnTapVals * 128 + q * 32;
-      const float* cbase = input + cb + 4 * sub;
-      // ---- 8 rounds: pixel pw = 4*rd + pq of this warp, channels cb + 4*sub .. +3.  The rounds run in
-      // two batches of four: all 16 line loads of a batch are issued before the first blend, so four
-      // rounds of L1/L2 latency overlap (the kernel is latency-bound: ncu long_scoreboard on top).
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float4 v[4][4];
-        float wv[4][5];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float* tv = tvb + 4 * (4 * half + u) + pq;
-          const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
-                    o3 = __float_as_int(tv[384]);
-          wv[u][0] = tv[512]; wv[u][1] = tv[640]; wv[u][2] = tv[768]; wv[u][3] = tv[896]; wv[u][4] = tv[1024];
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          v[u][0] = o0 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o0 * s.Ci)) : z;
-          v[u][1] = o1 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o1 * s.Ci)) : z;
-          v[u][2] = o2 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o2 * s.Ci)) : z;
-          v[u][3] = o3 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o3 * s.Ci)) : z;
+    auto pixel_of = [&](int tile, long long& b, int& ho, int& wo) -> bool {
+      b = tile / tiles_per_img;
+      const int tix = tile - (int)b * tiles_per_img;
+      ho = (tix / s.tiles_x) * kDcnTileH + px / kDcnTileW;
+      wo = (tix % s.tiles_x) * kDcnTileW + px % kDcnTileW;
+      return ho < s.Ho && wo < s.Wo;
+    };
+    auto compute_taps = [&](int tile, float* tab) {
+      long long b; int ho, wo;
+      const bool valid = pixel_of(tile, b, ho, wo);
+      const int r = valid ? ho * s.Wo + wo : 0;
+#pragma unroll 3
+      for (int t = 0; t < kDcnTaps; ++t) {
+        float* dst = tab + (size_t)t * kDcnTapVals * 128 + px;
+        int o[4] = {-1, -1, -1, -1};        // -1: neighbour outside the map (contributes exactly 0)
+        float wgt[4] = {0.f, 0.f, 0.f, 0.f};
+        float mk = 0.f;
+        if (valid) {
+          const int i = t / 3, j = t - 3 * i;
+          const float* offp = offset + ((size_t)b * 2 * kDcnTaps + 2 * t) * HoWo + r;
+          const float off_h = __ldg(offp), off_w = __ldg(offp + HoWo);
+          const float h_im = (float)(ho * s.sh - s.ph + i * s.dh) + off_h;
+          const float w_im = (float)(wo * s.sw - s.pw + j * s.dw) + off_w;
+          if (h_im > -1.f && w_im > -1.f && h_im < (float)s.H && w_im < (float)s.W) {
+            mk = __ldg(mask + ((size_t)b * kDcnTaps + t) * HoWo + r);
+            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+            const int h_high = h_low + 1, w_high = w_low + 1;
+            const float lh = h_im - (float)h_low, lwd = w_im - (float)w_low;
+            const float hh = 1.f - lh, hw = 1.f - lwd;
+            const bool t0 = h_low >= 0, t1 = h_high <= s.H - 1, l0 = w_low >= 0, l1 = w_high <= s.W - 1;
+            const int img0 = (int)b * s.H * s.W;        // NHWC pixel index of the image's first pixel
+            if (t0 && l0) { o[0] = img0 + h_low * s.W + w_low; wgt[0] = hh * hw; }
+            if (t0 && l1) { o[1] = img0 + h_low * s.W + w_high; wgt[1] = hh * lwd; }
+            if (t1 && l0) { o[2] = img0 + h_high * s.W + w_low; wgt[2] = lh * hw; }
+            if (t1 && l1) { o[3] = img0 + h_high * s.W + w_high; wgt[3] = lh * lwd; }
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int pw = 4 * (4 * half + u) + pq;
-          // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
-          float4 r4;
-          r4.x = (wv[u][0] * v[u][0].x + wv[u][1] * v[u][1].x + wv[u][2] * v[u][2].x + wv[u][3] * v[u][3].x) * wv[u][4];
-          r4.y = (wv[u][0] * v[u][0].y + wv[u][1] * v[u][1].y + wv[u][2] * v[u][2].y + wv[u][3] * v[u][3].y) * wv[u][4];
-          r4.z = (wv[u][0] * v[u][0].z + wv[u][1] * v[u][1].z + wv[u][2] * v[u][2].z + wv[u][3] * v[u][3].z) * wv[u][4];
-          r4.w = (wv[u][0] * v[u][0].w + wv[u][1] * v[u][1].w + wv[u][2] * v[u][2].w + wv[u][3] * v[u][3].w) * wv[u][4];
-          *reinterpret_cast<float4*>(tile + pw * kDcnTileStride + 4 * sub) = r4;
+          dst[u * 128] = __int_as_float(o[u]);
+          dst[(4 + u) * 128] = wgt[u];
         }
+        dst[8 * 128] = mk;
       }
+    };
+    if (my_tiles > 0) {
+      compute_taps((int)blockIdx.x, sTap);
       __syncwarp();
-      // ---- transpose: lane = pixel reads its 32 channels
-      float val[32];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 x = *reinterpret_cast<const float4*>(tile + lane * kDcnTileStride + 4 * k);
-        val[4 * k] = x.x; val[4 * k + 1] = x.y; val[4 * k + 2] = x.z; val[4 * k + 3] = x.w;
-      }
-      __syncwarp();
-      const int sa = i % kDcnStagesA;
-      ptx::mbar_wait(a_empty + sa, ((i / kDcnStagesA) & 1) ^ 1);
-      ptx::tc_fence_after();
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const uint16_t h0 = f32_to_bf16_rn(val[2 * u]), h1 = f32_to_bf16_rn(val[2 * u + 1]);
-        hi[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-        lo[u] = (uint32_t)f32_to_bf16_rn(val[2 * u] - bf16_to_f32(h0)) |
-                ((uint32_t)f32_to_bf16_rn(val[2 * u + 1] - bf16_to_f32(h1)) << 16);
-      }
-      const uint32_t acol = tmem_base + lane_addr + kDcnACol0 + sa * 32;
-      ptx::tmem_st16(acol, hi);
-      ptx::tmem_st16(acol + 16, lo);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_full + sa);
-      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tap_full + 0);
     }
-    if (lw < 4) {
-      // ===== epilogue: D[pixel, co] + bias -> output[b, co, ho, wo] =====
-      ptx::mbar_wait(d_full, 0);
+    for (int n = 0; n < my_tiles; ++n) {
+      const int tile = (int)blockIdx.x + n * (int)gridDim.x;
+      if (n + 1 < my_tiles) {
+        const int nb = (n + 1) & 1;
+        ptx::mbar_wait(tap_empty + nb, (uint32_t)(((n + 1) >> 1) & 1) ^ 1u);    // loaders left that buffer
+        compute_taps(tile + (int)gridDim.x, sTap + (size_t)nb * (kDcnTapBytes / 4));
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tap_full + nb);
+      }
+      // epilogue: D[pixel, co] + bias -> output[b, co, ho, wo]
+      const int db = dbl ? (n & 1) : 0;
+      const int use = dbl ? (n >> 1) : n;
+      long long b; int ho, wo;
+      const bool valid = pixel_of(tile, b, ho, wo);
+      ptx::mbar_wait(d_full + db, (uint32_t)(use & 1));
       ptx::tc_fence_after();
-      float* dst = output + (size_t)b * s.Co * HoWo + r;
+      float* dst = output + (size_t)b * s.Co * HoWo + (valid ? ho * s.Wo + wo : 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < s.Co; c0 += 16) {
         uint32_t d[16];
-        ptx::tmem_ld16(tmem_base + lane_addr + c0, d);
+        ptx::tmem_ld16(tmem_base + lane_addr + db * 128 + c0, d);
         ptx::tmem_ld_wait();
         if (valid) {
 #pragma unroll
@@ -312,6 +371,9 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
             dst[(size_t)(c0 + u) * HoWo] = __uint_as_float(d[u]) + (bias ? __ldg(bias + c0 + u) : 0.f);
         }
       }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(d_empty + db);
     }
   }
   ptx::tc_fence_before();

@@ -1021,8 +1021,11 @@ int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* wei
   const long long ctas = (long long)batch * sh.tiles_x * sh.tiles_y;
   if (ctas >= (1LL << 31)) return SMPLB200_ERR_UNSUPPORTED;
   const uint32_t idesc = ptx::make_idesc(ptx::kFmtBF16, 128, (uint32_t)channels_out);
-  k_dcn_fwd<<<(unsigned)ctas, kDcnThreads, smem, s>>>(
-      nhwc, offset, mask, ws, bias, sh, idesc, output);
+  int num_sms = 0;
+  CU_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  const unsigned grid = (unsigned)std::min<long long>(ctas, num_sms);      // persistent: one CTA per SM
+  k_dcn_fwd<<<grid, kDcnThreads, smem, s>>>(
+      nhwc, offset, mask, ws, bias, sh, idesc, (int)ctas, dcn_stages_b(channels_out), output);
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }
