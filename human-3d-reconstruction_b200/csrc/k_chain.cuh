@@ -64,6 +64,12 @@ __device__ __forceinline__ uint16_t f32_to_bf16_rn(float x) {
   return r;
 }
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(uint32_t(h) << 16); }
+// two floats -> packed bf16x2 (lo element in the low half), one instruction
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2_rn(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
 constexpr int kCoefBlock = 128;   // bodies per tensor-core coefficient image (MMA N)
 constexpr int kLbsBlock = 8;     // bodies per LBS blend image (MMA N = 12 * 8 = 96)

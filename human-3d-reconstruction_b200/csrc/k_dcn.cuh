@@ -18,9 +18,9 @@
 //     makes 8 rounds of 4 pixels x 8 lanes, blends the 4 neighbours with the tap's weights, applies
 //     the mask, transposes the 32 x 32 values through a private shared-memory tile so that lane =
 //     pixel, splits them into bf16 hi + lo and writes its TMEM lanes with tcgen05.st.
-//   * per pixel and tap the sampling geometry (4 plane offsets, 4 bilinear weights with the border
-//     rules folded in, mask) is computed ONCE into shared memory ([tap][value][pixel], conflict free)
-//     and reused for all Ci channels.
+//   * per pixel and tap the sampling geometry (4 pixel offsets, 4 bilinear weights with the border
+//     rules and the modulation mask folded in) is computed ONCE into shared memory ([tap][pixel][8],
+//     read back as two LDS.128) and reused for all Ci channels.
 //   * B (the weights) is re-tiled on the device before the launch (k_dcn_pack_w) into K-major bf16
 //     hi | lo tiles with K ordered tap-major (k' = tap * Ci + ci), one bulk-TMA copy per K-step.
 //   * split-bf16 (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM): ~2^-16 relative, i.e. fp32-class
@@ -44,12 +44,12 @@ constexpr int kDcnLoadGroups = 3;                            // loader groups of
 constexpr int kDcnAuxWarp0 = 2 + 4 * kDcnLoadGroups;         // warps 14..17: tap tables + epilogue
 constexpr int kDcnThreads = (kDcnAuxWarp0 + 4) * 32;         // 576
 constexpr int kDcnTaps = 9;
-constexpr int kDcnTapVals = 9;                               // 4 offsets, 4 weights, mask
+constexpr int kDcnTapVals = 8;                               // 4 offsets, 4 (bilinear weight x mask): 2 float4 per (tap, pixel)
 constexpr int kDcnMaxStagesB = 3;                            // weight-tile ring (2 stages when Co > 128)
 constexpr int kDcnStagesA = 8;                               // 32 TMEM columns each (16 hi | 16 lo)
 constexpr int kDcnACol0 = 256;
 constexpr int kDcnMaxCo = 256;
-constexpr uint32_t kDcnTapBytes = kDcnTaps * kDcnTapVals * 128 * 4;   // 41,472
+constexpr uint32_t kDcnTapBytes = kDcnTaps * kDcnTapVals * 128 * 4;   // 36,864
 
 struct DcnShape {
   int B, Ci, H, W, Co, Ho, Wo;
@@ -128,7 +128,7 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t stage_bytes = 128u * (uint32_t)s.Co;
   uint8_t* sB = smem;
-  float* sTap = reinterpret_cast<float*>(smem + (size_t)nstB * stage_bytes);            // [2][tap][val][128]
+  float* sTap = reinterpret_cast<float*>(smem + (size_t)nstB * stage_bytes);            // [2][tap][128 px][8]
   float* sTile = reinterpret_cast<float*>(smem + (size_t)nstB * stage_bytes + 2 * kDcnTapBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nstB * stage_bytes + 2 * kDcnTapBytes +
                                                4 * kDcnLoadGroups * kDcnTileBytes);
@@ -224,20 +224,21 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
       for (int i = grp; i < nks; i += kDcnLoadGroups) {
         const long long gi = gbase + i;
         const int t = i / steps_per_tap, cb = (i - t * steps_per_tap) * 32;
-        const float* tvb = tap0 + (size_t)t * kDcnTapVals * 128 + q * 32;
+        const float4* tvb = reinterpret_cast<const float4*>(tap0 + ((size_t)t * 128 + q * 32) * kDcnTapVals);
         const float* cbase = input + cb + 4 * sub;
         // 8 rounds (pixel pw = 4*rd + pq, channels cb + 4*sub .. +3) in two batches of four: all 16
         // line loads of a batch are issued before the first blend, so four rounds of latency overlap
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float4 v[4][4];
-          float wv[4][5];
+          float wv[4][4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float* tv = tvb + 4 * (4 * half + u) + pq;
-            const int o0 = __float_as_int(tv[0]), o1 = __float_as_int(tv[128]), o2 = __float_as_int(tv[256]),
-                      o3 = __float_as_int(tv[384]);
-            wv[u][0] = tv[512]; wv[u][1] = tv[640]; wv[u][2] = tv[768]; wv[u][3] = tv[896]; wv[u][4] = tv[1024];
+            const float4* tv = tvb + (4 * (4 * half + u) + pq) * 2;       // this round's pixel: 2 x LDS.128
+            const float4 to = tv[0], tw = tv[1];
+            const int o0 = __float_as_int(to.x), o1 = __float_as_int(to.y), o2 = __float_as_int(to.z),
+                      o3 = __float_as_int(to.w);
+            wv[u][0] = tw.x; wv[u][1] = tw.y; wv[u][2] = tw.z; wv[u][3] = tw.w;
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             v[u][0] = o0 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o0 * s.Ci)) : z;
             v[u][1] = o1 >= 0 ? __ldg(reinterpret_cast<const float4*>(cbase + (size_t)o1 * s.Ci)) : z;
@@ -247,12 +248,12 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int pw = 4 * (4 * half + u) + pq;
-            // reference order: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
+            // sum_i (w_i * mask) * v_i : the modulation mask is folded into the four bilinear weights
             float4 r4;
-            r4.x = (wv[u][0] * v[u][0].x + wv[u][1] * v[u][1].x + wv[u][2] * v[u][2].x + wv[u][3] * v[u][3].x) * wv[u][4];
-            r4.y = (wv[u][0] * v[u][0].y + wv[u][1] * v[u][1].y + wv[u][2] * v[u][2].y + wv[u][3] * v[u][3].y) * wv[u][4];
-            r4.z = (wv[u][0] * v[u][0].z + wv[u][1] * v[u][1].z + wv[u][2] * v[u][2].z + wv[u][3] * v[u][3].z) * wv[u][4];
-            r4.w = (wv[u][0] * v[u][0].w + wv[u][1] * v[u][1].w + wv[u][2] * v[u][2].w + wv[u][3] * v[u][3].w) * wv[u][4];
+            r4.x = wv[u][0] * v[u][0].x + wv[u][1] * v[u][1].x + wv[u][2] * v[u][2].x + wv[u][3] * v[u][3].x;
+            r4.y = wv[u][0] * v[u][0].y + wv[u][1] * v[u][1].y + wv[u][2] * v[u][2].y + wv[u][3] * v[u][3].y;
+            r4.z = wv[u][0] * v[u][0].z + wv[u][1] * v[u][1].z + wv[u][2] * v[u][2].z + wv[u][3] * v[u][3].z;
+            r4.w = wv[u][0] * v[u][0].w + wv[u][1] * v[u][1].w + wv[u][2] * v[u][2].w + wv[u][3] * v[u][3].w;
             *reinterpret_cast<float4*>(tile + pw * kDcnTileStride + 4 * sub) = r4;
           }
         }
@@ -269,11 +270,10 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
         ptx::tc_fence_after();
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const uint16_t h0 = f32_to_bf16_rn(val[2 * u]), h1 = f32_to_bf16_rn(val[2 * u + 1]);
-          hi[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-          lo[u] = (uint32_t)f32_to_bf16_rn(val[2 * u] - bf16_to_f32(h0)) |
-                  ((uint32_t)f32_to_bf16_rn(val[2 * u + 1] - bf16_to_f32(h1)) << 16);
+        for (int u = 0; u < 16; ++u) {      // one packed cvt per pair; residuals from the packed hi word
+          hi[u] = f32x2_to_bf16x2_rn(val[2 * u], val[2 * u + 1]);
+          lo[u] = f32x2_to_bf16x2_rn(val[2 * u] - __uint_as_float(hi[u] << 16),
+                                     val[2 * u + 1] - __uint_as_float(hi[u] & 0xffff0000u));
         }
         const uint32_t acol = tmem_base + lane_addr + kDcnACol0 + sa * 32;
         ptx::tmem_st16(acol, hi);
@@ -306,7 +306,7 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
       const int r = valid ? ho * s.Wo + wo : 0;
 #pragma unroll 3
       for (int t = 0; t < kDcnTaps; ++t) {
-        float* dst = tab + (size_t)t * kDcnTapVals * 128 + px;
+        float4* dst = reinterpret_cast<float4*>(tab + ((size_t)t * 128 + px) * kDcnTapVals);
         int o[4] = {-1, -1, -1, -1};        // -1: neighbour outside the map (contributes exactly 0)
         float wgt[4] = {0.f, 0.f, 0.f, 0.f};
         float mk = 0.f;
@@ -330,12 +330,8 @@ k_dcn_fwd(const float* __restrict__ input /* NHWC */, const float* __restrict__ 
             if (t1 && l1) { o[3] = img0 + h_high * s.W + w_high; wgt[3] = lh * lwd; }
           }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          dst[u * 128] = __int_as_float(o[u]);
-          dst[(4 + u) * 128] = wgt[u];
-        }
-        dst[8 * 128] = mk;
+        dst[0] = make_float4(__int_as_float(o[0]), __int_as_float(o[1]), __int_as_float(o[2]), __int_as_float(o[3]));
+        dst[1] = make_float4(wgt[0] * mk, wgt[1] * mk, wgt[2] * mk, wgt[3] * mk);
       }
     };
     if (my_tiles > 0) {
