@@ -68,7 +68,7 @@ k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, Deco
   __shared__ uint32_t s_key[kDecMaxK];
   __shared__ int s_idx[kDecMaxK];
   __shared__ int s_rank_idx[kDecMaxK];
-  __shared__ uint32_t s_prefix, s_need, s_count, s_eq_base;
+  __shared__ uint32_t s_prefix, s_need, s_count, s_eq_base, s_eq_total;
   __shared__ uint32_t s_warp_sum[kDecThreads / 32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hw = H * W, M = C * hw;
@@ -107,15 +107,36 @@ k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, Deco
       }
     }
     __syncthreads();
-    if (tid == 0) {   // walk the bins from the top until the running count covers `need`
-      uint32_t need = s_need, above = 0;
-      int d = (int)masks[pass];
-      for (; d > 0; --d) {
-        if (above + s_hist[d] >= need) break;
-        above += s_hist[d];
+    {
+      // Find the highest bin d whose suffix count (bins >= d) covers `need`: a block-wide scan from
+      // the top, four bins per thread.  (A single thread walking up to 2047 bins of dependent
+      // shared-memory loads cost ~60 K clk per pass -- most of the kernel's first version.)
+      const uint32_t need = s_need;
+      const int top = 2047 - 4 * tid;                       // this thread: bins top .. top-3
+      const uint32_t h0 = s_hist[top], h1 = s_hist[top - 1], h2 = s_hist[top - 2], h3 = s_hist[top - 3];
+      const uint32_t v = h0 + h1 + h2 + h3;
+      uint32_t inc = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += nb;
       }
-      s_need = need - above;
-      s_prefix = prefix | ((uint32_t)d << shifts[pass]);
+      __syncthreads();                                      // everyone has read s_need / s_hist
+      if (lane == 31) s_warp_sum[warp] = inc;
+      __syncthreads();
+      uint32_t warp_excl = 0;
+      for (int w = 0; w < warp; ++w) warp_excl += s_warp_sum[w];
+      const uint32_t above = inc - v + warp_excl;           // elements in bins strictly above `top`
+      if (above < need && above + v >= need) {              // the cut falls inside this thread's bins
+        uint32_t a = above;
+        int d = top;
+        if (a + h0 < need) { a += h0; d = top - 1;
+          if (a + h1 < need) { a += h1; d = top - 2;
+            if (a + h2 < need) { a += h2; d = top - 3; } } }
+        s_need = need - a;
+        s_prefix = prefix | ((uint32_t)d << shifts[pass]);
+        s_eq_total = d == top ? h0 : (d == top - 1 ? h1 : (d == top - 2 ? h2 : h3));   // after the last pass: #(key == T)
+      }
     }
     __syncthreads();
   }
@@ -125,6 +146,18 @@ k_decode_gather(const float* __restrict__ heat, int C, int H, int W, int K, Deco
   // ---- collect: everything above T (any order), then == T in flat-index order ------------------
   if (tid == 0) { s_count = 0; s_eq_base = 0; }
   __syncthreads();
+  if (s_eq_total == need_eq) {
+    // no tie straddles the cut (the usual case for real scores): every element with key >= T is in
+    // the top K, the order of collection is irrelevant (a rank sort follows) -> no scans, no barriers
+    for (int e = tid; e < M; e += kDecThreads) {
+      const uint32_t key = key_of(e);
+      if (key >= T) {
+        const uint32_t slot = atomicAdd(&s_count, 1u);
+        s_key[slot] = key; s_idx[slot] = e;
+      }
+    }
+    __syncthreads();
+  } else
   for (int e0 = 0; e0 < M; e0 += kDecThreads) {
     const int e = e0 + tid;
     uint32_t key = 0;

@@ -47,6 +47,27 @@ def test_decode_matches_oracle(B, C, H, W, K):
         assert torch.equal(a.cpu()[untied], b[untied])
 
 
+def test_ties_at_the_cut_take_the_lowest_index_first():
+    """Heavily quantised scores: many exact ties straddle the K-th value.  The kernel's documented rule
+    (score descending, flat index ascending) is checked against a stable numpy sort; this is the
+    ordered-collect path, the tie-free fast path is covered by the golden cases."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(12)
+    B, C, H, W, K = 3, 2, 16, 24, 40
+    heat = (rng.integers(1, 5, size=(B, C, H, W)) / 4.0).astype(np.float32)     # 4 levels -> plateaus
+    head = rng.normal(size=(B, 5, H, W)).astype(np.float32)
+    scores, inds, clses, ys, xs, (g,) = decode_gather(torch.from_numpy(heat).to(dev), [torch.from_numpy(head).to(dev)], K)
+    th = torch.from_numpy(heat)
+    keep = (torch.nn.functional.max_pool2d(th, 3, stride=1, padding=1) == th).float()
+    nms = (th * keep).reshape(B, -1).numpy()
+    for b in range(B):
+        order = np.lexsort((np.arange(nms.shape[1]), -nms[b]))[:K]              # score desc, index asc
+        np.testing.assert_array_equal(scores[b].cpu().numpy(), nms[b][order])
+        np.testing.assert_array_equal(clses[b].cpu().numpy(), order // (H * W))
+        np.testing.assert_array_equal(inds[b].cpu().numpy(), order % (H * W))
+        np.testing.assert_array_equal(g[b].cpu().numpy(), head[b].reshape(5, -1)[:, order % (H * W)].T)
+
+
 def test_decode_feeds_smpl_layer():
     """configs[4] shape: batch 32 images, K = 32 people -> 1024 bodies through the SMPL kernels."""
     dev = torch.device("cuda:0")
