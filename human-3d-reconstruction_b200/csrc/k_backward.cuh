@@ -241,6 +241,189 @@ k_lbs_bwd(DeviceModel m, LbsBwdArgs a, long long n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// kb3, default (the body fits shared memory): the two halves of the skinning backward run as two
+// DECOUPLED warp groups of one persistent CTA, each looping over the CTA's bodies at its own pace:
+//   group P1 (warps 0..11)   g_vposed = T_R^T g_v, thread = vertex, reads g_v straight from global;
+//                            needs no staging at all, only the 24 transforms of the body;
+//   group P2 (warps 12..23)  g_A[j] = sum_v w_vj g_v (x) [vposed_v, 1] from the bulk-TMA-staged copy
+//                            of g_v and vposed (warp w reduces joints w and w + 12).
+// The groups never synchronise with each other (named barriers 1 and 2), so P1's global-load
+// latency overlaps P2's shared-memory gathers and the staging wait.  In the first version all 24
+// warps ran stage -> phase 1 -> phase 2 in lock step (ncu: long_scoreboard + barrier stalls on top,
+// LSU pipe 63 %, issue 43 %).
+// ---------------------------------------------------------------------------------------------
+constexpr int kLbsBwdGroupThreads = kLbsBwdThreads / 2;   // 384
+
+__global__ void __launch_bounds__(kLbsBwdThreads, 1)
+k_lbs_bwd_split(DeviceModel m, LbsBwdArgs a, long long n) {
+  extern __shared__ __align__(128) float smem_bw[];
+  __shared__ float s_At[12 * kJ];          // P1: transforms, transposed [entry][joint] (conflict-free gathers)
+  __shared__ float s_gj1[kJ * 3], s_gj2[kJ * 3];   // regressed joints: gradient flowing into the vertices
+  __shared__ __align__(8) uint64_t s_bar;
+  float* s_vp = smem_bw;                   // [3][VP]
+  float* s_gbuf = smem_bw + 3 * m.VP;      // 16-byte aligned landing zone of the g_v slab
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = m.V, VP = m.VP;
+  if (tid == 0) { ptx::mbar_init(&s_bar, 1); ptx::fence_barrier_init(); }
+  __syncthreads();
+
+  // effective joint gradient that flows into the VERTICES (regressed joints only): g_joints + s * g_kp2d
+  auto joint_term = [&](long long b, int i) -> float {
+    const int j = i / 3, c = i - 3 * j;
+    float v = 0.f;
+    if (a.g_joints) v = __ldg(a.g_joints + (size_t)b * (kJ * 3) + i);
+    if (a.g_kp2d && c < 2) v = fmaf(__ldg(a.cam + (size_t)b * 3), __ldg(a.g_kp2d + (size_t)b * (kJ * 2) + 2 * j + c), v);
+    return v;
+  };
+  auto add_regressed = [&](const float* gj, int v, float g[3]) {      // g_v += J_regressor[v,:] . g_joint
+    const float* jr = m.dense_jreg + (size_t)v * kJ;
+    for (int j = 0; j < kJ; ++j) {
+      const float r = __ldg(jr + j);
+      if (r != 0.f) {
+        g[0] = fmaf(r, gj[3 * j], g[0]); g[1] = fmaf(r, gj[3 * j + 1], g[1]); g[2] = fmaf(r, gj[3 * j + 2], g[2]);
+      }
+    }
+  };
+
+  if (warp < kLbsBwdGroupThreads / 32) {
+    // ===================== group P1 =====================
+    for (long long b = blockIdx.x; b < n; b += gridDim.x) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kLbsBwdGroupThreads) : "memory");     // previous body's table reads done
+      if (tid < kJ * 12) {
+        const int j = tid / 12, e = tid - 12 * j;
+        s_At[e * kJ + j] = __ldg(a.A + (size_t)b * (kJ * 12) + tid);
+      } else if (a.regressed && tid < kJ * 12 + kJ * 3) {
+        s_gj1[tid - kJ * 12] = joint_term(b, tid - kJ * 12);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kLbsBwdGroupThreads) : "memory");
+      const float* gv = a.g_verts ? a.g_verts + (size_t)b * V * 3 : nullptr;
+#pragma unroll 3
+      for (int v = tid; v < VP; v += kLbsBwdGroupThreads) {
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        if (v < V) {
+          float g[3];
+          g[0] = gv ? __ldg(gv + 3 * v) : 0.f; g[1] = gv ? __ldg(gv + 3 * v + 1) : 0.f;
+          g[2] = gv ? __ldg(gv + 3 * v + 2) : 0.f;
+          if (a.regressed) add_regressed(s_gj1, v, g);
+          float T[9];
+#pragma unroll
+          for (int e = 0; e < 9; ++e) T[e] = 0.f;
+          if (m.max_nnz <= 4) {
+            const float4 w4 = __ldg(m.ell_w + v);
+            const uint32_t jj = __ldg(m.ell_j + v);
+            const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const float* Aj = s_At + ((jj >> (8 * s)) & 0xffu);
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[3 * r + c] = fmaf(ws[s], Aj[(4 * r + c) * kJ], T[3 * r + c]);
+            }
+          } else {
+            const float* wr = m.dense_w + (size_t)v * kJ;
+            for (int j = 0; j < kJ; ++j) {
+              const float w = __ldg(wr + j);
+              if (w == 0.f) continue;
+              const float* Aj = s_At + j;
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[3 * r + c] = fmaf(w, Aj[(4 * r + c) * kJ], T[3 * r + c]);
+            }
+          }
+          o0 = fmaf(T[6], g[2], fmaf(T[3], g[1], T[0] * g[0]));
+          o1 = fmaf(T[7], g[2], fmaf(T[4], g[1], T[1] * g[0]));
+          o2 = fmaf(T[8], g[2], fmaf(T[5], g[1], T[2] * g[0]));
+        }
+        float* dst = a.g_vposed + (size_t)b * 3 * VP + v;
+        dst[0] = o0; dst[VP] = o1; dst[2 * (size_t)VP] = o2;
+      }
+    }
+  } else {
+    // ===================== group P2 =====================
+    const int t2 = tid - kLbsBwdGroupThreads, w2 = warp - kLbsBwdGroupThreads / 32;
+    uint32_t phase = 0;
+    for (long long b = blockIdx.x; b < n; b += gridDim.x) {
+      asm volatile("bar.sync 2, %0;" ::"n"(kLbsBwdGroupThreads) : "memory");     // previous body's gathers done
+      const float* gv = a.g_verts ? a.g_verts + (size_t)b * V * 3 : nullptr;
+      // the body's g_v slab starts at a 4-byte aligned address: copy the enclosing 16-byte granules
+      const uint32_t shift = gv ? (uint32_t)(reinterpret_cast<uintptr_t>(gv) & 15u) : 0u;
+      float* s_g = s_gbuf + shift / 4;
+      if (t2 == 0) {      // one thread stages the whole body with bulk-TMA copies
+        const uint32_t vp_bytes = 3u * (uint32_t)VP * 4u;
+        const uint32_t g_bytes = gv ? ((shift + (uint32_t)V * 12u + 15u) & ~15u) : 0u;
+        ptx::fence_proxy_async();          // the previous body's generic-proxy accesses come first
+        ptx::mbar_arrive_expect_tx(&s_bar, vp_bytes + g_bytes);
+        ptx::bulk_g2s_split(s_vp, a.vposed + (size_t)b * 3 * VP, vp_bytes, &s_bar);
+        if (gv) ptx::bulk_g2s_split(s_gbuf, reinterpret_cast<const uint8_t*>(gv) - shift, g_bytes, &s_bar);
+      }
+      if (a.regressed && t2 >= 32 && t2 < 32 + kJ * 3) s_gj2[t2 - 32] = joint_term(b, t2 - 32);
+      if (!gv)
+        for (int i = t2; i < 3 * V; i += kLbsBwdGroupThreads) s_gbuf[i] = 0.f;
+      ptx::mbar_wait(&s_bar, phase);
+      phase ^= 1;
+      if (a.regressed || !gv) {
+        asm volatile("bar.sync 2, %0;" ::"n"(kLbsBwdGroupThreads) : "memory");   // s_gj2 / zero fill visible
+        if (a.regressed) {
+          for (int v = t2; v < V; v += kLbsBwdGroupThreads) {
+            float g[3] = {s_g[3 * v], s_g[3 * v + 1], s_g[3 * v + 2]};
+            add_regressed(s_gj2, v, g);
+            s_g[3 * v] = g[0]; s_g[3 * v + 1] = g[1]; s_g[3 * v + 2] = g[2];
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(kLbsBwdGroupThreads) : "memory");
+        }
+      }
+      // g_A[j] = sum_{v in skin(j)} w_vj * g_v (x) [vposed_v, 1]: warp w2 takes joints w2 and w2 + 12
+      for (int j = w2; j < kJ; j += kLbsBwdGroupThreads / 32) {
+        const int beg = __ldg(m.wcsr_ptr + j), end = __ldg(m.wcsr_ptr + j + 1);
+        float acc[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) acc[e] = 0.f;
+        for (int i0 = beg + lane; i0 < end; i0 += 4 * 32) {
+          int vi[4]; float wi[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            const bool ok = i < end;
+            vi[u] = ok ? __ldg(m.wcsr_idx + i) : 0;
+            wi[u] = ok ? __ldg(m.wcsr_val + i) : 0.f;
+          }
+          float gg[4][3], pp[4][3];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            gg[u][0] = s_g[3 * vi[u]]; gg[u][1] = s_g[3 * vi[u] + 1]; gg[u][2] = s_g[3 * vi[u] + 2];
+            pp[u][0] = s_vp[vi[u]]; pp[u][1] = s_vp[VP + vi[u]]; pp[u][2] = s_vp[2 * VP + vi[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {     // entries in ascending order: same sum order as one-at-a-time
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const float wg = wi[u] * gg[u][r];
+              acc[4 * r] = fmaf(wg, pp[u][0], acc[4 * r]);
+              acc[4 * r + 1] = fmaf(wg, pp[u][1], acc[4 * r + 1]);
+              acc[4 * r + 2] = fmaf(wg, pp[u][2], acc[4 * r + 2]);
+              acc[4 * r + 3] += wg;
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+        }
+        if (lane < 12) {
+          float v = acc[0];
+#pragma unroll
+          for (int e = 1; e < 12; ++e) v = lane == e ? acc[e] : v;
+          a.g_A[(size_t)b * (kJ * 12) + j * 12 + lane] = v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // kb1: g_coef[b,k] = sum_col g_vposed[b,col] * basis[k,col]  (k < NB + 207; the template row has a
 // constant coefficient).  CUDA-core kernel: CTA = 16 bodies x all 224 k x one slice of the planar
 // columns; the slices' partial sums are added, in slice order, by kb2.

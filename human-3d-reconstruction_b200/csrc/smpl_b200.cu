@@ -516,7 +516,7 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     {  // backward skinning kernel: shared-memory staging when one body's g_v + vposed fit
       const size_t need = lbs_bwd_smem_bytes(V, VP);
       if (need + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {
-        e = cudaFuncSetAttribute(k_lbs_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        e = cudaFuncSetAttribute(k_lbs_bwd_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
         if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
         m->lbs_bwd_staged = true;
       }
@@ -899,7 +899,7 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
     la.g_vposed = g_vposed; la.g_A = g_A; la.regressed = p.regressed ? 1 : 0;
     const unsigned grid = (unsigned)std::min<long long>(n, 4LL * model->num_sms);
     if (model->lbs_bwd_staged)
-      k_lbs_bwd<true><<<std::min<unsigned>(grid, (unsigned)model->num_sms), kLbsBwdThreads,
+      k_lbs_bwd_split<<<std::min<unsigned>(grid, (unsigned)model->num_sms), kLbsBwdThreads,
                         lbs_bwd_smem_bytes(model->d.V, model->d.VP), s>>>(model->d, la, n);
     else
       k_lbs_bwd<false><<<grid, kLbsBwdThreads, 0, s>>>(model->d, la, n);
