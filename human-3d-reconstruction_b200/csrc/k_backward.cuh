@@ -6,8 +6,9 @@
 // Reverse of the forward kernels.  A and vposed are either recomputed (k2 + k1 run again) or, when the
 // caller kept the forward's workspace, read from it:
 //
-//   kb3  k_lbs_bwd        skinning:      g_vposed = T_R^T g_v         (thread per vertex)
-//                                        g_A[j]   = sum_v w_vj g_v (x) [vposed_v, 1]   (warp per joint)
+//   kb3  skinning:        g_vposed = T_R^T g_v  (thread per vertex),  g_A[j] = sum_v w_vj g_v (x) [vposed_v, 1]
+//        k_lbs_bwd_split  the default: both halves as decoupled warp groups of a persistent CTA;
+//        k_lbs_bwd<false> lock-step variant without shared-memory staging, for meshes that do not fit
 //   kb1  blendshapes:     g_coef = g_vposed . basis^T, split over column slices:
 //        k_blend_bwd_tc   (k_blend_bwd_tc.cuh) tcgen05, the default;
 //        k_blend_bwd_fma  (here) CUDA cores, only for an explicit precision='fp32' below 256 bodies
