@@ -949,7 +949,7 @@ int smplb200_decode_gather(int32_t device, const float* heat, int32_t batch, int
   const size_t key_bytes = (size_t)num_classes * height * width * sizeof(uint32_t);
   if (key_bytes <= 200 * 1024) {
     CU_TRY(cudaFuncSetAttribute(k_decode_gather<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)key_bytes));
+                                200 * 1024));   // the largest staged size: never lowered by a concurrent caller
     k_decode_gather<true><<<(unsigned)batch, kDecThreads, key_bytes, static_cast<cudaStream_t>(stream)>>>(
         heat, num_classes, height, width, k, dh, scores, reinterpret_cast<long long*>(inds), clses, ys, xs);
   } else {
@@ -1015,7 +1015,10 @@ int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* wei
     nhwc = xt;
   }
   const size_t smem = dcn_smem_bytes(channels_out);
-  CU_TRY(cudaFuncSetAttribute(k_dcn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // always opt in to the largest size any supported shape needs: concurrent callers with different
+  // Co must not lower each other's limit between the attribute call and the launch
+  CU_TRY(cudaFuncSetAttribute(k_dcn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)std::max(dcn_smem_bytes(kDcnMaxCo), dcn_smem_bytes(128))));
   sh.tiles_x = (sh.Wo + kDcnTileW - 1) / kDcnTileW;
   sh.tiles_y = (sh.Ho + kDcnTileH - 1) / kDcnTileH;
   const long long ctas = (long long)batch * sh.tiles_x * sh.tiles_y;
