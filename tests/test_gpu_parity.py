@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from human_3d_reconstruction_b200 import SMPL, capi, synthetic
+from human_3d_reconstruction_b200 import SMPL, capi, sharding, synthetic
 from human_3d_reconstruction_b200 import smpl as ops
 from human_3d_reconstruction_b200.smpl import HostRunner
 from oracle.smpl_ref import smpl_forward, smpl_forward_chunked
@@ -361,6 +361,28 @@ def test_full_size_vs_oracle(dev, models, big):
         check_verts(v, ref_v, precision, f"N=4096 vertices {precision}")
         assert_close(j, ref_j, what="joints")
         assert_close(k, ref_k, atol=2e-6, what="kp2d")
+
+
+def test_largest_config_is_shard_invariant(dev, models):
+    """BASELINE.json configs[3]: 65,536 bodies in one call (11 GB of outputs + scratch on one GPU) equal,
+    bit for bit, the eight 8,192-body shards an 8-GPU job would compute (SURVEY A.9 viii), and every
+    sampled body matches the oracle."""
+    n, world = 65536, 8
+    betas, pose, cam = synthetic.make_inputs(n, 65)
+    layer = SMPL(models["sparse"], precision="bf16x3", lbs="tc").to(dev)
+    tb, tp, tc = to_dev(dev, betas, pose, cam)
+    with torch.no_grad():
+        v, j, k = layer(tb, tp, tc)
+        for r in (0, 3, 7):
+            lo, hi = sharding.shard_bounds(n, world, r)
+            sv, sj, sk = layer(tb[lo:hi], tp[lo:hi], tc[lo:hi])
+            assert torch.equal(sv, v[lo:hi]) and torch.equal(sj, j[lo:hi]) and torch.equal(sk, k[lo:hi])
+            del sv, sj, sk
+    pick = np.array([0, 1, 8191, 8192, 40000, 65535])
+    rv, rj, rk = smpl_forward(models["sparse"], betas[pick], pose[pick], cam[pick])
+    check_verts(v[pick], rv, "bf16x3", "N=65536 sampled vertices")
+    assert_close(j[pick], rj, what="joints")
+    assert_close(k[pick], rk, atol=2e-6, what="kp2d")
 
 
 def test_full_size_properties(dev, models, big):
