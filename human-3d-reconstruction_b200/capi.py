@@ -25,8 +25,8 @@ JOINTS_KINEMATIC, JOINTS_REGRESSED = 0, 1 << 3
 ROTATE_BASE = 1 << 4
 LBS_AUTO, LBS_FMA, LBS_TC, LBS_DENSE = 0, 1 << 5, 2 << 5, 3 << 5
 TC_MIN_BATCH = 32        # AUTO: tcgen05 (bf16x3) blendshapes from this many bodies
-TC_LBS_MIN_BATCH = 384
-DCN_INPUT_NHWC = 1   # AUTO: tcgen05 skinning blend from this many bodies
+TC_LBS_MIN_BATCH = 384   # AUTO: tcgen05 skinning blend from this many bodies
+DCN_INPUT_NHWC = 1       # smplb200_dcn_v2_forward flag: the input tensor is already channels-last
 COEF_K = 224
 
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32,

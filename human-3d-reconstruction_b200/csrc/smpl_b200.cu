@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <utility>
 #include <vector>
@@ -46,6 +47,7 @@ thread_local int tl_last_cuda_error = 0;
 
 constexpr int kDefaultChunk = 0;
 constexpr int kDefaultK1Variant = 1;
+constexpr long long kMaxGridYBodies16 = 65535LL * 16;   // FMA kernels: 16 bodies per grid.y slot
 
 inline int cuda_fail(cudaError_t e) {
   tl_last_cuda_error = (int)e;
@@ -186,8 +188,15 @@ int launch_blend_fma(const SmplB200Model* m, const float* coef, long long n, flo
                      cudaStream_t s) {
   if (n == 0) return SMPLB200_OK;
   // same 4-way K split for every batch size (bitwise shard invariance); body tile 8 or 16
-  if (n <= 8) blend_fma_launch<8, 4>(m->d, coef, n, vposed, s);
-  else blend_fma_launch<16, 4>(m->d, coef, n, vposed, s);
+  if (n <= 8) {
+    blend_fma_launch<8, 4>(m->d, coef, n, vposed, s);
+  } else {
+    // bodies ride on grid.y (<= 65535 groups of 16): very large batches go in several launches
+    for (long long b0 = 0; b0 < n; b0 += kMaxGridYBodies16) {
+      const long long nb = std::min<long long>(kMaxGridYBodies16, n - b0);
+      blend_fma_launch<16, 4>(m->d, coef + (size_t)b0 * kCoefK, nb, vposed + (size_t)b0 * 3 * m->d.VP, s);
+    }
+  }
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }
@@ -197,13 +206,21 @@ int launch_lbs_fma(const SmplB200Model* m, bool dense, const float* vposed, cons
                    float* kp2d, cudaStream_t s) {
   if (n == 0) return SMPLB200_OK;
   const int bodies_per_cta = 16;
-  dim3 grid((unsigned)(m->d.VP / kVertTile), (unsigned)((n + bodies_per_cta - 1) / bodies_per_cta));
-  if (dense)
-    k_lbs_fma<true><<<grid, kLbsThreads, 0, s>>>(m->d, vposed, A, n, bodies_per_cta, verts,
-                                                 joints_in, cam, kp2d);
-  else
-    k_lbs_fma<false><<<grid, kLbsThreads, 0, s>>>(m->d, vposed, A, n, bodies_per_cta, verts,
-                                                  joints_in, cam, kp2d);
+  // bodies ride on grid.y (<= 65535 groups of 16): very large batches go in several launches
+  for (long long b0 = 0; b0 < n; b0 += kMaxGridYBodies16) {
+    const long long nb = std::min<long long>(kMaxGridYBodies16, n - b0);
+    dim3 grid((unsigned)(m->d.VP / kVertTile), (unsigned)((nb + bodies_per_cta - 1) / bodies_per_cta));
+    const float* vp = vposed + (size_t)b0 * 3 * m->d.VP;
+    const float* Ab = A + (size_t)b0 * kJ * 12;
+    float* vo = verts + (size_t)b0 * m->d.V * 3;
+    const float* ji = joints_in ? joints_in + (size_t)b0 * kJ * 3 : nullptr;
+    const float* cm = cam ? cam + (size_t)b0 * 3 : nullptr;
+    float* kp = kp2d ? kp2d + (size_t)b0 * kJ * 2 : nullptr;
+    if (dense)
+      k_lbs_fma<true><<<grid, kLbsThreads, 0, s>>>(m->d, vp, Ab, nb, bodies_per_cta, vo, ji, cm, kp);
+    else
+      k_lbs_fma<false><<<grid, kLbsThreads, 0, s>>>(m->d, vp, Ab, nb, bodies_per_cta, vo, ji, cm, kp);
+  }
   CU_TRY(cudaGetLastError());
   return SMPLB200_OK;
 }
@@ -477,8 +494,9 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
         wtf[(size_t)v * kLbsK + 24 + j] = lo;
       }
 
-    SmplB200Model* m = new (std::nothrow) SmplB200Model();
-    if (!m) return SMPLB200_ERR_ALLOC;
+    std::unique_ptr<SmplB200Model> mp(new (std::nothrow) SmplB200Model());   // freed on every early return / throw
+    if (!mp) return SMPLB200_ERR_ALLOC;
+    SmplB200Model* m = mp.get();
     const size_t o_basis = bb.add(basis.data(), basis.size() * 4);
     const size_t o_jt = bb.add(jt.data(), jt.size() * 4);
     const size_t o_jsd = bb.add(jsd.data(), jsd.size() * 4);
@@ -504,20 +522,26 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     const size_t o_gbbl = bb.add(gbbl.data(), gbbl.size() * 2);
 
     DeviceGuard guard(desc->device);
-    if (guard.err != cudaSuccess) { delete m; return cuda_fail(guard.err); }
+    if (guard.err != cudaSuccess) return cuda_fail(guard.err);
     cudaError_t e = cudaMalloc(&m->blob, bb.bytes.size());
-    if (e != cudaSuccess) { delete m; tl_last_cuda_error = (int)e; cudaGetLastError(); return SMPLB200_ERR_ALLOC; }
+    if (e != cudaSuccess) { m->blob = nullptr; tl_last_cuda_error = (int)e; cudaGetLastError(); return SMPLB200_ERR_ALLOC; }
     e = cudaMemcpy(m->blob, bb.bytes.data(), bb.bytes.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
+    if (e != cudaSuccess) { cudaFree(m->blob); return cuda_fail(e); }
     // opt-in shared memory sizes for the tensor-core kernels
     e = configure_tc_kernels();
-    if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
+    if (e != cudaSuccess) { cudaFree(m->blob); return cuda_fail(e); }
 
-    {  // backward skinning kernel: shared-memory staging when one body's g_v + vposed fit
+    {  // backward skinning kernel: shared-memory staging when one body's g_v + vposed fit.  The
+       // attribute belongs to the FUNCTION on the device, not to this model: always opt in to the
+       // device maximum so a second, smaller model can never lower the limit under a larger one.
       const size_t need = lbs_bwd_smem_bytes(V, VP);
-      if (need + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {
-        e = cudaFuncSetAttribute(k_lbs_bwd_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-        if (e != cudaSuccess) { cudaFree(m->blob); delete m; return cuda_fail(e); }
+      cudaFuncAttributes fa;
+      e = cudaFuncGetAttributes(&fa, k_lbs_bwd_split);
+      if (e != cudaSuccess) { cudaFree(m->blob); return cuda_fail(e); }
+      const size_t cap = (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes;
+      if (need <= cap) {
+        e = cudaFuncSetAttribute(k_lbs_bwd_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        if (e != cudaSuccess) { cudaFree(m->blob); return cuda_fail(e); }
         m->lbs_bwd_staged = true;
       }
     }
@@ -557,7 +581,7 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     d.bwd_basis_tf32_lo = reinterpret_cast<const uint32_t*>(base + o_gbl);
     d.bwd_basis_bf16_hi = reinterpret_cast<const uint16_t*>(base + o_gbbh);
     d.bwd_basis_bf16_lo = reinterpret_cast<const uint16_t*>(base + o_gbbl);
-    *out_model = m;
+    *out_model = mp.release();
     return SMPLB200_OK;
   } catch (const std::bad_alloc&) {
     return SMPLB200_ERR_ALLOC;
@@ -992,6 +1016,7 @@ int smplb200_dcn_v2_forward(int32_t device, const float* input, const float* wei
   sh.Wo = (width + 2 * pad_w - (dilation_w * (kernel_w - 1) + 1)) / stride_w + 1;
   if (sh.Ho < 1 || sh.Wo < 1) return SMPLB200_ERR_INVALID_ARG;
   if ((long long)batch * height * width >= (1LL << 31)) return SMPLB200_ERR_UNSUPPORTED;   // pixel offsets are int32
+  if (batch > 65535 && !(flags & SMPLB200_DCN_INPUT_NHWC)) return SMPLB200_ERR_UNSUPPORTED;   // layout copy: batch on grid.z
   if (batch == 0) return SMPLB200_OK;
   if (!input || !weight || !offset || !mask || !output) return SMPLB200_ERR_INVALID_ARG;
   if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))

@@ -142,6 +142,36 @@ class SMPL(nn.Module):
         self._handles = {}
         self._handles_lock = threading.Lock()
 
+    # -- packed-model cache hygiene --------------------------------------------------------------
+    # The per-device SmplB200Model is packed ONCE from the registered buffers.  Anything that can
+    # change the buffers drops the cache so the next forward re-packs: load_state_dict(), .to() /
+    # .float() / .cuda() (`_apply`), and `invalidate()` for callers that edit a buffer in place.
+    def invalidate(self):
+        """Drop the packed per-device models; the next forward re-packs them from the buffers."""
+        with self._handles_lock:
+            self._handles.clear()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
+    def __getstate__(self):
+        # copy.deepcopy / torch.save(module): device handles and the lock are per-process state
+        state = self.__dict__.copy()
+        state.pop("_handles", None)
+        state.pop("_handles_lock", None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._handles = {}
+        self._handles_lock = threading.Lock()
+
     # -- construction helpers ------------------------------------------------------------------
     @classmethod
     def synthetic(cls, seed: int = 0, weights: str = "sparse", regressor: str = "sparse", **kw):

@@ -49,3 +49,40 @@ def test_sparse_regressor_is_densified(small_model):
     off = model_io.to_official_layout(small_model)
     off["J_regressor"] = FakeSparse(off["J_regressor"])
     np.testing.assert_array_equal(model_io.from_official_layout(off)["J_regressor"], small_model["J_regressor"])
+
+
+def test_official_pickle_loads_without_chumpy_or_scipy(tmp_path, small_model):
+    """The release's .pkl holds chumpy.ch.Ch arrays and a scipy.sparse J_regressor; neither package is
+    imported by the loader (chumpy is not installed here at all)."""
+    import importlib.util
+    import sys
+    from _official_pkl import write_official_pickle
+    assert importlib.util.find_spec("chumpy") is None
+    for kind in ("fake-old-path", "scipy"):
+        path = str(tmp_path / f"basicModel_{kind}.pkl")
+        write_official_pickle(path, small_model, sparse=kind)
+        assert "chumpy" not in sys.modules and "chumpy.ch" not in sys.modules
+        got = model_io.load_model(path)
+        for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "weights"):
+            np.testing.assert_array_equal(got[k], small_model[k])
+            assert got[k].dtype == np.float32
+        assert got["parents"][0] == -1 and list(got["parents"][1:]) == list(small_model["parents"][1:])
+    layer = SMPL(path)
+    np.testing.assert_array_equal(layer.J_regressor.numpy(), small_model["J_regressor"])
+
+
+def test_model_pickle_refuses_other_globals(tmp_path):
+    """Unpickling a model file must not be able to run code: any global outside the whitelist raises."""
+    import os
+    import pytest
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    p = tmp_path / "evil.pkl"
+    with open(p, "wb") as f:
+        pickle.dump({"v_template": Evil()}, f, protocol=2)
+    with pytest.raises(pickle.UnpicklingError):
+        model_io.load_model(str(p))
+    assert not (tmp_path / "pwned").exists()
