@@ -1,0 +1,42 @@
+"""oracle/dla34_ref.py (the configs[4] producer network) vs the fixture generated from the UNMODIFIED
+reference `dla_net` (tests/golden/make_dla_golden.py: equal seeded weights, bit-identical head maps)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_dla_golden import SEED, golden_input, param_checksums   # noqa: E402
+from oracle.dla34_ref import HEADS_HMR, dla_net                    # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dla_golden_v1.npz")
+
+
+def test_seeded_init_and_head_maps_match_the_reference_fixture():
+    g = np.load(GOLDEN)
+    net = dla_net(dict(HEADS_HMR), seed=SEED).eval()
+    assert sum(p.numel() for p in net.parameters()) == int(g["num_params"][0])
+    for grp, (s, q, n) in param_checksums(net).items():
+        ref = g[f"param_{grp}"]
+        assert n == int(ref[2]), grp
+        np.testing.assert_allclose([s, q], ref[:2], rtol=1e-9, atol=1e-9, err_msg=f"seeded init of {grp}")
+    with torch.no_grad():
+        out = net(golden_input())[0]
+    for h, ch in HEADS_HMR.items():
+        ref = g[f"head_{h}"]
+        assert out[h].shape == ref.shape == (1, ch, 16, 16)
+        # same ops in the same order: equal up to the conv kernels oneDNN picks for this CPU
+        np.testing.assert_allclose(out[h].numpy(), ref, rtol=1e-4, atol=1e-6, err_msg=h)
+
+
+def test_network_shape_is_the_reference_dla34():
+    net = dla_net(dict(HEADS_HMR), seed=1)
+    from oracle.dla34_ref import DeformConv
+    necks = [m for m in net.modules() if isinstance(m, DeformConv)]
+    assert len(necks) == 16                                # 12 in dla_up + 4 in ida_up (reference model.py:365-416)
+    shapes = sorted({(m.conv.in_channels, m.conv.out_channels) for m in necks})
+    assert shapes == [(64, 64), (128, 64), (128, 128), (256, 64), (256, 128), (256, 256), (512, 256)]
+    with torch.no_grad():
+        out = net.eval()(torch.zeros(1, 3, 96, 64))[0]
+    assert out["pose"].shape == (1, 72, 24, 16) and out["hm"].shape == (1, 1, 24, 16)   # down_ratio 4
