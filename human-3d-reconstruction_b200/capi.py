@@ -50,6 +50,20 @@ class ModelDesc(C.Structure):
     ]
 
 
+class ForwardOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("joints_ready_event", C.c_void_p)]
+
+
+def forward_opts(joints_ready_event=None):
+    """SmplB200ForwardOpts for the `_opts` entry points; `joints_ready_event`: a recorded torch.cuda.Event."""
+    if joints_ready_event is None:
+        return None
+    handle = joints_ready_event.cuda_event
+    if not handle:
+        raise RuntimeError("joints_ready event has no CUDA handle yet: call event.record() once before passing it")
+    return C.byref(ForwardOpts(C.sizeof(ForwardOpts), handle))
+
+
 # every symbol include/smpl_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _u32, _sz, _int = C.c_void_p, C.c_int64, C.c_uint32, C.c_size_t, C.c_int
 SYMBOLS = {
@@ -63,6 +77,12 @@ SYMBOLS = {
     "smplb200_model_device_bytes": (_sz, [_vp]),
     "smplb200_workspace_bytes": (_sz, [_vp, _i64, _u32]),
     "smplb200_forward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _u32, _vp]),
+    "smplb200_forward_opts": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp]),
+    "smplb200_forward_host_opts": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _u32, _vp, _vp]),
+    "smplb200_host_staging_layout": (_int, [_vp, _i64, _u32, C.POINTER(_sz), C.POINTER(_sz)]),
+    "smplb200_push_rows": (_int, [C.c_int32, _vp, _vp, _i64, _i64, _vp, _vp, C.c_int32, C.c_int32, _u32, _vp, _vp]),
+    "smplb200_wait_rows": (_int, [C.c_int32, _vp, C.c_int32, _u32, _vp]),
+    "smplb200_probe_fp32_fma": (_int, [C.c_int32, C.c_int32, _vp, C.POINTER(C.c_double), _vp]),
     "smplb200_host_staging_bytes": (_sz, [_vp, _i64, _u32]),
     "smplb200_forward_host": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _u32, _vp]),
     "smplb200_padded_verts": (_i64, [_vp]),

@@ -23,6 +23,8 @@ struct ChainOut {
   uint16_t* coef_bf16_lo;
   uint32_t* coef_tf32;
   uint32_t* a_tf32;       // [n/8 blocks][12 chunks][96 rows][4] tf32 hi|lo image of A (LBS blend)
+  const float* cam;       // [n, 3] (s, tx, ty) or null
+  float* kp2d;            // [n, 24, 2] weak-perspective projection of the KINEMATIC joints (k4), or null
 };
 
 __device__ __forceinline__ void rodrigues_hmr(float tx, float ty, float tz, float R[9]) {
@@ -168,6 +170,14 @@ k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __rest
   if (active && out.joints) {
     float* jo = out.joints + (b * kJ + j) * 3;
     jo[0] = G[3]; jo[1] = G[7]; jo[2] = G[11];
+  }
+  // k4 for kinematic joints: the joints are final HERE, ~10 us into the step, so the
+  // projection (same two rounded ops as the skinning-epilogue version) and everything downstream of
+  // joints/kp2d -- the multi-GPU exchange -- need not wait for the skinning kernel.
+  if (active && out.kp2d) {
+    const float sc = __ldg(out.cam + b * 3), tx = __ldg(out.cam + b * 3 + 1), ty = __ldg(out.cam + b * 3 + 2);
+    float2* kp = reinterpret_cast<float2*>(out.kp2d + (b * kJ + j) * 2);
+    *kp = make_float2(__fmul_rn(sc, __fadd_rn(G[3], tx)), __fmul_rn(sc, __fadd_rn(G[7], ty)));
   }
   float* sa = s_A[warp];
   if (active) {

@@ -27,6 +27,7 @@
 #include "k_backward.cuh"
 #include "k_blend_bwd_tc.cuh"
 #include "k_dcn.cuh"
+#include "k_exchange.cuh"
 
 using namespace smplb200;
 
@@ -713,8 +714,25 @@ int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, i
 int smplb200_forward(const SmplB200Model* model, const float* betas, const float* pose,
                      const float* cam, int64_t n, float* vertices, float* joints, float* kp2d,
                      void* workspace, size_t workspace_bytes, uint32_t flags, void* stream) {
+  return smplb200_forward_opts(model, betas, pose, cam, n, vertices, joints, kp2d, workspace, workspace_bytes,
+                               flags, stream, nullptr);
+}
+
+int smplb200_forward_opts(const SmplB200Model* model, const float* betas, const float* pose,
+                          const float* cam, int64_t n, float* vertices, float* joints, float* kp2d,
+                          void* workspace, size_t workspace_bytes, uint32_t flags, void* stream,
+                          const SmplB200ForwardOpts* opts) {
   if (!model || n < 0) return SMPLB200_ERR_INVALID_ARG;
-  if (n == 0) return SMPLB200_OK;
+  if (opts && opts->struct_size != sizeof(SmplB200ForwardOpts)) return SMPLB200_ERR_INVALID_ARG;
+  cudaEvent_t ev_joints = opts ? static_cast<cudaEvent_t>(opts->joints_ready_event) : nullptr;
+  if (n == 0) {
+    if (ev_joints) {
+      DeviceGuard g0(model->device);
+      if (g0.err != cudaSuccess) return cuda_fail(g0.err);
+      CU_TRY(cudaEventRecord(ev_joints, static_cast<cudaStream_t>(stream)));
+    }
+    return SMPLB200_OK;
+  }
   if (!betas || !pose || !vertices) return SMPLB200_ERR_INVALID_ARG;
   if ((kp2d != nullptr) != (cam != nullptr)) return SMPLB200_ERR_INVALID_ARG;
   Plan p;
@@ -741,10 +759,14 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
   if (p.prec == SMPLB200_PREC_BF16X3) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.coef_lo);
   if (p.prec == SMPLB200_PREC_TF32) out.coef_tf32 = reinterpret_cast<uint32_t*>(ws + w.coef_tf32);
   if (p.lbs == SMPLB200_LBS_TC) out.a_tf32 = reinterpret_cast<uint32_t*>(ws + w.a_tf32);
+  // k4 for kinematic joints rides in k2 (the joints are final there); the skinning epilogue keeps its
+  // projection for the stand-alone smplb200_lbs entry point
+  if (kp2d != nullptr && !p.regressed) { out.cam = cam; out.kp2d = kp2d; }
   int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
   if (st) return st;
+  if (ev_joints && !p.regressed) CU_TRY(cudaEventRecord(ev_joints, s));   // joints + kp2d are final
 
-  const bool proj_in_lbs = (kp2d != nullptr) && !p.regressed;
+  const bool proj_in_lbs = false;
   const bool chunked = model->chunk > 0 && p.prec != SMPLB200_PREC_FP32 && p.lbs == SMPLB200_LBS_TC &&
                        n > model->chunk;
   if (chunked) {
@@ -788,6 +810,8 @@ int smplb200_forward(const SmplB200Model* model, const float* betas, const float
   }
 
   if (p.regressed && (joints || kp2d)) st = launch_regress(model, vertices, n, jbuf, cam, kp2d, s);
+  if (st) return st;
+  if (ev_joints && p.regressed) CU_TRY(cudaEventRecord(ev_joints, s));
   return st;
 }
 
@@ -1073,8 +1097,33 @@ int smplb200_forward_host(const SmplB200Model* model, const float* betas_host,
                           const float* pose_host, const float* cam_host, int64_t n,
                           float* vertices_host, float* joints_host, float* kp2d_host,
                           void* staging, size_t staging_bytes, uint32_t flags, void* stream) {
+  return smplb200_forward_host_opts(model, betas_host, pose_host, cam_host, n, vertices_host, joints_host,
+                                    kp2d_host, staging, staging_bytes, flags, stream, nullptr);
+}
+
+int smplb200_host_staging_layout(const SmplB200Model* model, int64_t n, uint32_t flags,
+                                 size_t* joints_offset, size_t* kp2d_offset) {
+  Plan p;
+  if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
+  const size_t nn = (size_t)std::max<int64_t>(n, 1);
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off = align_up(off + b, 256); return o; };
+  take(nn * model->d.NB * 4); take(nn * 3 * kJ * 4); take(nn * 3 * 4);
+  take(nn * (size_t)model->d.V * 3 * 4);
+  const size_t oj = take(nn * kJ * 3 * 4), ok = take(nn * kJ * 2 * 4);
+  if (joints_offset) *joints_offset = oj;
+  if (kp2d_offset) *kp2d_offset = ok;
+  return SMPLB200_OK;
+}
+
+int smplb200_forward_host_opts(const SmplB200Model* model, const float* betas_host,
+                               const float* pose_host, const float* cam_host, int64_t n,
+                               float* vertices_host, float* joints_host, float* kp2d_host,
+                               void* staging, size_t staging_bytes, uint32_t flags, void* stream,
+                               const SmplB200ForwardOpts* opts) {
   if (!model || n < 0) return SMPLB200_ERR_INVALID_ARG;
-  if (n == 0) return SMPLB200_OK;
+  if (n == 0) return smplb200_forward_opts(model, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                                           nullptr, 0, flags, stream, opts);
   if (!betas_host || !pose_host) return SMPLB200_ERR_INVALID_ARG;
   if (kp2d_host && !cam_host) return SMPLB200_ERR_INVALID_ARG;
   const size_t need = smplb200_host_staging_bytes(model, n, flags);
@@ -1099,8 +1148,8 @@ int smplb200_forward_host(const SmplB200Model* model, const float* betas_host,
   CU_TRY(cudaMemcpyAsync(d_pose, pose_host, nn * 3 * kJ * 4, cudaMemcpyHostToDevice, s));
   if (cam_host) CU_TRY(cudaMemcpyAsync(d_cam, cam_host, nn * 3 * 4, cudaMemcpyHostToDevice, s));
   const bool proj = cam_host != nullptr;
-  int st = smplb200_forward(model, d_betas, d_pose, proj ? d_cam : nullptr, n, d_verts, d_joints,
-                            proj ? d_kp : nullptr, ws, staging_bytes - off, flags, stream);
+  int st = smplb200_forward_opts(model, d_betas, d_pose, proj ? d_cam : nullptr, n, d_verts, d_joints,
+                                 proj ? d_kp : nullptr, ws, staging_bytes - off, flags, stream, opts);
   if (st) return st;
   if (vertices_host)
     CU_TRY(cudaMemcpyAsync(vertices_host, d_verts, nn * (size_t)model->d.V * 3 * 4, cudaMemcpyDeviceToHost, s));
@@ -1108,6 +1157,53 @@ int smplb200_forward_host(const SmplB200Model* model, const float* betas_host,
     CU_TRY(cudaMemcpyAsync(joints_host, d_joints, nn * kJ * 3 * 4, cudaMemcpyDeviceToHost, s));
   if (kp2d_host && proj)
     CU_TRY(cudaMemcpyAsync(kp2d_host, d_kp, nn * kJ * 2 * 4, cudaMemcpyDeviceToHost, s));
+  return SMPLB200_OK;
+}
+
+// ---- multi-GPU exchange of joints | kp2d rows over peer-mapped memory (k_exchange.cuh) ----------
+int smplb200_push_rows(int32_t device, const float* joints, const float* kp2d, int64_t n, int64_t row_offset,
+                       void* const* peer_buffers, void* const* peer_flags, int32_t world, int32_t rank,
+                       uint32_t epoch, void* counter, void* stream) {
+  if (world < 1 || world > kXchgMaxRanks || rank < 0 || rank >= world || n < 0 || row_offset < 0 ||
+      !peer_buffers || !peer_flags || !counter)
+    return SMPLB200_ERR_INVALID_ARG;
+  if (n > 0 && !joints) return SMPLB200_ERR_INVALID_ARG;
+  if (!aligned16(joints) || !aligned16(kp2d)) return SMPLB200_ERR_ALIGNMENT;
+  XchgPeers peers{};
+  for (int r = 0; r < world; ++r) {
+    if (!peer_buffers[r] || !peer_flags[r] || !aligned16(peer_buffers[r])) return SMPLB200_ERR_INVALID_ARG;
+    peers.buf[r] = static_cast<float*>(peer_buffers[r]);
+    peers.flags[r] = static_cast<uint32_t*>(peer_flags[r]);
+  }
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  const long long items = (long long)n * (kXchgRow / 4);
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((items + kXchgThreads - 1) / kXchgThreads, 64));
+  k_push_rows<<<grid, kXchgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      peers, world, rank, joints, kp2d, n, row_offset, epoch, static_cast<unsigned int*>(counter));
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+int smplb200_wait_rows(int32_t device, const void* my_flags, int32_t world, uint32_t epoch, void* stream) {
+  if (world < 1 || world > kXchgMaxRanks || !my_flags) return SMPLB200_ERR_INVALID_ARG;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  k_wait_rows<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(my_flags), world, epoch);
+  CU_TRY(cudaGetLastError());
+  return SMPLB200_OK;
+}
+
+int smplb200_probe_fp32_fma(int32_t device, int32_t iters, void* scratch, double* flop, void* stream) {
+  if (iters < 1 || !scratch) return SMPLB200_ERR_INVALID_ARG;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  int num_sms = 0;
+  CU_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  const unsigned grid = (unsigned)num_sms * 8u;
+  k_probe_fma<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float*>(scratch), iters, 0.999f, 1e-3f);
+  CU_TRY(cudaGetLastError());
+  if (flop) *flop = (double)grid * 256.0 * 16.0 * (double)iters;
   return SMPLB200_OK;
 }
 

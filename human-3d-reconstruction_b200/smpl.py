@@ -19,6 +19,7 @@ is one small kernel.  CUDA-only: a CPU tensor raises -- there is no CPU path in 
 """
 from __future__ import annotations
 
+import ctypes as C
 import threading
 
 import numpy as np
@@ -199,12 +200,15 @@ class SMPL(nn.Module):
         return h
 
     # -- the forward pass ------------------------------------------------------------------------
-    def forward(self, betas, pose, cam=None, *, return_kp2d=None, flags=None):
+    def forward(self, betas, pose, cam=None, *, return_kp2d=None, flags=None, joints_ready=None):
         """betas[N,NB], pose[N,72] (axis-angle), cam[N,3]=(s,tx,ty) or None.
 
         Returns (vertices[N,V,3], joints[N,24,3]) and, when ``cam`` is given, kp2d[N,24,2].
         ``return_kp2d`` (SURVEY.md §8b signature): None = follow ``cam``; True requires ``cam``;
         False drops the projection even when ``cam`` is passed.
+        ``joints_ready``: an (already once-recorded) ``torch.cuda.Event`` that the library re-records on the
+        current stream as soon as joints and kp2d are final -- right after the ~10 us chain kernel, long
+        before the vertices -- so a side stream can start exchanging them (sharding.PeerExchange).
         """
         if return_kp2d and cam is None:
             raise ValueError("return_kp2d=True needs cam[N,3]")
@@ -220,10 +224,12 @@ class SMPL(nn.Module):
             cam = _check_in("cam", cam, n, 3, device)
         flags = self.flags if flags is None else int(flags)
         if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (betas, pose, cam)):
+            if joints_ready is not None:
+                raise ValueError("joints_ready is an inference-path option (no_grad)")
             return _SMPLFunction.apply(self, flags, betas, pose, cam)
-        return self._forward_impl(betas, pose, cam, flags)
+        return self._forward_impl(betas, pose, cam, flags, joints_ready=joints_ready)
 
-    def _forward_impl(self, betas, pose, cam, flags, return_workspace=False):
+    def _forward_impl(self, betas, pose, cam, flags, return_workspace=False, joints_ready=None):
         device, n = betas.device, int(betas.shape[0])
         h = self.handle(device)
         verts = torch.empty((n, self.num_verts, 3), dtype=torch.float32, device=device)
@@ -235,9 +241,12 @@ class SMPL(nn.Module):
             if ws_bytes == 0:
                 raise RuntimeError("smplb200_workspace_bytes rejected the flag combination")
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
-            capi.check(capi.lib().smplb200_forward(
+            capi.check(capi.lib().smplb200_forward_opts(
                 h.ptr, _ptr(betas), _ptr(pose), _ptr(cam), n, _ptr(verts), _ptr(joints), _ptr(kp2d),
-                _ptr(ws), ws_bytes, flags, _stream_ptr(device)), "smplb200_forward")
+                _ptr(ws), ws_bytes, flags, _stream_ptr(device), capi.forward_opts(joints_ready)),
+                "smplb200_forward")
+        elif joints_ready is not None:
+            joints_ready.record(torch.cuda.current_stream(device))
         outs = (verts, joints) if cam is None else (verts, joints, kp2d)
         return outs + (ws,) if return_workspace else outs
 
@@ -303,6 +312,13 @@ class HostRunner:
         self.staging_bytes = self.h.host_staging_bytes(n, smpl.flags)
         with torch.cuda.device(self.device):
             self.staging = torch.empty(self.staging_bytes, dtype=torch.uint8, device=self.device)
+        # device copies of the small outputs inside the staging arena (what a multi-GPU caller exchanges)
+        oj, ok = C.c_size_t(), C.c_size_t()
+        capi.check(capi.lib().smplb200_host_staging_layout(self.h.ptr, self.n, smpl.flags, C.byref(oj), C.byref(ok)),
+                   "smplb200_host_staging_layout")
+        nj = smpl.num_joints
+        self.joints_dev = self.staging[oj.value: oj.value + n * nj * 12].view(torch.float32).view(n, nj, 3)
+        self.kp2d_dev = self.staging[ok.value: ok.value + n * nj * 8].view(torch.float32).view(n, nj, 2)
 
     @property
     def h2d_bytes(self) -> int:
@@ -312,13 +328,14 @@ class HostRunner:
     def d2h_bytes(self) -> int:
         return sum(t.numel() * 4 for t in (self.vertices, self.joints, self.kp2d) if t is not None)
 
-    def run(self, stream=None):
+    def run(self, stream=None, joints_ready=None):
         s = _stream_ptr(self.device) if stream is None else stream.cuda_stream
         with torch.cuda.device(self.device):
-            capi.check(capi.lib().smplb200_forward_host(
+            capi.check(capi.lib().smplb200_forward_host_opts(
                 self.h.ptr, _ptr(self.betas), _ptr(self.pose), _ptr(self.cam), self.n,
                 _ptr(self.vertices), _ptr(self.joints), _ptr(self.kp2d),
-                _ptr(self.staging), self.staging_bytes, self.smpl.flags, s), "smplb200_forward_host")
+                _ptr(self.staging), self.staging_bytes, self.smpl.flags, s, capi.forward_opts(joints_ready)),
+                "smplb200_forward_host")
 
 
 # ---- per-kernel entry points (unit parity, ncu) --------------------------------------------------

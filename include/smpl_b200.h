@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SMPLB200_VERSION 110 /* 0.1.1: + backward */
+#define SMPLB200_VERSION 120 /* 0.2.0: + forward options (joints-ready event), peer-store row exchange */
 
 /* ---- status codes ---------------------------------------------------------------------- */
 enum {
@@ -118,6 +118,23 @@ int smplb200_forward(const SmplB200Model* model,
                      float* vertices, float* joints, float* kp2d,
                      void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
 
+/* Options for the `_opts` variants below (NULL = none).
+ *   joints_ready_event  a cudaEvent_t (as void*), recorded on `stream` as soon as `joints` (and `kp2d`)
+ *                       are final: right after k2 for kinematic joints (~10 us into the step, the
+ *                       projection rides in k2), after the regression kernel for regressed joints.
+ *                       Lets the caller start the multi-GPU exchange of the small outputs on a side
+ *                       stream while the blendshape / skinning kernels still run (SURVEY.md §5, §8e;
+ *                       reference analogue: the DataParallel gather at src/lib/trains/trainer.py:176).   */
+typedef struct SmplB200ForwardOpts {
+  uint32_t struct_size;        /* = sizeof(SmplB200ForwardOpts) */
+  void* joints_ready_event;    /* cudaEvent_t or NULL            */
+} SmplB200ForwardOpts;
+int smplb200_forward_opts(const SmplB200Model* model,
+                          const float* betas, const float* pose, const float* cam, int64_t n,
+                          float* vertices, float* joints, float* kp2d,
+                          void* workspace, size_t workspace_bytes, uint32_t flags, void* stream,
+                          const SmplB200ForwardOpts* opts);
+
 /* Same pass with HOST buffers (pinned recommended): copies betas/pose/cam host->device,
  * runs the forward, copies the requested outputs device->host, all ordered on `stream`.
  * `vertices_host`/`joints_host`/`kp2d_host` may each be NULL to skip that copy.
@@ -128,6 +145,40 @@ int smplb200_forward_host(const SmplB200Model* model,
                           const float* betas_host, const float* pose_host, const float* cam_host,
                           int64_t n, float* vertices_host, float* joints_host, float* kp2d_host,
                           void* staging, size_t staging_bytes, uint32_t flags, void* stream);
+
+int smplb200_forward_host_opts(const SmplB200Model* model,
+                               const float* betas_host, const float* pose_host, const float* cam_host,
+                               int64_t n, float* vertices_host, float* joints_host, float* kp2d_host,
+                               void* staging, size_t staging_bytes, uint32_t flags, void* stream,
+                               const SmplB200ForwardOpts* opts);
+/* Byte offsets, inside `staging`, of the DEVICE copies of joints[N,J,3] and kp2d[N,J,2] the host entry
+ * produces (valid once `joints_ready_event` has fired): what a multi-GPU caller pushes to its peers.  */
+int smplb200_host_staging_layout(const SmplB200Model* model, int64_t n, uint32_t flags,
+                                 size_t* joints_offset, size_t* kp2d_offset);
+
+/* ---- multi-GPU: exchange of the small per-body outputs over peer-mapped memory ----
+ * Bodies are sharded over ranks with no data-path collective.  The one optional exchange -- every
+ * rank's joints (288 B/body) and kp2d (192 B/body) visible on every rank, what the reference gets from
+ * nn.DataParallel's gather (src/lib/trains/trainer.py:176) -- is done with plain peer stores over
+ * NVLink / NVSwitch instead of an NCCL launch: `smplb200_push_rows` writes this rank's rows
+ * [row_offset, row_offset + n) of the gathered buffer [n_total][120] fp32 (joints 72 | kp2d 48) into
+ * EVERY rank's copy of it and then publishes `epoch` in flags[peer][rank]; `smplb200_wait_rows`
+ * returns (on the stream) once all `world` flags of this rank have reached `epoch`.
+ *   peer_buffers / peer_flags  HOST arrays of `world` DEVICE pointers, peer-mapped by the caller (CUDA
+ *                              IPC or symmetric memory); entry `rank` is the local buffer / flag array
+ *                              (uint32[world], zero-initialised); world <= 16
+ *   counter                    a zero-initialised local uint32 in device memory (scratch of the call)
+ * Epochs must increase from call to call (wrap-around is handled).  A peer that never arrives faults
+ * the waiting launch after a few seconds instead of hanging the device.                               */
+int smplb200_push_rows(int32_t device, const float* joints, const float* kp2d, int64_t n, int64_t row_offset,
+                       void* const* peer_buffers, void* const* peer_flags, int32_t world, int32_t rank,
+                       uint32_t epoch, void* counter, void* stream);
+int smplb200_wait_rows(int32_t device, const void* my_flags, int32_t world, uint32_t epoch, void* stream);
+
+/* Measurement aid for bench.py (the fp32-FMA peak is measured in the same run): launches
+ * 8 CTAs per SM of 256 threads running 8 independent FMA chains for `iters` rounds; `*flop` receives the
+ * flop count of the launch.  `scratch`: >= 4 bytes of device memory.                                  */
+int smplb200_probe_fp32_fma(int32_t device, int32_t iters, void* scratch, double* flop, void* stream);
 
 /* ---- per-kernel entry points (unit parity + ncu) ---------------------------------------- */
 /* Internal intermediate layouts (owned by this library, stable within a version):
@@ -140,7 +191,8 @@ int64_t smplb200_padded_verts(const SmplB200Model* model);          /* VP       
 #define SMPLB200_COEF_K 224
 
 /* k2: folded joint regression + Rodrigues + kinematic chain (one warp per body).
- * Writes coef, A, and optionally joints (kinematic J_posed).  Any output may be NULL.       */
+ * Writes coef, A, and optionally joints (kinematic J_posed).  Any output may be NULL.
+ * (Inside smplb200_forward the same kernel also writes kp2d for kinematic joints.)          */
 int smplb200_pose_chain(const SmplB200Model* model, const float* betas, const float* pose,
                         int64_t n, float* coef, float* A, float* joints,
                         uint32_t flags, void* stream);

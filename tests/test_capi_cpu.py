@@ -37,7 +37,7 @@ def test_header_symbols_all_exported_and_bound():
 
 def test_version_and_strerror():
     lib = capi.lib()
-    assert lib.smplb200_version() == 110
+    assert lib.smplb200_version() == 120
     assert capi.strerror(0) == "ok"
     assert "workspace" in capi.strerror(3)
     assert capi.strerror(12345) == "unknown status"
