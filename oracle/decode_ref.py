@@ -66,3 +66,32 @@ def decode_gather(heat: torch.Tensor, heads, K: int):
     heat = nms(heat)
     scores, inds, clses, ys, xs = topk(heat, K)
     return scores, inds, clses, ys, xs, [transpose_and_gather_feat(h, inds) for h in heads]
+
+
+def check_equivalent(got, heat, heads, K: int):
+    """Is `got` (a decode_gather result) what the reference computes on (heat, heads), up to the ORDER OF
+    EQUAL SCORES?  `torch.topk` leaves the order (and, at the cut, the choice) of tied scores unspecified
+    (it differs between torch's CPU and CUDA kernels), so on head maps with ties an index-for-index
+    comparison is not defined; this checks everything that is:
+      1. the K scores equal the reference's, bit for bit, in order;
+      2. every returned index is distinct within its image and points at a pixel whose NMS-ed score is
+         exactly the returned score (so the selected SET is a valid top-K);
+      3. ys / xs / clses are the coordinates of that index;
+      4. each gathered vector is exactly the head's channel vector at that pixel.
+    Without ties 1-4 imply equality with the reference index for index.  Returns (ok, n_images_with_ties).
+    """
+    scores, inds, clses, ys, xs, gathered = got
+    B, C, H, W = heat.shape
+    hn = nms(heat)
+    ref_scores = topk(hn, K)[0]
+    ok = torch.equal(scores, ref_scores)
+    b_idx = torch.arange(B).view(B, 1).expand(B, K)
+    ok &= bool((hn[b_idx, clses.long(), ys.long(), xs.long()] == scores).all())
+    ok &= bool((ys.long() * W + xs.long() == inds).all())
+    for b in range(B):
+        ok &= len(set((clses[b].long() * H * W + inds[b]).tolist())) == K
+    for h, g in zip(heads, gathered):
+        ok &= torch.equal(h[b_idx, :, ys.long(), xs.long()], g)
+    top = torch.topk(hn.view(B, -1), min(K + 1, C * H * W)).values
+    ties = int((top[:, 1:] == top[:, :-1]).any(dim=1).sum())
+    return bool(ok), ties
