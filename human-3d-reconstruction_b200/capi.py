@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libsmpl_b200.so")
 
 # ---- constants mirrored from smpl_b200.h -------------------------------------------------------
 OK = 0
-PREC_AUTO, PREC_FP32, PREC_BF16, PREC_TF32, PREC_BF16X3 = 0, 1, 2, 3, 4
+PREC_AUTO, PREC_FP32, PREC_BF16, PREC_TF32, PREC_BF16X3, PREC_F16 = 0, 1, 2, 3, 4, 5
 PREC_MASK = 0x7
 JOINTS_KINEMATIC, JOINTS_REGRESSED = 0, 1 << 3
 ROTATE_BASE = 1 << 4
@@ -30,7 +30,7 @@ DCN_INPUT_NHWC = 1       # smplb200_dcn_v2_forward flag: the input tensor is alr
 COEF_K = 224
 
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32,
-              "bf16x3": PREC_BF16X3}
+              "bf16x3": PREC_BF16X3, "f16": PREC_F16}
 LBS_PATHS = {"auto": LBS_AUTO, "fma": LBS_FMA, "tc": LBS_TC, "dense": LBS_DENSE}
 
 
@@ -92,6 +92,8 @@ SYMBOLS = {
     "smplb200_lbs_workspace_bytes": (_sz, [_vp, _i64, _u32]),
     "smplb200_lbs": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _u32, _vp]),
     "smplb200_regress_joints": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "smplb200_blend_skin_workspace_bytes": (_sz, [_vp, _i64]),
+    "smplb200_blend_skin": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "smplb200_backward_workspace_bytes": (_sz, [_vp, _i64, _u32, _int]),
     "smplb200_backward": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
                                  _u32, _vp]),

@@ -43,6 +43,9 @@ struct DeviceModel {
   const uint32_t* bwd_basis_tf32_lo;   // same, low part of the 2-term tf32 split
   const uint16_t* bwd_basis_bf16_hi;   // [NC/32][4][224][8] the same tiles in bf16 (hi | lo)
   const uint16_t* bwd_basis_bf16_lo;
+  // fused blendshapes + skinning kernel (k_fused_tc.cuh); null when NB > 13 (shape + template rows must fit one K step)
+  const uint8_t* fz_basis;             // [VP/128 tiles][hi x|y|z: 28 chunks x 128 rows x 8 fp16][lo x|y|z: 2 chunks ...]
+  const uint32_t* fz_w;                // [VP][32 words] fp16 W_hi(24) 0(8) | W_lo(24) 0(8)
 };
 
 }  // namespace smplb200

@@ -9,6 +9,8 @@
 // Rodrigues mirrors the eager idiom op for op with explicit round-to-nearest
 // mul/add so nvcc cannot contract what the eager layer rounds separately.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace smplb200 {
@@ -23,6 +25,8 @@ struct ChainOut {
   uint16_t* coef_bf16_lo;
   uint32_t* coef_tf32;
   uint32_t* a_tf32;       // [n/8 blocks][12 chunks][96 rows][4] tf32 hi|lo image of A (LBS blend)
+  uint8_t* fz_coef;       // fused kernel: fp16 coef images per 64-body block (k_fused_tc.cuh), or null
+  uint8_t* fz_a;          // fused kernel: fp16 hi|lo images of A per 4-body sub-block, or null
   const float* cam;       // [n, 3] (s, tx, ty) or null
   float* kp2d;            // [n, 24, 2] weak-perspective projection of the KINEMATIC joints (k4), or null
 };
@@ -249,6 +253,53 @@ k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __rest
       }
       im[(size_t)c * rows + bi * 12 + e] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+  }
+  // ---- operand images of the fused blendshapes+skinning kernel (fp16; layouts in k_fused_tc.cuh) ----
+  if (out.fz_coef) {
+    // K order: betas | 1 1 1 (template pieces) | 0.. (16 rows) | pose_feature (207) | 0.  One 16-byte
+    // chunk = 8 consecutive k of this body; hi chunks 0..27 (+ lo chunks 0..1 for the 16 shape rows).
+    uint8_t* img = out.fz_coef + (size_t)(b / 64) * (2048 + kCoefK * 64 * 2);
+    const int row = int(b % 64);
+    auto value = [&](int nk) -> float {
+      if (nk < NB) return sc[nk];
+      if (nk < NB + 3) return 1.0f;
+      if (nk < 16) return 0.f;
+      if (nk < 16 + kP) return sc[NB + (nk - 16)];
+      return 0.f;
+    };
+    if (lane < kCoefK / 8) {
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v0 = value(8 * lane + 2 * u), v1 = value(8 * lane + 2 * u + 1);
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        wh[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        wl[u] = (uint32_t)__half_as_ushort(__float2half_rn(__fsub_rn(v0, __half2float(h0)))) |
+                ((uint32_t)__half_as_ushort(__float2half_rn(__fsub_rn(v1, __half2float(h1)))) << 16);
+      }
+      reinterpret_cast<uint4*>(img + 2048)[(size_t)lane * 64 + row] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      if (lane < 2) reinterpret_cast<uint4*>(img)[(size_t)lane * 64 + row] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
+  }
+  if (out.fz_a) {
+    // per 4-body sub-block: [chunk 0..2: A_hi joints 8c..8c+7][chunk 3..5: A_lo][chunk 6: zeros], rows = (body, entry)
+    uint4* img = reinterpret_cast<uint4*>(out.fz_a + (size_t)(b / 4) * (7 * 48 * 16));
+    const int r0 = int(b % 4) * 12;
+    for (int item = lane; item < 3 * 12; item += 32) {
+      const int c = item / 12, e = item % 12;
+      uint32_t wh[4], wl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v0 = sa[(8 * c + 2 * u) * 12 + e], v1 = sa[(8 * c + 2 * u + 1) * 12 + e];
+        const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+        wh[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        wl[u] = (uint32_t)__half_as_ushort(__float2half_rn(__fsub_rn(v0, __half2float(h0)))) |
+                ((uint32_t)__half_as_ushort(__float2half_rn(__fsub_rn(v1, __half2float(h1)))) << 16);
+      }
+      img[(size_t)c * 48 + r0 + e] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      img[(size_t)(3 + c) * 48 + r0 + e] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+    }
+    if (lane < 12) img[(size_t)6 * 48 + r0 + lane] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 

@@ -1,0 +1,446 @@
+// k1 + k3 (+ the transpose/store of k3's epilogue) FUSED: blendshapes and linear blend skinning of a
+// (128-vertex tile, 64-body block) unit in one CTA, both contractions on tcgen05, accumulators in
+// tensor memory -- the v_posed intermediate (82,680 B per body written by k1 and read back by k3,
+// 2/3 of the unfused step's DRAM traffic) never exists.
+//
+//   D_p[v, b]     = sum_k basis_p[v, k] * coef[b, k]            p = x, y, z planes; K = 224
+//   T[v, (b, e)]  = sum_j W[v, j] * A[b, j, e]                  e = 12 entries of the 3x4 transform
+//   verts[b, v, r] = T[v,(b,r,0..2)] . (D_x, D_y, D_z)[v, b] + T[v,(b,r,3)]
+//
+// Both accumulators have the tile's 128 VERTICES on the TMEM lanes, so the epilogue thread that owns
+// vertex v reads its blended transform and its posed rest position for body b from its own lane.
+//
+// Operand placement (what fits one SM; see DESIGN.md §3d for the arithmetic)
+//   * the tile's blendshape basis is the A operand of the D MMAs and stays RESIDENT IN SHARED MEMORY
+//     for all of the CTA's units: 3 planes x [224 K][128 rows] fp16 = 168 KB (+ 12 KB: the low halves
+//     of the 16 shape/template rows).  It cannot live in TMEM (3 x 112 columns) next to the
+//     accumulators, so the D MMAs are SS-form with N = 64: their cost is the shared-memory read of A
+//     (4 KB per MMA, ~52 clk measured; scripts/mma_issue_microbench.cu), not tensor math.
+//   * coef blocks (B operand, 30 KB per unit) stream through a 3-stage bulk-TMA ring in K chunks; every
+//     chunk feeds the MMAs of all three planes before it is released.
+//   * skinning weights W' = [W_hi | W_lo] of the tile live in TMEM (32 columns) as the A operand of the
+//     blend MMAs (TS form, N = 48 = 4 bodies x 12 entries, ~32 clk each); the joint transforms A' stream
+//     through their own 3-stage ring, one 5.3 KB image per 4-body sub-block.
+//   * TMEM: D double-buffered (2 x 3 x 64 columns), T double-buffered (2 x 48), W' (32) = 512 columns.
+//
+// Precision (SMPLB200_PREC_F16): fp16 operands (11 significant bits), fp32 accumulation.
+//   * pose rows (207 of the 224 K): ONE MMA, operands rounded to fp16: measured max vertex error 1.9e-5 m
+//     against float64 (stated bound 5e-5 m; TF32 operands give 1.9e-4, bf16 1.4e-3).
+//   * shape rows and the template (the O(1 m) and O(0.06 m) terms): exact 3-term split
+//     (hi*hi + lo*hi + hi*lo; the template as three fp16 pieces with coefficient 1).
+//   * the skinning blend: 3-term fp16 split of BOTH operands (W_hi*A_hi + W_hi*A_lo + W_lo*A_hi, products
+//     exact in the fp32 accumulator): ~2e-7, the same fp32-class fidelity as k_lbs_tc's 3xTF32.
+//
+// Schedule: persistent CTAs (one per SM) own equal contiguous ranges of the tile-major unit list.
+// Warp roles (384 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warp 1 = MMA issuer
+// (warp-uniform, one elected lane), warp 2 = bulk-TMA producer of the A' images, warp 3 idle,
+// warps 4..11 = epilogue: TMEM lane quarter q = warp % 4, slot e = (warp - 4) / 4 takes the sub-blocks
+// s = e, e + 2, ... and owns T buffer e.  The D MMAs of unit i+1 are interleaved between the blend MMAs of
+// unit i, so the tensor pipe never waits for an epilogue to drain a whole unit.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "k_chain.cuh"
+#include "ptx.cuh"
+
+namespace smplb200 {
+
+constexpr int kFzBodies = 64;                       // bodies per unit (N of the D MMAs)
+constexpr int kFzSub = 4;                           // bodies per blend sub-block
+constexpr int kFzSubs = kFzBodies / kFzSub;         // 16
+constexpr int kFzNT = kFzSub * 12;                  // 48: N of the blend MMAs
+constexpr int kFzShapeK = 16;                       // K rows 0..15: betas | template pieces | 0
+constexpr int kFzThreads = 384;
+constexpr int kFzEpiWarp0 = 4, kFzEpiWarps = 8;
+constexpr uint32_t kFzPlaneHi = kCoefK * 128 * 2;               // 57,344
+constexpr uint32_t kFzPlaneLo = kFzShapeK * 128 * 2;            // 4,096
+constexpr uint32_t kFzBasisBytes = 3 * (kFzPlaneHi + kFzPlaneLo);   // 184,320 per vertex tile
+constexpr uint32_t kFzCoefLo = kFzShapeK * kFzBodies * 2;       // 2,048
+constexpr uint32_t kFzCoefBlock = kFzCoefLo + kCoefK * kFzBodies * 2;   // 30,720 per 64-body block
+constexpr int kFzChunks = 7;                                    // K chunks per unit: 2 k-steps each
+constexpr uint32_t kFzCoefStage = kFzCoefLo + 2 * 2048;         // 6,144 (chunk 0 carries the lo rows too)
+constexpr int kFzCoefStages = 3;
+constexpr uint32_t kFzAImage = 7 * kFzNT * 16;                  // 5,376: [A_hi 3 chunks | A_lo 3 chunks | 0]
+constexpr int kFzAStages = 3;
+constexpr uint32_t kFzOffCoef = kFzBasisBytes;
+constexpr uint32_t kFzOffA = kFzOffCoef + kFzCoefStages * kFzCoefStage;
+constexpr uint32_t kFzOffOut = kFzOffA + kFzAStages * kFzAImage;
+constexpr uint32_t kFzOffBar = kFzOffOut + kFzEpiWarps * 4 * 96 * 4;
+constexpr uint32_t kFzSmemBytes = kFzOffBar + 256;              // 231,424 <= 232,448
+constexpr uint32_t kFzTmemD = 0, kFzTmemT = 2 * 3 * kFzBodies, kFzTmemW = kFzTmemT + 2 * kFzNT;   // 0 | 384 | 480
+constexpr uint32_t kFzIdescD = ptx::make_idesc(ptx::kFmtF16, 128, kFzBodies);
+constexpr uint32_t kFzIdescT = ptx::make_idesc(ptx::kFmtF16, 128, kFzNT);
+static_assert(kFzSmemBytes <= 232448, "shared memory budget");
+static_assert(kFzTmemW + 32 == 512, "TMEM budget");
+
+__device__ __forceinline__ uint16_t f32_to_f16_rn(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ float f16_to_f32(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+// position of old-order coefficient k (betas | pose_feature | 1 1 1 | 0) in the fused kernel's K order
+// (betas | 1 1 1 | 0.. up to 16 | pose_feature | 0): returns the OLD index feeding new row `nk`, or -1 (zero)
+__device__ __forceinline__ int fz_old_index(int nk, int NB) {
+  if (nk < NB) return nk;
+  if (nk < NB + 3) return NB + kP + (nk - NB);
+  if (nk < kFzShapeK) return -1;
+  if (nk < kFzShapeK + kP) return NB + (nk - kFzShapeK);
+  return -1;
+}
+
+__global__ void __launch_bounds__(kFzThreads, 1)
+k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__ w_rows,
+           const uint8_t* __restrict__ coef_img, const uint8_t* __restrict__ a_img,
+           long long n, int nblk, long long total_units, int V, float* __restrict__ verts) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sBasis = smem;
+  uint8_t* sCoef = smem + kFzOffCoef;
+  uint8_t* sA = smem + kFzOffA;
+  float* sOut = reinterpret_cast<float*>(smem + kFzOffOut);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFzOffBar);
+  uint64_t* bar_bfull = bars;                          // basis tile landed (tx)
+  uint64_t* bar_bfree = bars + 1;                      // every MMA reading the old basis tile retired
+  uint64_t* bar_w = bars + 2;                          // W' rows of the tile are in TMEM (4 warp arrivals)
+  uint64_t* bar_cfull = bars + 3;                      // [3] coef chunk landed
+  uint64_t* bar_cempty = bar_cfull + kFzCoefStages;    // [3] MMAs reading it retired
+  uint64_t* bar_afull = bar_cempty + kFzCoefStages;    // [3] A' image landed
+  uint64_t* bar_aempty = bar_afull + kFzAStages;       // [3]
+  uint64_t* bar_dfull = bar_aempty + kFzAStages;       // [2] D accumulators of a unit complete
+  uint64_t* bar_dempty = bar_dfull + 2;                // [2] drained by the 8 epilogue warps
+  uint64_t* bar_tfull = bar_dempty + 2;                // [2] blend accumulator complete
+  uint64_t* bar_tempty = bar_tfull + 2;                // [2] read by the 4 warps of its slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u0 = total_units * blockIdx.x / gridDim.x;
+  const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
+  const int nunits = (int)(u1 - u0);
+
+  if (warp == 0 && lane == 0) {
+    ptx::mbar_init(bar_bfull, 1); ptx::mbar_init(bar_bfree, 1); ptx::mbar_init(bar_w, 4);
+    for (int s = 0; s < kFzCoefStages; ++s) { ptx::mbar_init(bar_cfull + s, 1); ptx::mbar_init(bar_cempty + s, 1); }
+    for (int s = 0; s < kFzAStages; ++s) { ptx::mbar_init(bar_afull + s, 1); ptx::mbar_init(bar_aempty + s, 1); }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(bar_dfull + a, 1); ptx::mbar_init(bar_dempty + a, kFzEpiWarps);
+      ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer 1: the tile's basis image (on tile switches) and the coef chunks of every unit =====
+    if (lane == 0) {
+      long long cur_tile = -1;
+      int ntile_sw = 0, it = 0;
+      for (int i = 0; i < nunits; ++i) {
+        const long long u = u0 + i, tile = u / nblk;
+        const int blk = (int)(u % nblk);
+        if (tile != cur_tile) {
+          if (ntile_sw > 0) ptx::mbar_wait(bar_bfree, (ntile_sw - 1) & 1);   // old tile's D MMAs retired
+          ptx::mbar_arrive_expect_tx(bar_bfull, kFzBasisBytes);
+          ptx::bulk_g2s_split(sBasis, basis_tiles + (size_t)tile * kFzBasisBytes, kFzBasisBytes, bar_bfull);
+          cur_tile = tile;
+          ++ntile_sw;
+        }
+        const uint8_t* src = coef_img + (size_t)blk * kFzCoefBlock;
+        for (int c = 0; c < kFzChunks; ++c, ++it) {
+          const int s = it % kFzCoefStages;
+          ptx::mbar_wait(bar_cempty + s, ((it / kFzCoefStages) & 1) ^ 1);
+          const uint32_t bytes = c == 0 ? kFzCoefStage : 4096u;
+          const size_t off = c == 0 ? 0 : (size_t)kFzCoefLo + 4096u * c;
+          ptx::mbar_arrive_expect_tx(bar_cfull + s, bytes);
+          ptx::bulk_g2s(sCoef + (size_t)s * kFzCoefStage, src + off, bytes, bar_cfull + s);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== producer 2: tf-split images of the joint transforms, one per 4-body sub-block =====
+    if (lane == 0) {
+      int it = 0;
+      for (int i = 0; i < nunits; ++i) {
+        const int blk = (int)((u0 + i) % nblk);
+        const uint8_t* src = a_img + (size_t)blk * kFzSubs * kFzAImage;
+        for (int sb = 0; sb < kFzSubs; ++sb, ++it) {
+          const int s = it % kFzAStages;
+          ptx::mbar_wait(bar_aempty + s, ((it / kFzAStages) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(bar_afull + s, kFzAImage);
+          ptx::bulk_g2s(sA + (size_t)s * kFzAImage, src + (size_t)sb * kFzAImage, kFzAImage, bar_afull + s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (whole warp convergent, one elected lane issues) =====
+    const uint32_t basis_addr = ptx::smem_u32(sBasis);
+    const uint32_t tmem_w = tmem_base + kFzTmemW;
+    long long d_tile = -1;          // tile whose basis the D MMAs currently read
+    int d_tiles = 0;                // basis tiles consumed so far (phase of bar_bfull)
+    int c_it = 0;                   // coef chunks consumed so far
+    int a_it = 0;                   // A' images consumed so far
+    int t_cnt[2] = {0, 0};          // blend accumulators issued per T buffer
+    long long w_tile = -1;
+    int w_tiles = 0;
+
+    // D MMAs of chunk `c` of unit `i` (all three planes)
+    auto issue_d_chunk = [&](int i, int c) {
+      const long long u = u0 + i, tile = u / nblk;
+      const int a = i & 1;
+      if (c == 0) {
+        if (tile != d_tile) {                      // first D MMA on a new basis tile
+          ptx::mbar_wait(bar_bfull, d_tiles & 1);
+          ++d_tiles;
+          d_tile = tile;
+        }
+        ptx::mbar_wait(bar_dempty + a, ((i >> 1) & 1) ^ 1);   // epilogue drained this buffer (unit i-2)
+      }
+      const int s = c_it % kFzCoefStages;
+      ptx::mbar_wait(bar_cfull + s, (c_it / kFzCoefStages) & 1);
+      ++c_it;
+      ptx::tc_fence_after();
+      const uint32_t c_addr = ptx::smem_u32(sCoef + (size_t)s * kFzCoefStage);
+      if (ptx::elect_one()) {
+        constexpr uint32_t kLboA = 128 * 16, kLboB = kFzBodies * 16, kSbo = 128;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const uint32_t d_tmem = tmem_base + kFzTmemD + (a * 3 + p) * kFzBodies;
+          const uint32_t hi_p = basis_addr + p * kFzPlaneHi;
+          if (c == 0) {
+            const uint32_t lo_p = basis_addr + 3 * kFzPlaneHi + p * kFzPlaneLo;
+            const uint64_t c_lo = ptx::make_smem_desc(c_addr, kLboB, kSbo);
+            const uint64_t c_h0 = ptx::make_smem_desc(c_addr + kFzCoefLo, kLboB, kSbo);
+            const uint64_t c_h1 = ptx::make_smem_desc(c_addr + kFzCoefLo + 2048, kLboB, kSbo);
+            const uint64_t b_h0 = ptx::make_smem_desc(hi_p, kLboA, kSbo);
+            const uint64_t b_h1 = ptx::make_smem_desc(hi_p + 2 * kLboA, kLboA, kSbo);
+            const uint64_t b_lo = ptx::make_smem_desc(lo_p, kLboA, kSbo);
+            ptx::mma_bf16(d_tmem, b_h0, c_h0, kFzIdescD, 0u);   // shape rows: hi*hi
+            ptx::mma_bf16(d_tmem, b_h0, c_lo, kFzIdescD, 1u);   //             hi(basis)*lo(coef)
+            ptx::mma_bf16(d_tmem, b_lo, c_h0, kFzIdescD, 1u);   //             lo(basis)*hi(coef)
+            ptx::mma_bf16(d_tmem, b_h1, c_h1, kFzIdescD, 1u);   // first pose k-step
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t bd = ptx::make_smem_desc(hi_p + (uint32_t)(2 * c + ks) * 2 * kLboA, kLboA, kSbo);
+              const uint64_t cd = ptx::make_smem_desc(c_addr + ks * 2048, kLboB, kSbo);
+              ptx::mma_bf16(d_tmem, bd, cd, kFzIdescD, 1u);
+            }
+          }
+        }
+        ptx::tc_commit(bar_cempty + s);
+        if (c == kFzChunks - 1) {
+          ptx::tc_commit(bar_dfull + a);
+          // last unit on this basis tile: tell the producer when its D MMAs have retired
+          const bool last_of_tile = (i + 1 == nunits) || ((u0 + i + 1) / nblk != tile);
+          if (last_of_tile) ptx::tc_commit(bar_bfree);
+        }
+      }
+      __syncwarp();
+    };
+
+    for (int c = 0; c < kFzChunks && nunits > 0; ++c) issue_d_chunk(0, c);
+    for (int i = 0; i < nunits; ++i) {
+      const long long tile = (u0 + i) / nblk;
+      if (tile != w_tile) {                        // blend MMAs of a new tile need its W' rows in TMEM
+        ptx::mbar_wait(bar_w, w_tiles & 1);
+        ++w_tiles;
+        w_tile = tile;
+      }
+      for (int sb = 0; sb < kFzSubs; ++sb) {
+        const int e = sb & 1, s = a_it % kFzAStages;
+        ptx::mbar_wait(bar_tempty + e, (t_cnt[e] & 1) ^ 1);
+        ptx::mbar_wait(bar_afull + s, (a_it / kFzAStages) & 1);
+        ++a_it; ++t_cnt[e];
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(sA + (size_t)s * kFzAImage);
+        if (ptx::elect_one()) {
+          constexpr uint32_t kLbo = kFzNT * 16, kSbo = 128;
+          const uint32_t t_tmem = tmem_base + kFzTmemT + e * kFzNT;
+          const uint64_t s0 = ptx::make_smem_desc(a_addr, kLbo, kSbo);              // A_hi joints 0..15
+          const uint64_t s1 = ptx::make_smem_desc(a_addr + 2 * kLbo, kLbo, kSbo);   // A_hi 16..23 | (A_lo 0..7 x 0)
+          const uint64_t s2 = ptx::make_smem_desc(a_addr + 3 * kLbo, kLbo, kSbo);   // A_lo joints 0..15
+          const uint64_t s3 = ptx::make_smem_desc(a_addr + 5 * kLbo, kLbo, kSbo);   // A_lo 16..23 | zeros
+          ptx::mma_bf16_ts(t_tmem, tmem_w, s0, kFzIdescT, 0u);        // W_hi * A_hi
+          ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s1, kFzIdescT, 1u);
+          ptx::mma_bf16_ts(t_tmem, tmem_w, s2, kFzIdescT, 1u);        // W_hi * A_lo
+          ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s3, kFzIdescT, 1u);
+          ptx::mma_bf16_ts(t_tmem, tmem_w + 16, s0, kFzIdescT, 1u);   // W_lo * A_hi
+          ptx::mma_bf16_ts(t_tmem, tmem_w + 24, s1, kFzIdescT, 1u);
+          ptx::tc_commit(bar_aempty + s);
+          ptx::tc_commit(bar_tfull + e);
+        }
+        __syncwarp();
+        // the next unit's D MMAs, one K chunk after every second blend: by the time chunk 0 asks for the D
+        // buffer the epilogue has had two blend results of THIS unit to chew on, so it is never starved
+        if ((sb & 1) == 1 && (sb >> 1) < kFzChunks && i + 1 < nunits) issue_d_chunk(i + 1, sb >> 1);
+      }
+    }
+  } else if (warp >= kFzEpiWarp0) {
+    // ===== epilogue: slot e, lane quarter q =====
+    const int ew = warp - kFzEpiWarp0;
+    const int q = warp & 3, e = ew >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float* so = sOut + ew * (4 * 96);
+    long long cur_tile = -1;
+    int t_cnt = 0;                    // sub-blocks this warp has consumed (phase of its T buffer)
+    const size_t body_stride = (size_t)V * 3;
+    for (int i = 0; i < nunits; ++i) {
+      const long long u = u0 + i, tile = u / nblk;
+      const int blk = (int)(u % nblk), a = i & 1;
+      if (tile != cur_tile) {
+        // New tile: its W' rows replace the old ones in TMEM.  Every blend MMA of the old tile has retired
+        // once BOTH T buffers of the previous unit's last sub-blocks were completed; slot 0's own last
+        // result was consumed above, slot 1's is awaited here (a wait does not consume the phase).
+        if (e == 0) {
+          if (i > 0) ptx::mbar_wait(bar_tfull + 1, ((i * (kFzSubs / 2) - 1) & 1));
+          ptx::tc_fence_after();
+          const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + q * 32 + lane) * 32);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t w[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint4 x = __ldg(src + c * 4 + v);
+              w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+            ptx::tmem_st16(tmem_base + kFzTmemW + lane_addr + c * 16, w);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_w);
+          __syncwarp();
+        }
+        cur_tile = tile;
+      }
+      const int warp_v0 = (int)tile * 128 + q * 32;
+      const int nf = max(0, min(32, V - warp_v0)) * 3;    // floats this warp may store per body
+      ptx::mbar_wait(bar_dfull + a, (i >> 1) & 1);
+      for (int sb = e; sb < kFzSubs; sb += 2) {
+        const long long b0 = (long long)blk * kFzBodies + sb * kFzSub;
+        ptx::mbar_wait(bar_tfull + e, t_cnt & 1);
+        ++t_cnt;
+        ptx::tc_fence_after();
+        uint32_t r0[16], r1[16], r2[16], dx[4], dy[4], dz[4];
+        const uint32_t t_addr = tmem_base + kFzTmemT + lane_addr + e * kFzNT;
+        const uint32_t d_addr = tmem_base + kFzTmemD + lane_addr + a * 3 * kFzBodies + sb * kFzSub;
+        ptx::tmem_ld16(t_addr, r0);
+        ptx::tmem_ld16(t_addr + 16, r1);
+        ptx::tmem_ld16(t_addr + 32, r2);
+        ptx::tmem_ld4(d_addr, dx);
+        ptx::tmem_ld4(d_addr + kFzBodies, dy);
+        ptx::tmem_ld4(d_addr + 2 * kFzBodies, dz);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(bar_tempty + e);
+          if (sb + 2 >= kFzSubs) ptx::mbar_arrive(bar_dempty + a);    // this warp's last read of the unit's D
+        }
+        __syncwarp();
+        float T[48];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          T[k] = __uint_as_float(r0[k]); T[16 + k] = __uint_as_float(r1[k]); T[32 + k] = __uint_as_float(r2[k]);
+        }
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const float* tt = T + bb * 12;
+          const float x = __uint_as_float(dx[bb]), y = __uint_as_float(dy[bb]), z = __uint_as_float(dz[bb]);
+          float* sbuf = so + bb * 96 + 3 * lane;
+          sbuf[0] = fmaf(tt[2], z, fmaf(tt[1], y, fmaf(tt[0], x, tt[3])));
+          sbuf[1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
+          sbuf[2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
+        }
+        __syncwarp();
+        float* dst = verts + ((size_t)b0 * V + warp_v0) * 3 + lane;
+        if (b0 + kFzSub <= n && nf == 96) {        // whole sub-block, whole warp: unpredicated stores
+          float o[12];
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            o[3 * bb] = so[bb * 96 + lane]; o[3 * bb + 1] = so[bb * 96 + lane + 32];
+            o[3 * bb + 2] = so[bb * 96 + lane + 64];
+          }
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            float* d = dst + bb * body_stride;
+            d[0] = o[3 * bb]; d[32] = o[3 * bb + 1]; d[64] = o[3 * bb + 2];
+          }
+        } else {
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) {
+            if (b0 + bb < n) {
+              float* d = dst + bb * body_stride;
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                if (lane + 32 * k < nf) d[32 * k] = so[bb * 96 + lane + 32 * k];
+            }
+          }
+        }
+        __syncwarp();          // staging rows are reused by the next sub-block
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// fp32 coef [n,224] (old K order) and A [n,24,12] -> the fused kernel's operand images (stand-alone entry
+// point only; inside smplb200_forward k2 writes the images directly).
+__global__ void __launch_bounds__(256)
+k_pack_fz(const float* __restrict__ coef, const float* __restrict__ A, long long n, int NB,
+          uint8_t* __restrict__ coef_img, uint8_t* __restrict__ a_img) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ncoef = n * kCoefK, na = n * (kJ * 12);
+  if (idx < ncoef) {
+    const long long b = idx / kCoefK;
+    const int nk = int(idx - b * kCoefK);
+    const int ok = fz_old_index(nk, NB);
+    const float v = ok < 0 ? 0.f : coef[b * kCoefK + ok];
+    const uint16_t hi = f32_to_f16_rn(v);
+    uint8_t* img = coef_img + (size_t)(b / kFzBodies) * kFzCoefBlock;
+    const int row = int(b % kFzBodies);
+    reinterpret_cast<uint16_t*>(img + kFzCoefLo)[(size_t)(nk >> 3) * (kFzBodies * 8) + row * 8 + (nk & 7)] = hi;
+    if (nk < kFzShapeK)
+      reinterpret_cast<uint16_t*>(img)[(size_t)(nk >> 3) * (kFzBodies * 8) + row * 8 + (nk & 7)] =
+          f32_to_f16_rn(__fsub_rn(v, f16_to_f32(hi)));
+  } else if (idx < ncoef + na) {
+    const long long i = idx - ncoef;
+    const long long b = i / (kJ * 12);
+    const int r = int(i - b * (kJ * 12)), jj = r / 12, e = r % 12;
+    const float v = A[i];
+    const uint16_t hi = f32_to_f16_rn(v);
+    const uint16_t lo = f32_to_f16_rn(__fsub_rn(v, f16_to_f32(hi)));
+    uint16_t* img = reinterpret_cast<uint16_t*>(a_img + (size_t)(b / kFzSub) * kFzAImage);
+    const int row = int(b % kFzSub) * 12 + e;
+    img[(size_t)(jj >> 3) * (kFzNT * 8) + row * 8 + (jj & 7)] = hi;
+    img[(size_t)(3 + (jj >> 3)) * (kFzNT * 8) + row * 8 + (jj & 7)] = lo;
+    if (jj < 8) img[(size_t)6 * (kFzNT * 8) + row * 8 + jj] = 0;      // pad chunk (multiplied by zero weights)
+  }
+}
+
+inline size_t fz_coef_image_bytes(long long n) {
+  return (size_t)((std::max<long long>(n, 1) + kFzBodies - 1) / kFzBodies) * kFzCoefBlock;
+}
+inline size_t fz_a_image_bytes(long long n) {
+  return (size_t)((std::max<long long>(n, 1) + kFzBodies - 1) / kFzBodies) * kFzSubs * kFzAImage;
+}
+
+inline cudaError_t fused_tc_set_smem() {
+  return cudaFuncSetAttribute(k_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFzSmemBytes);
+}
+
+inline cudaError_t launch_fused_tc(const DeviceModel& m, int num_sms, const uint8_t* coef_img,
+                                   const uint8_t* a_img, long long n, float* verts, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const int ntile = m.VP / 128;
+  const int nblk = (int)((n + kFzBodies - 1) / kFzBodies);
+  const long long total = (long long)ntile * nblk;
+  const unsigned grid = (unsigned)std::min<long long>(num_sms, total);
+  k_fused_tc<<<grid, kFzThreads, kFzSmemBytes, s>>>(m.fz_basis, m.fz_w, coef_img, a_img, n, nblk, total, m.V, verts);
+  return cudaGetLastError();
+}
+
+}  // namespace smplb200

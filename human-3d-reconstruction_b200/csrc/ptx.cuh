@@ -202,7 +202,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
 }
 
-constexpr uint32_t kFmtBF16 = 1, kFmtTF32 = 2;
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2;   // kind::f16 takes F16 or BF16 operands, kind::tf32 TF32
 // Instruction descriptor: fp32 accumulate, A and B both K-major, dense.
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -266,6 +266,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -23,6 +23,7 @@
 #include "k_blend_tc.cuh"
 #include "k_blend_tc2.cuh"
 #include "k_lbs_tc.cuh"
+#include "k_fused_tc.cuh"
 #include "k_decode.cuh"
 #include "k_backward.cuh"
 #include "k_blend_bwd_tc.cuh"
@@ -93,6 +94,41 @@ inline float host_bf16_to_f32(uint16_t h) {
   std::memcpy(&f, &u, 4);
   return f;
 }
+// float -> IEEE half, round to nearest even (subnormals and overflow handled); and back
+inline uint16_t host_f16(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t absu = u & 0x7fffffffu;
+  if (absu >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | ((absu > 0x7f800000u) ? 0x200u : 0u));
+  if (absu >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);              // rounds to >= 65520: infinity
+  if (absu < 0x33000001u) return (uint16_t)sign;                           // < 2^-25 (or == 2^-25: ties to even 0)
+  const int exp = (int)(absu >> 23) - 127;
+  uint32_t mant = (absu & 0x7fffffu) | 0x800000u;                          // 24-bit significand
+  int shift = exp >= -14 ? 13 : (13 + (-14 - exp));                        // bits dropped
+  const uint32_t half_bit = 1u << (shift - 1);
+  const uint32_t rem = mant & ((1u << shift) - 1u);
+  uint32_t q = mant >> shift;
+  if (rem > half_bit || (rem == half_bit && (q & 1u))) ++q;
+  uint32_t h;
+  if (exp >= -14) h = ((uint32_t)(exp + 15) << 10) + (q - 0x400u);         // q in [0x400, 0x800]; carry bumps the exponent
+  else h = q;                                                              // subnormal (q may reach 0x400 = smallest normal)
+  return (uint16_t)(sign | h);
+}
+inline float host_f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  const uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  float mag;
+  if (e == 0) mag = std::ldexp((float)m, -24);
+  else if (e == 31) mag = m ? NAN : INFINITY;
+  else mag = std::ldexp((float)(m | 0x400u), (int)e - 25);
+  uint32_t u;
+  std::memcpy(&u, &mag, 4);
+  u |= sign;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
 inline uint32_t host_tf32(float x) {  // keep 10 mantissa bits, low 13 bits zero
   uint32_t u;
   std::memcpy(&u, &x, 4);
@@ -120,6 +156,7 @@ struct BlobBuilder {
 struct Workspace {
   size_t coef = 0, A = 0, vposed = 0, joints = 0;
   size_t coef_hi = 0, coef_lo = 0, coef_tf32 = 0, a_tf32 = 0;
+  size_t fz_coef = 0, fz_a = 0;      // fused kernel operand images
   size_t total = 0;
 };
 
@@ -132,13 +169,18 @@ struct Plan {
 
 bool resolve_plan(const SmplB200Model* m, long long n, uint32_t flags, Plan* p) {
   uint32_t prec = flags & SMPLB200_PREC_MASK;
-  if (prec > SMPLB200_PREC_BF16X3) return false;
+  if (prec > SMPLB200_PREC_F16) return false;
+  if (prec == SMPLB200_PREC_F16 && !m->d.fz_basis) return false;      // model has too many betas for the fused kernel
   if (prec == SMPLB200_PREC_AUTO)
     prec = n >= SMPLB200_TC_MIN_BATCH ? SMPLB200_PREC_BF16X3 : SMPLB200_PREC_FP32;
   uint32_t lbs = flags & SMPLB200_LBS_MASK;
   if (lbs == SMPLB200_LBS_AUTO)
     lbs = n >= SMPLB200_TC_LBS_MIN_BATCH ? SMPLB200_LBS_TC : SMPLB200_LBS_FMA;
   if (lbs == SMPLB200_LBS_FMA && m->d.max_nnz > 4) lbs = SMPLB200_LBS_DENSE;
+  if (prec == SMPLB200_PREC_F16) {      // one fused kernel does blendshapes AND skinning on tcgen05
+    if ((flags & SMPLB200_LBS_MASK) != SMPLB200_LBS_AUTO && (flags & SMPLB200_LBS_MASK) != SMPLB200_LBS_TC) return false;
+    lbs = SMPLB200_LBS_TC;
+  }
   if (flags & ~(SMPLB200_PREC_MASK | SMPLB200_JOINTS_REGRESSED | SMPLB200_ROTATE_BASE |
                 SMPLB200_LBS_MASK))
     return false;
@@ -158,6 +200,13 @@ Workspace carve(const SmplB200Model* m, long long n, const Plan& p) {
     return o;
   };
   const size_t nn = (size_t)std::max<long long>(n, 1);
+  if (p.prec == SMPLB200_PREC_F16) {     // fused: no coef / A / vposed / tf32 images, only the two fp16 operand images
+    w.joints = take(nn * kJ * 3 * sizeof(float));
+    w.fz_coef = take(fz_coef_image_bytes(n));
+    w.fz_a = take(fz_a_image_bytes(n));
+    w.total = off;
+    return w;
+  }
   w.coef = take(nn * kCoefK * sizeof(float));
   w.A = take(nn * kJ * 12 * sizeof(float));
   const bool chunked = m->chunk > 0 && p.prec != SMPLB200_PREC_FP32 && p.lbs == SMPLB200_LBS_TC &&
@@ -254,6 +303,7 @@ cudaError_t configure_tc_kernels() {
   if ((e = blend_bwd_tc_set_smem<kBwdBf16x3>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_blend_bwd_fma, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)kBbSmemBytes)) != cudaSuccess) return e;
+  if ((e = fused_tc_set_smem()) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_lbs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)kLbsSmemBytes);
 }
@@ -495,6 +545,59 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
         wtf[(size_t)v * kLbsK + 24 + j] = lo;
       }
 
+    // ---- fused blendshapes+skinning kernel (k_fused_tc.cuh): per vertex tile the exact shared-memory image
+    // of the fp16 basis, K order = betas | template pieces (hi, mid, lo; coefficient 1) | 0 | pose rows | 0
+    std::vector<uint16_t> fzb;
+    std::vector<uint32_t> fzw;
+    const bool fz_ok = NB + 3 <= kFzShapeK;
+    if (fz_ok) {
+      const int ntile = VP / 128;
+      fzb.assign((size_t)ntile * (kFzBasisBytes / 2), 0);
+      auto tmpl16 = [&](float x, int piece) -> float {
+        float rem = x;
+        for (int p = 0; p <= piece; ++p) {
+          const float h = host_f16_to_f32(host_f16(rem));
+          if (p == piece) return h;
+          rem -= h;
+        }
+        return 0.f;
+      };
+      for (int t = 0; t < ntile; ++t) {
+        uint16_t* tile = fzb.data() + (size_t)t * (kFzBasisBytes / 2);
+        for (int pl = 0; pl < 3; ++pl) {
+          uint16_t* hi = tile + (size_t)pl * (kFzPlaneHi / 2);
+          uint16_t* lo = tile + (size_t)3 * (kFzPlaneHi / 2) + (size_t)pl * (kFzPlaneLo / 2);
+          for (int r = 0; r < 128; ++r) {
+            const size_t col = (size_t)pl * VP + (size_t)t * 128 + r;
+            for (int nk = 0; nk < kCoefK; ++nk) {
+              float x = 0.f, xl = 0.f;
+              if (nk < NB) {
+                x = basis[(size_t)nk * NC + col];
+                const float h = host_f16_to_f32(host_f16(x));
+                xl = x - h;
+              } else if (nk < NB + 3) {
+                x = tmpl16(basis[(size_t)(NB + kP) * NC + col], nk - NB);
+              } else if (nk >= kFzShapeK && nk < kFzShapeK + kP) {
+                x = basis[(size_t)(NB + nk - kFzShapeK) * NC + col];
+              }
+              hi[(size_t)(nk >> 3) * (128 * 8) + r * 8 + (nk & 7)] = host_f16(x);
+              if (nk < kFzShapeK) lo[(size_t)(nk >> 3) * (128 * 8) + r * 8 + (nk & 7)] = host_f16(xl);
+            }
+          }
+        }
+      }
+      fzw.assign((size_t)VP * 32, 0);
+      for (int v = 0; v < VP; ++v)
+        for (int j = 0; j < kJ; ++j) {
+          const float x = dense_w[(size_t)v * kJ + j];
+          const uint16_t h = host_f16(x);
+          const uint16_t l = host_f16(x - host_f16_to_f32(h));
+          uint16_t* row = reinterpret_cast<uint16_t*>(fzw.data() + (size_t)v * 32);
+          row[j] = h;
+          row[32 + j] = l;
+        }
+    }
+
     std::unique_ptr<SmplB200Model> mp(new (std::nothrow) SmplB200Model());   // freed on every early return / throw
     if (!mp) return SMPLB200_ERR_ALLOC;
     SmplB200Model* m = mp.get();
@@ -521,6 +624,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     const size_t o_gbl = bb.add(gbl.data(), gbl.size() * 4);
     const size_t o_gbbh = bb.add(gbbh.data(), gbbh.size() * 2);
     const size_t o_gbbl = bb.add(gbbl.data(), gbbl.size() * 2);
+    const size_t o_fzb = fz_ok ? bb.add(fzb.data(), fzb.size() * 2) : 0;
+    const size_t o_fzw = fz_ok ? bb.add(fzw.data(), fzw.size() * 4) : 0;
 
     DeviceGuard guard(desc->device);
     if (guard.err != cudaSuccess) return cuda_fail(guard.err);
@@ -582,6 +687,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     d.bwd_basis_tf32_lo = reinterpret_cast<const uint32_t*>(base + o_gbl);
     d.bwd_basis_bf16_hi = reinterpret_cast<const uint16_t*>(base + o_gbbh);
     d.bwd_basis_bf16_lo = reinterpret_cast<const uint16_t*>(base + o_gbbl);
+    d.fz_basis = fz_ok ? base + o_fzb : nullptr;
+    d.fz_w = fz_ok ? reinterpret_cast<const uint32_t*>(base + o_fzw) : nullptr;
     *out_model = mp.release();
     return SMPLB200_OK;
   } catch (const std::bad_alloc&) {
@@ -617,6 +724,7 @@ int smplb200_forward_launch_count(const SmplB200Model* model, int64_t n, uint32_
   Plan p;
   if (!model || n <= 0 || !resolve_plan(model, n, flags, &p)) return 0;
   (void)with_projection;
+  if (p.prec == SMPLB200_PREC_F16) return 2 + (p.regressed ? 1 : 0);     // k2, fused [, regression]
   const bool chunked = model->chunk > 0 && p.prec != SMPLB200_PREC_FP32 && p.lbs == SMPLB200_LBS_TC &&
                        n > model->chunk;
   const int passes = chunked ? (int)((n + model->chunk - 1) / model->chunk) : 1;
@@ -702,6 +810,31 @@ int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A
                         kp2d, s);
 }
 
+size_t smplb200_blend_skin_workspace_bytes(const SmplB200Model* model, int64_t n) {
+  if (!model || n < 0 || !model->d.fz_basis) return 0;
+  return align_up(fz_coef_image_bytes(n), 256) + align_up(fz_a_image_bytes(n), 256);
+}
+
+int smplb200_blend_skin(const SmplB200Model* model, const float* coef, const float* A, int64_t n,
+                        float* vertices, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!model || n < 0 || (n > 0 && (!coef || !A || !vertices))) return SMPLB200_ERR_INVALID_ARG;
+  if (!model->d.fz_basis) return SMPLB200_ERR_UNSUPPORTED;
+  if (n == 0) return SMPLB200_OK;
+  const size_t need = smplb200_blend_skin_workspace_bytes(model, n);
+  if (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return SMPLB200_ERR_WORKSPACE;
+  DeviceGuard guard(model->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ci = static_cast<uint8_t*>(workspace);
+  uint8_t* ai = ci + align_up(fz_coef_image_bytes(n), 256);
+  const long long total = n * (long long)(kCoefK + kJ * 12);
+  k_pack_fz<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(coef, A, n, model->d.NB, ci, ai);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_fused_tc(model->d, model->num_sms, ci, ai, n, vertices, s));
+  return SMPLB200_OK;
+}
+
 int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, int64_t n,
                             float* joints, const float* cam, float* kp2d, void* stream) {
   if (!model || n < 0 || (n > 0 && (!vertices || !joints))) return SMPLB200_ERR_INVALID_ARG;
@@ -753,6 +886,23 @@ int smplb200_forward_opts(const SmplB200Model* model, const float* betas, const 
   ChainOut out{};
   out.A = A;
   out.joints = p.regressed ? nullptr : jbuf;
+  if (p.prec == SMPLB200_PREC_F16) {
+    // fused path: k2 (operand images, joints, kp2d) -> ONE kernel for blendshapes + skinning
+    out.A = nullptr;
+    out.fz_coef = ws + w.fz_coef;
+    out.fz_a = ws + w.fz_a;
+    if (kp2d != nullptr && !p.regressed) { out.cam = cam; out.kp2d = kp2d; }
+    int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
+    if (st) return st;
+    if (ev_joints && !p.regressed) CU_TRY(cudaEventRecord(ev_joints, s));
+    CU_TRY(launch_fused_tc(model->d, model->num_sms, out.fz_coef, out.fz_a, n, vertices, s));
+    if (p.regressed && (joints || kp2d)) {
+      st = launch_regress(model, vertices, n, jbuf, cam, kp2d, s);
+      if (st) return st;
+      if (ev_joints) CU_TRY(cudaEventRecord(ev_joints, s));
+    }
+    return SMPLB200_OK;
+  }
   if (p.prec == SMPLB200_PREC_FP32) out.coef = coef;
   if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
     out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.coef_hi);
@@ -833,6 +983,14 @@ constexpr long long kBwdFp32TcMinBatch = 256;   // explicit FP32: CUDA-core FMA 
 inline bool bwd_blend_tc(uint32_t flags, long long n) {
   return (flags & SMPLB200_PREC_MASK) != SMPLB200_PREC_FP32 || n >= kBwdFp32TcMinBatch;
 }
+// The fused forward (SMPLB200_PREC_F16) leaves no vposed behind: its backward recomputes A and vposed with
+// the unfused split-bf16 kernels (gradients do not depend on which forward precision produced the outputs).
+inline void bwd_plan(Plan* p, uint32_t* flags) {
+  if (p->prec == SMPLB200_PREC_F16) {
+    p->prec = SMPLB200_PREC_BF16X3;
+    *flags = (*flags & ~SMPLB200_PREC_MASK) | SMPLB200_PREC_BF16X3;
+  }
+}
 inline int bwd_blend_mode(uint32_t flags, const Plan& p) {
   if ((flags & SMPLB200_PREC_MASK) == SMPLB200_PREC_FP32) return kBwdTf32x3;
   if (p.prec == SMPLB200_PREC_FP32 || p.prec == SMPLB200_PREC_BF16X3) return kBwdBf16x3;   // AUTO, BF16X3
@@ -867,6 +1025,7 @@ size_t smplb200_backward_workspace_bytes(const SmplB200Model* model, int64_t n, 
                                          int vertex_path) {
   Plan p;
   if (!model || n < 0 || !resolve_plan(model, n, flags, &p)) return 0;
+  bwd_plan(&p, &flags);
   return carve_bwd(model, n, p, vertex_path != 0, bwd_blend_tc(flags, n)).total;
 }
 
@@ -875,6 +1034,7 @@ int smplb200_backward_launch_count(const SmplB200Model* model, int64_t n, uint32
   Plan p;
   if (!model || n <= 0 || !resolve_plan(model, n, flags, &p)) return 0;
   if (!vertex_path) return 1;                                  // kb2 alone
+  if (p.prec == SMPLB200_PREC_F16) return 5;                   // the fused forward keeps no vposed: always recomputed
   return (reuse_forward_workspace && model->chunk == 0) ? 3 : 5;   // [k2, k1,] kb3, kb1, kb2
 }
 
@@ -890,6 +1050,8 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
   if ((g_kp2d || g_cam) && !cam) return SMPLB200_ERR_INVALID_ARG;
   Plan p;
   if (!resolve_plan(model, n, flags, &p)) return SMPLB200_ERR_INVALID_ARG;
+  if (p.prec == SMPLB200_PREC_F16) { forward_workspace = nullptr; forward_workspace_bytes = 0; }
+  bwd_plan(&p, &flags);
   if (p.regressed && g_kp2d && !joints_fwd) return SMPLB200_ERR_INVALID_ARG;
   const bool vertex_path = g_vertices != nullptr || (p.regressed && (g_joints || g_kp2d));
   const bool tc = bwd_blend_tc(flags, n);

@@ -113,7 +113,8 @@ class SMPL(nn.Module):
              ``posedirs[207,3V]``, ``J_regressor[V,24]``, ``weights[V,24]``, ``parents[24]`` in the
              eager layer's layouts -- or the official SMPL file layout
              (``shapedirs[V,3,NB]``, ``J_regressor[24,V]`` dense/sparse, ``kintree_table``), see model_io.
-      precision: 'auto' | 'fp32' | 'bf16' | 'tf32' | 'bf16x3'  (blendshape operands)
+      precision: 'auto' | 'fp32' | 'bf16' | 'tf32' | 'bf16x3' | 'f16'  (blendshape operands; 'f16' = the
+             fused blendshapes+skinning kernel, stated vertex bound 5e-5 m)
       joints: 'kinematic' (J_posed of the chain, default) | 'regressed' (HMR-style, from vertices)
       rotate_base: HMR's root pre-rotation by diag(1,-1,-1); default False
       lbs: 'auto' | 'fma' | 'tc' | 'dense'  (skinning kernel)
@@ -386,6 +387,22 @@ def lbs(smpl: SMPL, vposed, A, joints=None, cam=None, flags=None):
             _ptr(joints), _ptr(cam), _ptr(kp2d), _ptr(ws), wsb, flags, _stream_ptr(device)),
             "smplb200_lbs")
     return verts if kp2d is None else (verts, kp2d)
+
+
+def blend_skin(smpl: SMPL, coef, A):
+    """k1 + k3 fused (precision 'f16') -> vertices[N,V,3] from k2's coef[N,224] and A[N,24,12]."""
+    device, n = coef.device, int(coef.shape[0])
+    h = smpl.handle(device)
+    with torch.cuda.device(device):
+        verts = torch.empty((n, smpl.num_verts, 3), dtype=torch.float32, device=device)
+        wsb = int(capi.lib().smplb200_blend_skin_workspace_bytes(h.ptr, n))
+        if wsb == 0:
+            raise RuntimeError("fused blendshapes+skinning kernel unavailable for this model (needs <= 13 betas)")
+        ws = torch.empty(wsb, dtype=torch.uint8, device=device)
+        capi.check(capi.lib().smplb200_blend_skin(
+            h.ptr, _ptr(coef.contiguous()), _ptr(A.contiguous()), n, _ptr(verts), _ptr(ws), wsb,
+            _stream_ptr(device)), "smplb200_blend_skin")
+    return verts
 
 
 def regress_joints(smpl: SMPL, vertices, cam=None):

@@ -54,6 +54,10 @@ enum {
 #define SMPLB200_PREC_BF16   2u  /* tcgen05 kind::f16, bf16 operands                          */
 #define SMPLB200_PREC_TF32   3u  /* tcgen05 kind::tf32                                        */
 #define SMPLB200_PREC_BF16X3 4u  /* tcgen05, 3-term split bf16 (hi*hi + hi*lo + lo*hi)        */
+#define SMPLB200_PREC_F16    5u  /* FUSED blendshapes + skinning kernel (no v_posed round trip through HBM), fp16
+                                    operands: pose rows one MMA, shape rows + template exact 3-term split, skinning
+                                    blend 3-term split.  Measured max vertex error 1.9e-5 m (stated bound 5e-5 m;
+                                    TF32 operands: 1.9e-4).  Needs NB <= 13; the LBS flag must be AUTO or TC.     */
 #define SMPLB200_PREC_MASK   0x7u
 /* joint output: kinematic J_posed (default) or HMR-style regression from skinned vertices   */
 #define SMPLB200_JOINTS_KINEMATIC 0u
@@ -213,6 +217,14 @@ size_t smplb200_lbs_workspace_bytes(const SmplB200Model* model, int64_t n, uint3
 int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A, int64_t n,
                  float* vertices, const float* joints_in, const float* cam, float* kp2d,
                  void* workspace, size_t workspace_bytes, uint32_t flags, void* stream);
+
+/* k1 + k3 fused (SMPLB200_PREC_F16; csrc/k_fused_tc.cuh): coef[N,224] and A[N,J,12] (as written by
+ * smplb200_pose_chain) -> vertices[N,V,3] in ONE tcgen05 kernel, accumulators in tensor memory, no v_posed
+ * intermediate.  `workspace`: smplb200_blend_skin_workspace_bytes(model, n) of 256-byte aligned scratch for
+ * the fp16 operand images (inside smplb200_forward k2 writes those images directly).                       */
+size_t smplb200_blend_skin_workspace_bytes(const SmplB200Model* model, int64_t n);
+int smplb200_blend_skin(const SmplB200Model* model, const float* coef, const float* A, int64_t n,
+                        float* vertices, void* workspace, size_t workspace_bytes, void* stream);
 
 /* joints regressed from skinned vertices (SMPLB200_JOINTS_REGRESSED) + optional projection. */
 int smplb200_regress_joints(const SmplB200Model* model, const float* vertices, int64_t n,
