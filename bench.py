@@ -284,8 +284,11 @@ def main():
     ap.add_argument("--bodies-per-gpu", type=int, default=BODIES_PER_GPU)
     ap.add_argument("--total-bodies", type=int, default=0,
                     help="strong scaling: fix the whole job's batch (SURVEY C4: 65536) and shard it over the ranks")
-    ap.add_argument("--precision", default="auto", choices=["fp32", "bf16", "tf32", "bf16x3", "auto"],
-                    help="blendshape MMA operands; auto (default) = the near-fp32 split mode at this batch")
+    ap.add_argument("--precision", default="f16", choices=["fp32", "bf16", "tf32", "bf16x3", "auto", "f16"],
+                    help="blendshape MMA operands.  f16 (default) = the FUSED blendshapes+skinning kernel, fp16 operands "
+                         "(BASELINE configs[2] is the reduced-precision tensor-core regime: 'TF32/BF16 blendshapes ... fp32 "
+                         "LBS'; f16 is 10x / 70x more accurate than those, error measured in the run); auto / bf16x3 = the "
+                         "near-fp32 split mode (unfused kernels)")
     ap.add_argument("--lbs", default="auto", choices=["fma", "tc", "dense", "auto"])
     ap.add_argument("--weights", default="sparse", choices=["sparse", "dense"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -453,19 +456,24 @@ def main():
 
         # ---- per-kernel timing (rank 0) for the roofline ------------------------------------
         kernels = {}
+        fused = layer.flags & capi.PREC_MASK == capi.PREC_F16
         if rank == 0:
-            flags = layer.flags
-            coef, A, joints = ops.pose_chain(layer, tb, tp)
-            vposed = ops.blendshapes(layer, coef, flags=flags)
             it = args.kernel_iters
-            h = layer.handle(dev)
             lib = capi.lib()
             s = torch.cuda.current_stream(dev).cuda_stream
+            # the unfused tensor-core kernels (k1 split-bf16, k3 3xTF32): timed for every run so the table is complete
+            ulayer = layer if not fused else SMPL(model, precision="bf16x3", lbs="tc").to(dev)
+            flags = ulayer.flags
+            coef, A, joints = ops.pose_chain(ulayer, tb, tp)
+            vposed = ops.blendshapes(ulayer, coef, flags=flags)
+            h = ulayer.handle(dev)
             verts = torch.empty((n, layer.num_verts, 3), device=dev)
             kp = torch.empty((n, 24, 2), device=dev)
             ws = torch.empty(max(h.workspace_bytes(n, flags), 256), dtype=torch.uint8, device=dev)
             wsb = int(lib.smplb200_blendshapes_workspace_bytes(h.ptr, n, flags))
             wsl = int(lib.smplb200_lbs_workspace_bytes(h.ptr, n, flags))
+            wsf = int(lib.smplb200_blend_skin_workspace_bytes(h.ptr, n))
+            wsf_t = torch.empty(max(wsf, 256), dtype=torch.uint8, device=dev)
 
             def k2():
                 capi.check(lib.smplb200_pose_chain(h.ptr, tb.data_ptr(), tp.data_ptr(), n, coef.data_ptr(),
@@ -480,11 +488,19 @@ def main():
                                             joints.data_ptr(), tc.data_ptr(), kp.data_ptr(), ws.data_ptr(),
                                             wsl, flags, s), "k3")
 
+            def kf():  # fused kernel ALONE: operand images packed once below, reused (coef = A = NULL)
+                capi.check(lib.smplb200_blend_skin(h.ptr, None, None, n, verts.data_ptr(), wsf_t.data_ptr(), wsf, s), "fused")
+
             def whole():    # the forward alone on ONE stream (no second batch in flight)
                 layer(tb, tp, tc)
 
-            for name, fn, byts in (("k2_pose_chain", k2, BYTES_K2), ("k1_blendshapes", k1, BYTES_K1),
-                                   ("k3_lbs", k3, BYTES_K3), ("forward_one_stream", whole, BYTES_E2E)):
+            todo = [("k2_pose_chain", k2, BYTES_K2), ("k1_blendshapes", k1, BYTES_K1), ("k3_lbs", k3, BYTES_K3),
+                    ("forward_one_stream", whole, BYTES_E2E)]
+            if wsf:
+                capi.check(lib.smplb200_blend_skin(h.ptr, coef.data_ptr(), A.data_ptr(), n, verts.data_ptr(),
+                                                   wsf_t.data_ptr(), wsf, s), "fused (pack)")
+                todo.insert(3, ("fused_blend_skin", kf, BYTES_E2E))
+            for name, fn, byts in todo:
                 for _ in range(3):
                     fn()
                 dt = time_loop(fn, it, torch) / it
@@ -496,9 +512,9 @@ def main():
             from oracle.smpl_ref import smpl_forward_chunked
             na = min(n, 512)
             ref = smpl_forward_chunked(model, betas[:na], pose[:na], cam[:na], chunk=256, dtype=torch.float32)
-            bound = {"fp32": 1e-6, "bf16x3": 1e-5, "auto": 1e-5, "tf32": 5e-4, "bf16": 4e-3}
-            for prec in ("auto", "fp32", "bf16x3", "tf32", "bf16"):
-                lay = layer if prec == args.precision else SMPL(model, precision=prec, lbs=args.lbs).to(dev)
+            bound = {"fp32": 1e-6, "bf16x3": 1e-5, "auto": 1e-5, "f16": 5e-5, "tf32": 5e-4, "bf16": 4e-3}
+            for prec in ("f16", "auto", "fp32", "bf16x3", "tf32", "bf16"):
+                lay = layer if prec == args.precision else SMPL(model, precision=prec, lbs=args.lbs if prec != "f16" else "auto").to(dev)
                 v, j, k = lay(tb[:na], tp[:na], tc[:na])
                 ev = (v.cpu() - ref[0]).abs().max().item()
                 ej = (j.cpu() - ref[1]).abs().max().item()
@@ -572,7 +588,7 @@ def main():
         hbm = peaks["hbm_gbs"]
         tf_k1 = FLOPS_K1 * n / (k1["us"] * 1e-6) * 1e-12
         k1_roof = {"bound": "hbm", "achieved": k1["gbs"], "peak": hbm, "unit": "GB/s",
-                   "frac": k1["gbs"] / hbm, "us": k1["us"], "bytes_per_body": BYTES_K1,
+                   "frac": k1["gbs"] / hbm, "us": k1["us"], "bytes_per_body": BYTES_K1, "operands": "bf16x3 (unfused path)",
                    "tensor_tflops": tf_k1, "tensor_frac_of_bf16_burst": tf_k1 / peaks["bf16_tflops"],
                    "note": "K=217: write-bound; algorithmic flops (the split modes execute 2-3x as many MMAs)"}
         if run_peaks:
@@ -581,7 +597,7 @@ def main():
         one = kernels["forward_one_stream"]
         roof_k = {
             "k3_lbs": {"bound": "hbm", "achieved": k3["gbs"], "peak": hbm, "unit": "GB/s",
-                       "frac": k3["gbs"] / hbm, "us": k3["us"], "bytes_per_body": BYTES_K3},
+                       "frac": k3["gbs"] / hbm, "us": k3["us"], "bytes_per_body": BYTES_K3, "note": "unfused path (k_lbs_tc)"},
             "k1_blendshapes": k1_roof,
             "k2_pose_chain": {"bound": "latency", "us": kernels["k2_pose_chain"]["us"],
                               "achieved": kernels["k2_pose_chain"]["gbs"], "unit": "GB/s"},
@@ -592,8 +608,22 @@ def main():
                            "unit": "GB/s", "frac": BYTES_E2E * value / world * 1e-9 / hbm,
                            "bytes_per_body": BYTES_E2E, "note": "the `value` leg (two batches in flight)"},
         }
+        if "fused_blend_skin" in kernels:
+            kf_ = kernels["fused_blend_skin"]
+            tf_f = (FLOPS_K1 + 3_968_640) * n / (kf_["us"] * 1e-6) * 1e-12
+            roof_k["fused_blend_skin"] = {
+                "bound": "hbm", "achieved": kf_["gbs"], "peak": hbm, "unit": "GB/s", "frac": kf_["gbs"] / hbm,
+                "us": kf_["us"], "bytes_per_body": BYTES_E2E,
+                "tensor_tflops_algorithmic": tf_f,
+                "note": "k_fused_tc alone (blendshapes + skinning in one kernel); algorithmic bytes = the whole step's "
+                        "83,500 B/body (340 in + 83,160 out): the kernel has no other mandatory HBM traffic"}
+            if run_peaks:
+                roof_k["fused_blend_skin"]["tensor_frac_of_bf16_peak_this_run"] = tf_f / run_peaks["bf16_tflops"]
+        dom = "fused_blend_skin" if fused else "k3_lbs"
+        dom_kernel = "k_fused_tc" if fused else ("k_lbs_tc" if n >= capi.TC_LBS_MIN_BATCH else "k_lbs_fma")
+        dom_bytes = BYTES_E2E if fused else BYTES_K3
         launches_per_step = layer.launch_count(n, True, dev) + (2 if (exchange is not None and exchange.transport == "peer") else 0)
-        traffic, traffic_src = ncu_traffic("k_lbs_tc") if n == BODIES_PER_GPU else (None, None)
+        traffic, traffic_src = ncu_traffic(dom_kernel) if n == BODIES_PER_GPU else (None, None)
         pcie_gbs = (h2d + d2h) / e2e_dt * 1e-9
         config = bench_config(n, world, args, strong)
         line = {
@@ -622,9 +652,9 @@ def main():
                                   "note": "same call returning joints + kp2d only; vertices stay device-resident"},
             "gpu_launches": launches_per_step * args.steps,
             "gpu_launches_per_step": launches_per_step,
-            "roofline": {**roof_k["k3_lbs"], "kernel": "k_lbs_tc" if n >= capi.TC_LBS_MIN_BATCH else "k_lbs_fma",
+            "roofline": {**roof_k[dom], "kernel": dom_kernel,
                          "peak_source": peaks["source"] + " (MEASURED_PEAKS.json hbm_gbs)",
-                         "algorithmic_bytes_per_launch": BYTES_K3 * n,
+                         "algorithmic_bytes_per_launch": dom_bytes * n,
                          "traffic": traffic, "traffic_source": traffic_src},
             "peaks_this_run": run_peaks,
             "variants_same_workload": variants,

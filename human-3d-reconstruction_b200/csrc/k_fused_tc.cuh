@@ -32,11 +32,11 @@
 //     exact in the fp32 accumulator): ~2e-7, the same fp32-class fidelity as k_lbs_tc's 3xTF32.
 //
 // Schedule: persistent CTAs (one per SM) own equal contiguous ranges of the tile-major unit list.
-// Warp roles (384 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warp 1 = MMA issuer
-// (warp-uniform, one elected lane), warp 2 = bulk-TMA producer of the A' images, warp 3 idle,
-// warps 4..11 = epilogue: TMEM lane quarter q = warp % 4, slot e = (warp - 4) / 4 takes the sub-blocks
-// s = e, e + 2, ... and owns T buffer e.  The D MMAs of unit i+1 are interleaved between the blend MMAs of
-// unit i, so the tensor pipe never waits for an epilogue to drain a whole unit.
+// Warp roles (384 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warp 1 = blend-MMA issuer,
+// warp 2 = bulk-TMA producer of the A' images, warp 3 = D-MMA issuer (both issuers warp-uniform, one elected
+// lane), warps 4..11 = epilogue: TMEM lane quarter q = warp % 4, slot e = (warp - 4) / 4 takes the sub-blocks
+// s = e, e + 2, ... and owns T buffer e.  The D issuer runs up to one unit ahead (D is double-buffered), so
+// the tensor pipe interleaves the next unit's blendshape MMAs with this unit's blend MMAs.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -172,109 +172,109 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (whole warp convergent, one elected lane issues) =====
+  } else if (warp == 3) {
+    // ===== D-MMA issuer (blendshapes): whole warp convergent, one elected lane issues.  Its own warp, so
+    // the scalar bookkeeping of the D chunks never sits in the blend issuer's loop (a single issuer doing both
+    // was the kernel's critical path: ~1300 clk of index math, waits and descriptor building per sub-block).
+    // All counters are incremental: no division / modulo in the loop. =====
     const uint32_t basis_addr = ptx::smem_u32(sBasis);
-    const uint32_t tmem_w = tmem_base + kFzTmemW;
-    long long d_tile = -1;          // tile whose basis the D MMAs currently read
-    int d_tiles = 0;                // basis tiles consumed so far (phase of bar_bfull)
-    int c_it = 0;                   // coef chunks consumed so far
-    int a_it = 0;                   // A' images consumed so far
-    int t_cnt[2] = {0, 0};          // blend accumulators issued per T buffer
-    long long w_tile = -1;
-    int w_tiles = 0;
-
-    // D MMAs of chunk `c` of unit `i` (all three planes)
-    auto issue_d_chunk = [&](int i, int c) {
-      const long long u = u0 + i, tile = u / nblk;
+    const uint32_t coef_addr = ptx::smem_u32(sCoef);
+    constexpr uint32_t kLboA = 128 * 16, kLboB = kFzBodies * 16, kSbo = 128;
+    // descriptor of address 0 for each operand family; the 14-bit address field (addr >> 4) is added per MMA
+    const uint64_t descA0 = ptx::make_smem_desc(0, kLboA, kSbo), descB0 = ptx::make_smem_desc(0, kLboB, kSbo);
+    auto dA = [&](uint32_t addr) { return descA0 | (uint64_t)((addr >> 4) & 0x3fffu); };
+    auto dB = [&](uint32_t addr) { return descB0 | (uint64_t)((addr >> 4) & 0x3fffu); };
+    int blk = (int)(u0 % nblk);                 // body block of the current unit (one division, outside the loop)
+    bool new_tile = true;                       // the first unit always loads a basis tile
+    uint32_t b_phase = 0;                       // parity of the next bar_bfull wait
+    int cs = 0; uint32_t c_phase = 0;           // coef ring stage / parity
+    for (int i = 0; i < nunits; ++i) {
       const int a = i & 1;
-      if (c == 0) {
-        if (tile != d_tile) {                      // first D MMA on a new basis tile
-          ptx::mbar_wait(bar_bfull, d_tiles & 1);
-          ++d_tiles;
-          d_tile = tile;
-        }
-        ptx::mbar_wait(bar_dempty + a, ((i >> 1) & 1) ^ 1);   // epilogue drained this buffer (unit i-2)
-      }
-      const int s = c_it % kFzCoefStages;
-      ptx::mbar_wait(bar_cfull + s, (c_it / kFzCoefStages) & 1);
-      ++c_it;
-      ptx::tc_fence_after();
-      const uint32_t c_addr = ptx::smem_u32(sCoef + (size_t)s * kFzCoefStage);
-      if (ptx::elect_one()) {
-        constexpr uint32_t kLboA = 128 * 16, kLboB = kFzBodies * 16, kSbo = 128;
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          const uint32_t d_tmem = tmem_base + kFzTmemD + (a * 3 + p) * kFzBodies;
-          const uint32_t hi_p = basis_addr + p * kFzPlaneHi;
+      const bool last_of_tile = (i + 1 == nunits) || (blk + 1 == nblk);
+      if (new_tile) { ptx::mbar_wait(bar_bfull, b_phase); b_phase ^= 1; }
+      ptx::mbar_wait(bar_dempty + a, ((i >> 1) & 1) ^ 1);     // epilogue drained this buffer (unit i-2)
+      const uint32_t d_tmem0 = tmem_base + kFzTmemD + a * 3 * kFzBodies;
+#pragma unroll 1
+      for (int c = 0; c < kFzChunks; ++c) {
+        ptx::mbar_wait(bar_cfull + cs, c_phase);
+        ptx::tc_fence_after();
+        const uint32_t c_addr = coef_addr + cs * kFzCoefStage;
+        if (ptx::elect_one()) {
           if (c == 0) {
-            const uint32_t lo_p = basis_addr + 3 * kFzPlaneHi + p * kFzPlaneLo;
-            const uint64_t c_lo = ptx::make_smem_desc(c_addr, kLboB, kSbo);
-            const uint64_t c_h0 = ptx::make_smem_desc(c_addr + kFzCoefLo, kLboB, kSbo);
-            const uint64_t c_h1 = ptx::make_smem_desc(c_addr + kFzCoefLo + 2048, kLboB, kSbo);
-            const uint64_t b_h0 = ptx::make_smem_desc(hi_p, kLboA, kSbo);
-            const uint64_t b_h1 = ptx::make_smem_desc(hi_p + 2 * kLboA, kLboA, kSbo);
-            const uint64_t b_lo = ptx::make_smem_desc(lo_p, kLboA, kSbo);
-            ptx::mma_bf16(d_tmem, b_h0, c_h0, kFzIdescD, 0u);   // shape rows: hi*hi
-            ptx::mma_bf16(d_tmem, b_h0, c_lo, kFzIdescD, 1u);   //             hi(basis)*lo(coef)
-            ptx::mma_bf16(d_tmem, b_lo, c_h0, kFzIdescD, 1u);   //             lo(basis)*hi(coef)
-            ptx::mma_bf16(d_tmem, b_h1, c_h1, kFzIdescD, 1u);   // first pose k-step
-          } else {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t bd = ptx::make_smem_desc(hi_p + (uint32_t)(2 * c + ks) * 2 * kLboA, kLboA, kSbo);
-              const uint64_t cd = ptx::make_smem_desc(c_addr + ks * 2048, kLboB, kSbo);
-              ptx::mma_bf16(d_tmem, bd, cd, kFzIdescD, 1u);
+            for (int p = 0; p < 3; ++p) {
+              const uint32_t d_tmem = d_tmem0 + p * kFzBodies;
+              const uint32_t hi_p = basis_addr + p * kFzPlaneHi;
+              const uint32_t lo_p = basis_addr + 3 * kFzPlaneHi + p * kFzPlaneLo;
+              ptx::mma_bf16(d_tmem, dA(hi_p), dB(c_addr + kFzCoefLo), kFzIdescD, 0u);                     // shape rows: hi*hi
+              ptx::mma_bf16(d_tmem, dA(hi_p), dB(c_addr), kFzIdescD, 1u);                                 //   hi(basis)*lo(coef)
+              ptx::mma_bf16(d_tmem, dA(lo_p), dB(c_addr + kFzCoefLo), kFzIdescD, 1u);                     //   lo(basis)*hi(coef)
+              ptx::mma_bf16(d_tmem, dA(hi_p + 2 * kLboA), dB(c_addr + kFzCoefLo + 2048), kFzIdescD, 1u);  // first pose k-step
+            }
+          } else {
+            const uint32_t k_off = (uint32_t)(2 * c) * 2 * kLboA;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              const uint32_t d_tmem = d_tmem0 + p * kFzBodies;
+              const uint32_t hi_p = basis_addr + p * kFzPlaneHi + k_off;
+              ptx::mma_bf16(d_tmem, dA(hi_p), dB(c_addr), kFzIdescD, 1u);
+              ptx::mma_bf16(d_tmem, dA(hi_p + 2 * kLboA), dB(c_addr + 2048), kFzIdescD, 1u);
             }
           }
+          ptx::tc_commit(bar_cempty + cs);
+          if (c == kFzChunks - 1) {
+            ptx::tc_commit(bar_dfull + a);
+            if (last_of_tile) ptx::tc_commit(bar_bfree);     // the producer may overwrite the basis tile
+          }
         }
-        ptx::tc_commit(bar_cempty + s);
-        if (c == kFzChunks - 1) {
-          ptx::tc_commit(bar_dfull + a);
-          // last unit on this basis tile: tell the producer when its D MMAs have retired
-          const bool last_of_tile = (i + 1 == nunits) || ((u0 + i + 1) / nblk != tile);
-          if (last_of_tile) ptx::tc_commit(bar_bfree);
-        }
+        __syncwarp();
+        if (++cs == kFzCoefStages) { cs = 0; c_phase ^= 1; }
       }
-      __syncwarp();
-    };
-
-    for (int c = 0; c < kFzChunks && nunits > 0; ++c) issue_d_chunk(0, c);
+      new_tile = (blk + 1 == nblk);
+      blk = new_tile ? 0 : blk + 1;
+    }
+  } else if (warp == 1) {
+    // ===== blend-MMA issuer (skinning): one 6-MMA group per 4-body sub-block =====
+    const uint32_t tmem_w = tmem_base + kFzTmemW;
+    const uint32_t a_addr0 = ptx::smem_u32(sA);
+    constexpr uint32_t kLbo = kFzNT * 16, kSbo = 128;
+    const uint64_t desc0 = ptx::make_smem_desc(0, kLbo, kSbo);
+    auto dS = [&](uint32_t addr) { return desc0 | (uint64_t)((addr >> 4) & 0x3fffu); };
+    int blk = (int)(u0 % nblk);
+    bool new_tile = true;
+    uint32_t w_phase = 0;
+    int as = 0; uint32_t a_phase = 0;           // A' ring stage / parity
+    uint32_t te_phase = 1;                      // parity for bar_tempty waits: both buffers start free
     for (int i = 0; i < nunits; ++i) {
-      const long long tile = (u0 + i) / nblk;
-      if (tile != w_tile) {                        // blend MMAs of a new tile need its W' rows in TMEM
-        ptx::mbar_wait(bar_w, w_tiles & 1);
-        ++w_tiles;
-        w_tile = tile;
-      }
+      if (new_tile) { ptx::mbar_wait(bar_w, w_phase); w_phase ^= 1; }     // the tile's W' rows are in TMEM
+#pragma unroll 1
       for (int sb = 0; sb < kFzSubs; ++sb) {
-        const int e = sb & 1, s = a_it % kFzAStages;
-        ptx::mbar_wait(bar_tempty + e, (t_cnt[e] & 1) ^ 1);
-        ptx::mbar_wait(bar_afull + s, (a_it / kFzAStages) & 1);
-        ++a_it; ++t_cnt[e];
+        const int e = sb & 1;
+        ptx::mbar_wait(bar_tempty + e, te_phase);
+        ptx::mbar_wait(bar_afull + as, a_phase);
         ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(sA + (size_t)s * kFzAImage);
         if (ptx::elect_one()) {
-          constexpr uint32_t kLbo = kFzNT * 16, kSbo = 128;
+          const uint32_t a_addr = a_addr0 + as * kFzAImage;
           const uint32_t t_tmem = tmem_base + kFzTmemT + e * kFzNT;
-          const uint64_t s0 = ptx::make_smem_desc(a_addr, kLbo, kSbo);              // A_hi joints 0..15
-          const uint64_t s1 = ptx::make_smem_desc(a_addr + 2 * kLbo, kLbo, kSbo);   // A_hi 16..23 | (A_lo 0..7 x 0)
-          const uint64_t s2 = ptx::make_smem_desc(a_addr + 3 * kLbo, kLbo, kSbo);   // A_lo joints 0..15
-          const uint64_t s3 = ptx::make_smem_desc(a_addr + 5 * kLbo, kLbo, kSbo);   // A_lo 16..23 | zeros
+          const uint64_t s0 = dS(a_addr);              // A_hi joints 0..15
+          const uint64_t s1 = dS(a_addr + 2 * kLbo);   // A_hi 16..23 | (A_lo 0..7 x 0)
+          const uint64_t s2 = dS(a_addr + 3 * kLbo);   // A_lo joints 0..15
+          const uint64_t s3 = dS(a_addr + 5 * kLbo);   // A_lo 16..23 | zeros
           ptx::mma_bf16_ts(t_tmem, tmem_w, s0, kFzIdescT, 0u);        // W_hi * A_hi
           ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s1, kFzIdescT, 1u);
           ptx::mma_bf16_ts(t_tmem, tmem_w, s2, kFzIdescT, 1u);        // W_hi * A_lo
           ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s3, kFzIdescT, 1u);
           ptx::mma_bf16_ts(t_tmem, tmem_w + 16, s0, kFzIdescT, 1u);   // W_lo * A_hi
           ptx::mma_bf16_ts(t_tmem, tmem_w + 24, s1, kFzIdescT, 1u);
-          ptx::tc_commit(bar_aempty + s);
+          ptx::tc_commit(bar_aempty + as);
           ptx::tc_commit(bar_tfull + e);
         }
         __syncwarp();
-        // the next unit's D MMAs, one K chunk after every second blend: by the time chunk 0 asks for the D
-        // buffer the epilogue has had two blend results of THIS unit to chew on, so it is never starved
-        if ((sb & 1) == 1 && (sb >> 1) < kFzChunks && i + 1 < nunits) issue_d_chunk(i + 1, sb >> 1);
+        if (++as == kFzAStages) { as = 0; a_phase ^= 1; }
+        if (e == 1) te_phase ^= 1;              // both buffers have been reused once more
       }
+      new_tile = (blk + 1 == nblk);
+      blk = new_tile ? 0 : blk + 1;
     }
   } else if (warp >= kFzEpiWarp0) {
     // ===== epilogue: slot e, lane quarter q =====

@@ -817,7 +817,8 @@ size_t smplb200_blend_skin_workspace_bytes(const SmplB200Model* model, int64_t n
 
 int smplb200_blend_skin(const SmplB200Model* model, const float* coef, const float* A, int64_t n,
                         float* vertices, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!model || n < 0 || (n > 0 && (!coef || !A || !vertices))) return SMPLB200_ERR_INVALID_ARG;
+  const bool repack = coef != nullptr || A != nullptr;     // both NULL: reuse the images a previous call left in `workspace`
+  if (!model || n < 0 || (n > 0 && !vertices) || (repack && (!coef || !A))) return SMPLB200_ERR_INVALID_ARG;
   if (!model->d.fz_basis) return SMPLB200_ERR_UNSUPPORTED;
   if (n == 0) return SMPLB200_OK;
   const size_t need = smplb200_blend_skin_workspace_bytes(model, n);
@@ -828,9 +829,11 @@ int smplb200_blend_skin(const SmplB200Model* model, const float* coef, const flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* ci = static_cast<uint8_t*>(workspace);
   uint8_t* ai = ci + align_up(fz_coef_image_bytes(n), 256);
-  const long long total = n * (long long)(kCoefK + kJ * 12);
-  k_pack_fz<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(coef, A, n, model->d.NB, ci, ai);
-  CU_TRY(cudaGetLastError());
+  if (repack) {
+    const long long total = n * (long long)(kCoefK + kJ * 12);
+    k_pack_fz<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(coef, A, n, model->d.NB, ci, ai);
+    CU_TRY(cudaGetLastError());
+  }
   CU_TRY(launch_fused_tc(model->d, model->num_sms, ci, ai, n, vertices, s));
   return SMPLB200_OK;
 }

@@ -221,7 +221,9 @@ int smplb200_lbs(const SmplB200Model* model, const float* vposed, const float* A
 /* k1 + k3 fused (SMPLB200_PREC_F16; csrc/k_fused_tc.cuh): coef[N,224] and A[N,J,12] (as written by
  * smplb200_pose_chain) -> vertices[N,V,3] in ONE tcgen05 kernel, accumulators in tensor memory, no v_posed
  * intermediate.  `workspace`: smplb200_blend_skin_workspace_bytes(model, n) of 256-byte aligned scratch for
- * the fp16 operand images (inside smplb200_forward k2 writes those images directly).                       */
+ * the fp16 operand images (inside smplb200_forward k2 writes those images directly).  `coef` and `A` may
+ * BOTH be NULL: the images a previous call left in `workspace` (same n) are reused and only the fused
+ * kernel is launched (kernel-only timing).                                                                 */
 size_t smplb200_blend_skin_workspace_bytes(const SmplB200Model* model, int64_t n);
 int smplb200_blend_skin(const SmplB200Model* model, const float* coef, const float* A, int64_t n,
                         float* vertices, void* workspace, size_t workspace_bytes, void* stream);
