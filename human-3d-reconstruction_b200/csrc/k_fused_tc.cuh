@@ -32,10 +32,10 @@
 //     exact in the fp32 accumulator): ~2e-7, the same fp32-class fidelity as k_lbs_tc's 3xTF32.
 //
 // Schedule: persistent CTAs (one per SM) own equal contiguous ranges of the tile-major unit list.
-// Warp roles (384 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warp 1 = blend-MMA issuer,
-// warp 2 = bulk-TMA producer of the A' images, warp 3 = D-MMA issuer (both issuers warp-uniform, one elected
-// lane), warps 4..11 = epilogue: TMEM lane quarter q = warp % 4, slot e = (warp - 4) / 4 takes the sub-blocks
-// s = e, e + 2, ... and owns T buffer e.  The D issuer runs up to one unit ahead (D is double-buffered), so
+// Warp roles (416 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warps 1 and 12 = blend-MMA
+// issuers of T buffer 0 / 1, warp 2 = bulk-TMA producer of the A' images, warp 3 = D-MMA issuer (all issuers
+// warp-uniform, one elected lane), warps 4..11 = epilogue: TMEM lane quarter q = warp % 4, slot
+// e = (warp - 4) / 4 takes the sub-blocks s = e, e + 2, ... and owns T buffer e.  The D issuer runs up to one unit ahead (D is double-buffered), so
 // the tensor pipe interleaves the next unit's blendshape MMAs with this unit's blend MMAs.
 #pragma once
 #include <cuda_fp16.h>
@@ -51,8 +51,8 @@ constexpr int kFzSub = 4;                           // bodies per blend sub-bloc
 constexpr int kFzSubs = kFzBodies / kFzSub;         // 16
 constexpr int kFzNT = kFzSub * 12;                  // 48: N of the blend MMAs
 constexpr int kFzShapeK = 16;                       // K rows 0..15: betas | template pieces | 0
-constexpr int kFzThreads = 384;
-constexpr int kFzEpiWarp0 = 4, kFzEpiWarps = 8;
+constexpr int kFzThreads = 416;                     // 13 warps, see "Warp roles"
+constexpr int kFzEpiWarp0 = 4, kFzEpiWarps = 8, kFzWarpT1 = 12;   // warp 12: blend issuer of slot 1
 constexpr uint32_t kFzPlaneHi = kCoefK * 128 * 2;               // 57,344
 constexpr uint32_t kFzPlaneLo = kFzShapeK * 128 * 2;            // 4,096
 constexpr uint32_t kFzBasisBytes = 3 * (kFzPlaneHi + kFzPlaneLo);   // 184,320 per vertex tile
@@ -62,12 +62,12 @@ constexpr int kFzChunks = 7;                                    // K chunks per 
 constexpr uint32_t kFzCoefStage = kFzCoefLo + 2 * 2048;         // 6,144 (chunk 0 carries the lo rows too)
 constexpr int kFzCoefStages = 3;
 constexpr uint32_t kFzAImage = 7 * kFzNT * 16;                  // 5,376: [A_hi 3 chunks | A_lo 3 chunks | 0]
-constexpr int kFzAStages = 3;
+constexpr int kFzAStages = 2;                                   // PER SLOT: each blend issuer has its own ring
 constexpr uint32_t kFzOffCoef = kFzBasisBytes;
 constexpr uint32_t kFzOffA = kFzOffCoef + kFzCoefStages * kFzCoefStage;
-constexpr uint32_t kFzOffOut = kFzOffA + kFzAStages * kFzAImage;
-constexpr uint32_t kFzOffBar = kFzOffOut + kFzEpiWarps * 4 * 96 * 4;
-constexpr uint32_t kFzSmemBytes = kFzOffBar + 256;              // 231,424 <= 232,448
+constexpr uint32_t kFzOffOut = kFzOffA + 2 * kFzAStages * kFzAImage;
+constexpr uint32_t kFzOffBar = kFzOffOut + kFzEpiWarps * 2 * 96 * 4;   // per epilogue warp: 2 bodies x 96 floats
+constexpr uint32_t kFzSmemBytes = kFzOffBar + 256;              // 230,656 <= 232,448
 constexpr uint32_t kFzTmemD = 0, kFzTmemT = 2 * 3 * kFzBodies, kFzTmemW = kFzTmemT + 2 * kFzNT;   // 0 | 384 | 480
 constexpr uint32_t kFzIdescD = ptx::make_idesc(ptx::kFmtF16, 128, kFzBodies);
 constexpr uint32_t kFzIdescT = ptx::make_idesc(ptx::kFmtF16, 128, kFzNT);
@@ -102,13 +102,15 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
   uint64_t* bar_w = bars + 2;                          // W' rows of the tile are in TMEM (4 warp arrivals)
   uint64_t* bar_cfull = bars + 3;                      // [3] coef chunk landed
   uint64_t* bar_cempty = bar_cfull + kFzCoefStages;    // [3] MMAs reading it retired
-  uint64_t* bar_afull = bar_cempty + kFzCoefStages;    // [3] A' image landed
-  uint64_t* bar_aempty = bar_afull + kFzAStages;       // [3]
-  uint64_t* bar_dfull = bar_aempty + kFzAStages;       // [2] D accumulators of a unit complete
+  uint64_t* bar_afull = bar_cempty + kFzCoefStages;    // [slot][2] A' image landed
+  uint64_t* bar_aempty = bar_afull + 2 * kFzAStages;   // [slot][2]
+  uint64_t* bar_dfull = bar_aempty + 2 * kFzAStages;   // [2] D accumulators of a unit complete
   uint64_t* bar_dempty = bar_dfull + 2;                // [2] drained by the 8 epilogue warps
   uint64_t* bar_tfull = bar_dempty + 2;                // [2] blend accumulator complete
   uint64_t* bar_tempty = bar_tfull + 2;                // [2] read by the 4 warps of its slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint64_t* bar_wfree = bar_tempty + 2;                // slot-1 epilogue warps are done with the old tile's W' (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_wfree + 1);
+  volatile uint32_t* pace = tmem_slot + 1;             // blend groups issued so far (paces the D issuer, see below)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long u0 = total_units * blockIdx.x / gridDim.x;
@@ -116,9 +118,10 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
   const int nunits = (int)(u1 - u0);
 
   if (warp == 0 && lane == 0) {
-    ptx::mbar_init(bar_bfull, 1); ptx::mbar_init(bar_bfree, 1); ptx::mbar_init(bar_w, 4);
+    *pace = 0u;
+    ptx::mbar_init(bar_bfull, 1); ptx::mbar_init(bar_bfree, 1); ptx::mbar_init(bar_w, 4); ptx::mbar_init(bar_wfree, 4);
     for (int s = 0; s < kFzCoefStages; ++s) { ptx::mbar_init(bar_cfull + s, 1); ptx::mbar_init(bar_cempty + s, 1); }
-    for (int s = 0; s < kFzAStages; ++s) { ptx::mbar_init(bar_afull + s, 1); ptx::mbar_init(bar_aempty + s, 1); }
+    for (int s = 0; s < 2 * kFzAStages; ++s) { ptx::mbar_init(bar_afull + s, 1); ptx::mbar_init(bar_aempty + s, 1); }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_dfull + a, 1); ptx::mbar_init(bar_dempty + a, kFzEpiWarps);
       ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4);
@@ -140,7 +143,7 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
         const long long u = u0 + i, tile = u / nblk;
         const int blk = (int)(u % nblk);
         if (tile != cur_tile) {
-          if (ntile_sw > 0) ptx::mbar_wait(bar_bfree, (ntile_sw - 1) & 1);   // old tile's D MMAs retired
+          if (ntile_sw > 0) ptx::mbar_wait_nohint(bar_bfree, (ntile_sw - 1) & 1);   // old tile's D MMAs retired
           ptx::mbar_arrive_expect_tx(bar_bfull, kFzBasisBytes);
           ptx::bulk_g2s_split(sBasis, basis_tiles + (size_t)tile * kFzBasisBytes, kFzBasisBytes, bar_bfull);
           cur_tile = tile;
@@ -148,8 +151,9 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
         }
         const uint8_t* src = coef_img + (size_t)blk * kFzCoefBlock;
         for (int c = 0; c < kFzChunks; ++c, ++it) {
+          SMPLB200_PROGRESS((i << 8) | c);
           const int s = it % kFzCoefStages;
-          ptx::mbar_wait(bar_cempty + s, ((it / kFzCoefStages) & 1) ^ 1);
+          ptx::mbar_wait_nohint(bar_cempty + s, ((it / kFzCoefStages) & 1) ^ 1);
           const uint32_t bytes = c == 0 ? kFzCoefStage : 4096u;
           const size_t off = c == 0 ? 0 : (size_t)kFzCoefLo + 4096u * c;
           ptx::mbar_arrive_expect_tx(bar_cfull + s, bytes);
@@ -158,15 +162,20 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
       }
     }
   } else if (warp == 2) {
-    // ===== producer 2: tf-split images of the joint transforms, one per 4-body sub-block =====
+    // ===== producer 2: fp16 hi|lo images of the joint transforms, one per 4-body sub-block.  The images
+    // alternate between the two blend issuers, and EACH ISSUER HAS ITS OWN 2-STAGE RING: a ring shared by
+    // two consumers breaks the parity protocol (a waiter must have seen the barrier's previous phase, which
+    // belonged to the other consumer). =====
     if (lane == 0) {
       int it = 0;
       for (int i = 0; i < nunits; ++i) {
         const int blk = (int)((u0 + i) % nblk);
         const uint8_t* src = a_img + (size_t)blk * kFzSubs * kFzAImage;
         for (int sb = 0; sb < kFzSubs; ++sb, ++it) {
-          const int s = it % kFzAStages;
-          ptx::mbar_wait(bar_aempty + s, ((it / kFzAStages) & 1) ^ 1);
+          SMPLB200_PROGRESS((i << 8) | sb);
+          const int k = it >> 1;                           // this slot's image counter
+          const int s = (it & 1) * kFzAStages + (k & 1);   // [slot][stage]
+          ptx::mbar_wait_nohint(bar_aempty + s, ((k >> 1) & 1) ^ 1);
           ptx::mbar_arrive_expect_tx(bar_afull + s, kFzAImage);
           ptx::bulk_g2s(sA + (size_t)s * kFzAImage, src + (size_t)sb * kFzAImage, kFzAImage, bar_afull + s);
         }
@@ -191,71 +200,86 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
     for (int i = 0; i < nunits; ++i) {
       const int a = i & 1;
       const bool last_of_tile = (i + 1 == nunits) || (blk + 1 == nblk);
-      if (new_tile) { ptx::mbar_wait(bar_bfull, b_phase); b_phase ^= 1; }
-      ptx::mbar_wait(bar_dempty + a, ((i >> 1) & 1) ^ 1);     // epilogue drained this buffer (unit i-2)
+      if (new_tile) { ptx::mbar_wait_nohint(bar_bfull, b_phase); b_phase ^= 1; }
+      ptx::mbar_wait_nohint(bar_dempty + a, ((i >> 1) & 1) ^ 1);     // epilogue drained this buffer (unit i-2)
       const uint32_t d_tmem0 = tmem_base + kFzTmemD + a * 3 * kFzBodies;
+      // The unit's 54 MMAs go out as 16 groups of 3 (one MMA per plane; chunk 0 = 4 groups, chunks 1..6 = 2
+      // each).  The tensor pipe executes in issue order, so a whole unit of D MMAs issued at once (2.8 kclk)
+      // would stall every blend MMA -- and with it the epilogue -- behind it.  Group g of unit i is therefore
+      // held back until the blend issuer has issued sub-block g of unit i-1 (`pace`, a monotonic counter in
+      // shared memory): the two MMA streams interleave one group per sub-block.
+      const uint32_t pace_base = (uint32_t)(i - 1) * kFzSubs;
+      int g = 0;
 #pragma unroll 1
       for (int c = 0; c < kFzChunks; ++c) {
-        ptx::mbar_wait(bar_cfull + cs, c_phase);
+        ptx::mbar_wait_nohint(bar_cfull + cs, c_phase);
         ptx::tc_fence_after();
         const uint32_t c_addr = coef_addr + cs * kFzCoefStage;
-        if (ptx::elect_one()) {
-          if (c == 0) {
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-              const uint32_t d_tmem = d_tmem0 + p * kFzBodies;
-              const uint32_t hi_p = basis_addr + p * kFzPlaneHi;
-              const uint32_t lo_p = basis_addr + 3 * kFzPlaneHi + p * kFzPlaneLo;
-              ptx::mma_bf16(d_tmem, dA(hi_p), dB(c_addr + kFzCoefLo), kFzIdescD, 0u);                     // shape rows: hi*hi
-              ptx::mma_bf16(d_tmem, dA(hi_p), dB(c_addr), kFzIdescD, 1u);                                 //   hi(basis)*lo(coef)
-              ptx::mma_bf16(d_tmem, dA(lo_p), dB(c_addr + kFzCoefLo), kFzIdescD, 1u);                     //   lo(basis)*hi(coef)
-              ptx::mma_bf16(d_tmem, dA(hi_p + 2 * kLboA), dB(c_addr + kFzCoefLo + 2048), kFzIdescD, 1u);  // first pose k-step
+        const int ngroups = c == 0 ? 4 : 2;
+#pragma unroll 1
+        for (int m = 0; m < ngroups; ++m, ++g) {
+          SMPLB200_PROGRESS((i << 8) | g);
+          if (i > 0) {
+            const uint32_t need = pace_base + (uint32_t)g + 1u;
+            while ((int32_t)(*pace - need) < 0) __nanosleep(64);
+          }
+          if (ptx::elect_one()) {
+            uint32_t a_off, b_off, acc = 1u;      // byte offsets of the A (basis) / B (coef) k-step of this group
+            if (c == 0) {
+              // m: 0 hi*hi (shape rows)  1 hi(basis)*lo(coef)  2 lo(basis)*hi(coef)  3 first pose k-step
+              a_off = m == 2 ? 3 * kFzPlaneHi : (m == 3 ? 2 * kLboA : 0u);
+              b_off = m == 1 ? 0u : (m == 3 ? kFzCoefLo + 2048u : kFzCoefLo);
+              acc = m != 0;
+            } else {
+              a_off = (uint32_t)(2 * c + m) * 2 * kLboA;
+              b_off = (uint32_t)m * 2048u;
             }
-          } else {
-            const uint32_t k_off = (uint32_t)(2 * c) * 2 * kLboA;
+            const uint32_t plane_stride = (c == 0 && m == 2) ? kFzPlaneLo : kFzPlaneHi;
+            const uint64_t bd = dB(c_addr + b_off);
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-              const uint32_t d_tmem = d_tmem0 + p * kFzBodies;
-              const uint32_t hi_p = basis_addr + p * kFzPlaneHi + k_off;
-              ptx::mma_bf16(d_tmem, dA(hi_p), dB(c_addr), kFzIdescD, 1u);
-              ptx::mma_bf16(d_tmem, dA(hi_p + 2 * kLboA), dB(c_addr + 2048), kFzIdescD, 1u);
+            for (int p = 0; p < 3; ++p)
+              ptx::mma_bf16(d_tmem0 + p * kFzBodies, dA(basis_addr + a_off + p * plane_stride), bd, kFzIdescD, acc);
+            if (m == ngroups - 1) {
+              ptx::tc_commit(bar_cempty + cs);
+              if (c == kFzChunks - 1) {
+                ptx::tc_commit(bar_dfull + a);
+                if (last_of_tile) ptx::tc_commit(bar_bfree);     // the producer may overwrite the basis tile
+              }
             }
           }
-          ptx::tc_commit(bar_cempty + cs);
-          if (c == kFzChunks - 1) {
-            ptx::tc_commit(bar_dfull + a);
-            if (last_of_tile) ptx::tc_commit(bar_bfree);     // the producer may overwrite the basis tile
-          }
+          __syncwarp();
         }
-        __syncwarp();
         if (++cs == kFzCoefStages) { cs = 0; c_phase ^= 1; }
       }
       new_tile = (blk + 1 == nblk);
       blk = new_tile ? 0 : blk + 1;
     }
-  } else if (warp == 1) {
-    // ===== blend-MMA issuer (skinning): one 6-MMA group per 4-body sub-block =====
+  } else if (warp == 1 || warp == kFzWarpT1) {
+    // ===== blend-MMA issuers (skinning): one 6-MMA group per 4-body sub-block.  One issuer warp PER T buffer
+    // (slot e: sub-blocks e, e+2, ...): a slot's chain "blend MMAs -> epilogue reads T -> buffer free -> next
+    // blend" then never waits behind the other slot's bookkeeping in a shared instruction stream. =====
+    const int e = warp == 1 ? 0 : 1;
     const uint32_t tmem_w = tmem_base + kFzTmemW;
     const uint32_t a_addr0 = ptx::smem_u32(sA);
+    const uint32_t t_tmem = tmem_base + kFzTmemT + e * kFzNT;
     constexpr uint32_t kLbo = kFzNT * 16, kSbo = 128;
     const uint64_t desc0 = ptx::make_smem_desc(0, kLbo, kSbo);
     auto dS = [&](uint32_t addr) { return desc0 | (uint64_t)((addr >> 4) & 0x3fffu); };
     int blk = (int)(u0 % nblk);
     bool new_tile = true;
     uint32_t w_phase = 0;
-    int as = 0; uint32_t a_phase = 0;           // A' ring stage / parity
-    uint32_t te_phase = 1;                      // parity for bar_tempty waits: both buffers start free
+    int as = 0; uint32_t a_phase = 0;           // this slot's A' ring: stage / parity of its next image
+    uint32_t te_phase = 1;                      // parity of the bar_tempty wait: the buffer starts free
     for (int i = 0; i < nunits; ++i) {
-      if (new_tile) { ptx::mbar_wait(bar_w, w_phase); w_phase ^= 1; }     // the tile's W' rows are in TMEM
+      if (new_tile) { ptx::mbar_wait_nohint(bar_w, w_phase); w_phase ^= 1; }     // the tile's W' rows are in TMEM
 #pragma unroll 1
-      for (int sb = 0; sb < kFzSubs; ++sb) {
-        const int e = sb & 1;
-        ptx::mbar_wait(bar_tempty + e, te_phase);
-        ptx::mbar_wait(bar_afull + as, a_phase);
+      for (int sb = e; sb < kFzSubs; sb += 2) {
+        SMPLB200_PROGRESS((i << 8) | sb);
+        ptx::mbar_wait_nohint(bar_tempty + e, te_phase);
+        ptx::mbar_wait_nohint(bar_afull + e * kFzAStages + as, a_phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t a_addr = a_addr0 + as * kFzAImage;
-          const uint32_t t_tmem = tmem_base + kFzTmemT + e * kFzNT;
+          const uint32_t a_addr = a_addr0 + (e * kFzAStages + as) * kFzAImage;
           const uint64_t s0 = dS(a_addr);              // A_hi joints 0..15
           const uint64_t s1 = dS(a_addr + 2 * kLbo);   // A_hi 16..23 | (A_lo 0..7 x 0)
           const uint64_t s2 = dS(a_addr + 3 * kLbo);   // A_lo joints 0..15
@@ -266,34 +290,42 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
           ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s3, kFzIdescT, 1u);
           ptx::mma_bf16_ts(t_tmem, tmem_w + 16, s0, kFzIdescT, 1u);   // W_lo * A_hi
           ptx::mma_bf16_ts(t_tmem, tmem_w + 24, s1, kFzIdescT, 1u);
-          ptx::tc_commit(bar_aempty + as);
+          ptx::tc_commit(bar_aempty + e * kFzAStages + as);
           ptx::tc_commit(bar_tfull + e);
+          if (e == 1) *pace = (uint32_t)i * kFzSubs + (uint32_t)sb + 1u;      // lets the D issuer release its next groups
         }
         __syncwarp();
+        te_phase ^= 1;
         if (++as == kFzAStages) { as = 0; a_phase ^= 1; }
-        if (e == 1) te_phase ^= 1;              // both buffers have been reused once more
       }
       new_tile = (blk + 1 == nblk);
       blk = new_tile ? 0 : blk + 1;
     }
-  } else if (warp >= kFzEpiWarp0) {
+  } else if (warp >= kFzEpiWarp0 && warp < kFzEpiWarp0 + kFzEpiWarps) {
     // ===== epilogue: slot e, lane quarter q =====
     const int ew = warp - kFzEpiWarp0;
     const int q = warp & 3, e = ew >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* so = sOut + ew * (4 * 96);
+    float* so = sOut + ew * (2 * 96);
     long long cur_tile = -1;
     int t_cnt = 0;                    // sub-blocks this warp has consumed (phase of its T buffer)
+    uint32_t wf_phase = 0;            // parity of the next bar_wfree wait (slot 0 only)
     const size_t body_stride = (size_t)V * 3;
     for (int i = 0; i < nunits; ++i) {
       const long long u = u0 + i, tile = u / nblk;
       const int blk = (int)(u % nblk), a = i & 1;
       if (tile != cur_tile) {
         // New tile: its W' rows replace the old ones in TMEM.  Every blend MMA of the old tile has retired
-        // once BOTH T buffers of the previous unit's last sub-blocks were completed; slot 0's own last
-        // result was consumed above, slot 1's is awaited here (a wait does not consume the phase).
-        if (e == 0) {
-          if (i > 0) ptx::mbar_wait(bar_tfull + 1, ((i * (kFzSubs / 2) - 1) & 1));
+        // once BOTH slots have consumed the last blend results of the previous unit: slot 0's warps have
+        // (program order); slot 1's warps say so on bar_wfree.
+        if (e == 1) {
+          if (i > 0) {          // this slot has consumed its last blend result of the old tile (program order)
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_wfree);
+            __syncwarp();
+          }
+        } else {
+          if (i > 0) { ptx::mbar_wait_nohint(bar_wfree, wf_phase); wf_phase ^= 1; }
           ptx::tc_fence_after();
           const uint4* src = reinterpret_cast<const uint4*>(w_rows + ((size_t)tile * 128 + q * 32 + lane) * 32);
 #pragma unroll
@@ -316,10 +348,11 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
       }
       const int warp_v0 = (int)tile * 128 + q * 32;
       const int nf = max(0, min(32, V - warp_v0)) * 3;    // floats this warp may store per body
-      ptx::mbar_wait(bar_dfull + a, (i >> 1) & 1);
+      ptx::mbar_wait_nohint(bar_dfull + a, (i >> 1) & 1);
       for (int sb = e; sb < kFzSubs; sb += 2) {
         const long long b0 = (long long)blk * kFzBodies + sb * kFzSub;
-        ptx::mbar_wait(bar_tfull + e, t_cnt & 1);
+        SMPLB200_PROGRESS((i << 8) | sb);
+        ptx::mbar_wait_nohint(bar_tfull + e, t_cnt & 1);
         ++t_cnt;
         ptx::tc_fence_after();
         uint32_t r0[16], r1[16], r2[16], dx[4], dy[4], dz[4];
@@ -344,41 +377,47 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
         for (int k = 0; k < 16; ++k) {
           T[k] = __uint_as_float(r0[k]); T[16 + k] = __uint_as_float(r1[k]); T[32 + k] = __uint_as_float(r2[k]);
         }
+        float res[12];
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
           const float* tt = T + bb * 12;
           const float x = __uint_as_float(dx[bb]), y = __uint_as_float(dy[bb]), z = __uint_as_float(dz[bb]);
-          float* sbuf = so + bb * 96 + 3 * lane;
-          sbuf[0] = fmaf(tt[2], z, fmaf(tt[1], y, fmaf(tt[0], x, tt[3])));
-          sbuf[1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
-          sbuf[2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
+          res[3 * bb] = fmaf(tt[2], z, fmaf(tt[1], y, fmaf(tt[0], x, tt[3])));
+          res[3 * bb + 1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
+          res[3 * bb + 2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
         }
-        __syncwarp();
         float* dst = verts + ((size_t)b0 * V + warp_v0) * 3 + lane;
-        if (b0 + kFzSub <= n && nf == 96) {        // whole sub-block, whole warp: unpredicated stores
-          float o[12];
+        const bool full = b0 + kFzSub <= n && nf == 96;      // whole sub-block, whole warp: unpredicated stores
+        // xyz interleave through a per-warp shared-memory tile, two bodies per pass (the tile is 768 B: the
+        // shared-memory budget goes to the basis), then coalesced 128-byte stores
 #pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            o[3 * bb] = so[bb * 96 + lane]; o[3 * bb + 1] = so[bb * 96 + lane + 32];
-            o[3 * bb + 2] = so[bb * 96 + lane + 64];
-          }
+        for (int h = 0; h < 2; ++h) {
+          float* sbuf = so + 3 * lane;
+          sbuf[0] = res[6 * h]; sbuf[1] = res[6 * h + 1]; sbuf[2] = res[6 * h + 2];
+          sbuf[96] = res[6 * h + 3]; sbuf[97] = res[6 * h + 4]; sbuf[98] = res[6 * h + 5];
+          __syncwarp();
+          float o[6];
 #pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            float* d = dst + bb * body_stride;
-            d[0] = o[3 * bb]; d[32] = o[3 * bb + 1]; d[64] = o[3 * bb + 2];
-          }
-        } else {
+          for (int k = 0; k < 6; ++k) o[k] = so[(k / 3) * 96 + lane + 32 * (k % 3)];
+          if (full) {
 #pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            if (b0 + bb < n) {
-              float* d = dst + bb * body_stride;
+            for (int bb = 0; bb < 2; ++bb) {
+              float* d = dst + (2 * h + bb) * body_stride;
+              d[0] = o[3 * bb]; d[32] = o[3 * bb + 1]; d[64] = o[3 * bb + 2];
+            }
+          } else {
 #pragma unroll
-              for (int k = 0; k < 3; ++k)
-                if (lane + 32 * k < nf) d[32 * k] = so[bb * 96 + lane + 32 * k];
+            for (int bb = 0; bb < 2; ++bb) {
+              if (b0 + 2 * h + bb < n) {
+                float* d = dst + (2 * h + bb) * body_stride;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                  if (lane + 32 * k < nf) d[32 * k] = o[3 * bb + k];
+              }
             }
           }
+          __syncwarp();          // the tile is reused by the next pass
         }
-        __syncwarp();          // staging rows are reused by the next sub-block
       }
     }
   }

@@ -48,11 +48,59 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, ui
       : "memory");
   return ok != 0;
 }
+#ifdef SMPLB200_DEBUG_WAIT
+// Debug build only: a wait that times out is RECORDED (block, warp, barrier offset, parity) and the kernel
+// limps on to its end instead of trapping, so the host can read who was stuck where
+// (smplb200_debug_wait_dump).  [0] = number of timeouts (also the "give up everywhere" flag).
+__device__ unsigned int g_wait_dbg[4 + 4 * 60];
+__device__ volatile unsigned int* g_prog = nullptr;      // host-mapped progress words [block][16 warps]
+#define SMPLB200_PROGRESS(val) do { if (smplb200::ptx::g_prog && (threadIdx.x & 31) == 0) \
+    smplb200::ptx::g_prog[blockIdx.x * 16 + (threadIdx.x >> 5)] = (unsigned int)(val); } while (0)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; it < 60u; ++it) {
+    if (mbar_try_wait(bar, parity, 1000000u)) return;
+    if (it == 30u && g_prog && (threadIdx.x & 31) == 0) {      // stuck for 30 ms: say where (host-mapped), trap at 60
+      volatile unsigned int* rec = g_prog + 148 * 16 + (blockIdx.x * 16 + (threadIdx.x >> 5)) * 2;
+      rec[0] = smem_u32(bar);
+      rec[1] = 0x100u | parity;
+      __threadfence_system();
+    }
+  }
+  __trap();
+}
+#else
+#define SMPLB200_PROGRESS(val) do { } while (0)
 // Bounded wait: a protocol bug must fault the launch, never hang the GPU (~2 s).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; it < 2000u; ++it)
     if (mbar_try_wait(bar, parity, 1000000u)) return;   // up to 1 ms asleep per attempt
   __trap();
+}
+#endif
+// Wait without a suspend-time hint: `mbarrier.try_wait` blocks in hardware for its (short, system-defined)
+// default window and is simply retried.  Used by the fused kernel, where a hinted wait was seen to oversleep:
+// with two MMA-issuer warps the A' producer's waits on a commit-signalled barrier occasionally slept out most
+// of the 1 ms hint (10x the kernel's run time) while every other warp burned through its retry budget and
+// trapped.  The bound is wall-clock (~2 s), not a retry count.
+__device__ __forceinline__ void mbar_wait_nohint(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 255u) == 255u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
 }
 // Orders this thread's earlier generic-proxy shared-memory accesses (made visible to it by a
 // barrier) before later async-proxy operations (bulk copies) on the same locations.

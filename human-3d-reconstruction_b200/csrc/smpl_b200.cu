@@ -1372,4 +1372,26 @@ int smplb200_probe_fp32_fma(int32_t device, int32_t iters, void* scratch, double
   return SMPLB200_OK;
 }
 
+#ifdef SMPLB200_DEBUG_WAIT
+int smplb200_debug_progress_buffer(unsigned int** host_ptr) {
+  unsigned int* h = nullptr;
+  if (cudaHostAlloc(&h, 148 * 16 * 4 * 3, cudaHostAllocMapped) != cudaSuccess) return 7;
+  std::memset(h, 0xff, 148 * 16 * 4);
+  std::memset(h + 148 * 16, 0, 148 * 16 * 4 * 2);
+  unsigned int* d = nullptr;
+  if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return 5;
+  volatile unsigned int* dv = d;
+  if (cudaMemcpyToSymbol(smplb200::ptx::g_prog, &dv, sizeof(dv)) != cudaSuccess) return 5;
+  *host_ptr = h;
+  return 0;
+}
+int smplb200_debug_wait_dump(unsigned int* out /* [244] */) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, smplb200::ptx::g_wait_dbg, sizeof(unsigned int) * 244);
+  unsigned int zero[244] = {0};
+  cudaMemcpyToSymbol(smplb200::ptx::g_wait_dbg, zero, sizeof(zero));
+  return e == cudaSuccess ? 0 : 5;
+}
+#endif
+
 }  // extern "C"
