@@ -32,10 +32,10 @@
 //     exact in the fp32 accumulator): ~2e-7, the same fp32-class fidelity as k_lbs_tc's 3xTF32.
 //
 // Schedule: persistent CTAs (one per SM) own equal contiguous ranges of the tile-major unit list.
-// Warp roles (416 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warps 1 and 12 = blend-MMA
+// Warp roles (672 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warps 1 and 20 = blend-MMA
 // issuers of T buffer 0 / 1, warp 2 = bulk-TMA producer of the A' images, warp 3 = D-MMA issuer (all issuers
-// warp-uniform, one elected lane), warps 4..11 = epilogue: TMEM lane quarter q = warp % 4, slot
-// e = (warp - 4) / 4 takes the sub-blocks s = e, e + 2, ... and owns T buffer e.  The D issuer runs up to one unit ahead (D is double-buffered), so
+// warp-uniform, one elected lane), warps 4..19 = epilogue: TMEM lane quarter q = warp % 4, slot e takes the
+// sub-blocks s = e, e + 2, ... (T buffer e), body half h takes two of the sub-block's four bodies.  The D issuer runs up to one unit ahead (D is double-buffered), so
 // the tensor pipe interleaves the next unit's blendshape MMAs with this unit's blend MMAs.
 #pragma once
 #include <cuda_fp16.h>
@@ -51,13 +51,14 @@ constexpr int kFzSub = 4;                           // bodies per blend sub-bloc
 constexpr int kFzSubs = kFzBodies / kFzSub;         // 16
 constexpr int kFzNT = kFzSub * 12;                  // 48: N of the blend MMAs
 constexpr int kFzShapeK = 16;                       // K rows 0..15: betas | template pieces | 0
-constexpr int kFzThreads = 416;                     // 13 warps, see "Warp roles"
-constexpr int kFzEpiWarp0 = 4, kFzEpiWarps = 8, kFzWarpT1 = 12;   // warp 12: blend issuer of slot 1
+constexpr int kFzThreads = 672;                     // 21 warps, see "Warp roles"
+constexpr int kFzEpiWarp0 = 4, kFzEpiWarps = 16, kFzWarpT1 = 20;  // warp 20: blend issuer of slot 1
 constexpr uint32_t kFzPlaneHi = kCoefK * 128 * 2;               // 57,344
 constexpr uint32_t kFzPlaneLo = kFzShapeK * 128 * 2;            // 4,096
 constexpr uint32_t kFzBasisBytes = 3 * (kFzPlaneHi + kFzPlaneLo);   // 184,320 per vertex tile
 constexpr uint32_t kFzCoefLo = kFzShapeK * kFzBodies * 2;       // 2,048
 constexpr uint32_t kFzCoefBlock = kFzCoefLo + kCoefK * kFzBodies * 2;   // 30,720 per 64-body block
+constexpr int kFzDLead = 6;                                     // D groups run this many sub-blocks ahead of the pacing
 constexpr int kFzChunks = 7;                                    // K chunks per unit: 2 k-steps each
 constexpr uint32_t kFzCoefStage = kFzCoefLo + 2 * 2048;         // 6,144 (chunk 0 carries the lo rows too)
 constexpr int kFzCoefStages = 3;
@@ -66,7 +67,7 @@ constexpr int kFzAStages = 2;                                   // PER SLOT: eac
 constexpr uint32_t kFzOffCoef = kFzBasisBytes;
 constexpr uint32_t kFzOffA = kFzOffCoef + kFzCoefStages * kFzCoefStage;
 constexpr uint32_t kFzOffOut = kFzOffA + 2 * kFzAStages * kFzAImage;
-constexpr uint32_t kFzOffBar = kFzOffOut + kFzEpiWarps * 2 * 96 * 4;   // per epilogue warp: 2 bodies x 96 floats
+constexpr uint32_t kFzOffBar = kFzOffOut + kFzEpiWarps * 96 * 4;       // per epilogue warp: one body x 96 floats
 constexpr uint32_t kFzSmemBytes = kFzOffBar + 256;              // 230,656 <= 232,448
 constexpr uint32_t kFzTmemD = 0, kFzTmemT = 2 * 3 * kFzBodies, kFzTmemW = kFzTmemT + 2 * kFzNT;   // 0 | 384 | 480
 constexpr uint32_t kFzIdescD = ptx::make_idesc(ptx::kFmtF16, 128, kFzBodies);
@@ -87,10 +88,24 @@ __device__ __forceinline__ int fz_old_index(int nk, int NB) {
   return -1;
 }
 
+#ifdef SMPLB200_FZ_TIMING
+__device__ long long g_fz_time[148 * 32];
+// accumulate in registers (acc0..acc2 of the role), written once when the role's loop ends
+#define FZ_T0() const long long _t0 = clock64()
+#define FZ_ACC(var) do { var += clock64() - _t0; } while (0)
+#define FZ_DECL long long fz_a0 = 0, fz_a1 = 0, fz_a2 = 0
+#define FZ_OUT(slot, var) do { if (lane == 0) g_fz_time[blockIdx.x * 32 + (slot)] += var; } while (0)
+#else
+#define FZ_T0() do { } while (0)
+#define FZ_ACC(var) do { } while (0)
+#define FZ_DECL do { } while (0)
+#define FZ_OUT(slot, var) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kFzThreads, 1)
 k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__ w_rows,
            const uint8_t* __restrict__ coef_img, const uint8_t* __restrict__ a_img,
-           long long n, int nblk, long long total_units, int V, float* __restrict__ verts) {
+           long long n, int nblk, long long total_units, int V, float* __restrict__ verts, int dbg) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sBasis = smem;
   uint8_t* sCoef = smem + kFzOffCoef;
@@ -113,18 +128,21 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
   volatile uint32_t* pace = tmem_slot + 1;             // blend groups issued so far (paces the D issuer, see below)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef SMPLB200_FZ_TIMING
+  const long long t_kernel0 = clock64();
+#endif
   const long long u0 = total_units * blockIdx.x / gridDim.x;
   const long long u1 = total_units * (blockIdx.x + 1) / gridDim.x;
   const int nunits = (int)(u1 - u0);
 
   if (warp == 0 && lane == 0) {
     *pace = 0u;
-    ptx::mbar_init(bar_bfull, 1); ptx::mbar_init(bar_bfree, 1); ptx::mbar_init(bar_w, 4); ptx::mbar_init(bar_wfree, 4);
+    ptx::mbar_init(bar_bfull, 1); ptx::mbar_init(bar_bfree, 1); ptx::mbar_init(bar_w, 4); ptx::mbar_init(bar_wfree, kFzEpiWarps / 2);
     for (int s = 0; s < kFzCoefStages; ++s) { ptx::mbar_init(bar_cfull + s, 1); ptx::mbar_init(bar_cempty + s, 1); }
     for (int s = 0; s < 2 * kFzAStages; ++s) { ptx::mbar_init(bar_afull + s, 1); ptx::mbar_init(bar_aempty + s, 1); }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(bar_dfull + a, 1); ptx::mbar_init(bar_dempty + a, kFzEpiWarps);
-      ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, 4);
+      ptx::mbar_init(bar_tfull + a, 1); ptx::mbar_init(bar_tempty + a, kFzEpiWarps / 2);
     }
     ptx::fence_barrier_init();
   }
@@ -166,6 +184,7 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
     // alternate between the two blend issuers, and EACH ISSUER HAS ITS OWN 2-STAGE RING: a ring shared by
     // two consumers breaks the parity protocol (a waiter must have seen the barrier's previous phase, which
     // belonged to the other consumer). =====
+    FZ_DECL;
     if (lane == 0) {
       int it = 0;
       for (int i = 0; i < nunits; ++i) {
@@ -175,17 +194,19 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
           SMPLB200_PROGRESS((i << 8) | sb);
           const int k = it >> 1;                           // this slot's image counter
           const int s = (it & 1) * kFzAStages + (k & 1);   // [slot][stage]
-          ptx::mbar_wait_nohint(bar_aempty + s, ((k >> 1) & 1) ^ 1);
+          { FZ_T0(); ptx::mbar_wait_nohint(bar_aempty + s, ((k >> 1) & 1) ^ 1); FZ_ACC(fz_a0); }
           ptx::mbar_arrive_expect_tx(bar_afull + s, kFzAImage);
           ptx::bulk_g2s(sA + (size_t)s * kFzAImage, src + (size_t)sb * kFzAImage, kFzAImage, bar_afull + s);
         }
       }
+      FZ_OUT(0, fz_a0);
     }
   } else if (warp == 3) {
     // ===== D-MMA issuer (blendshapes): whole warp convergent, one elected lane issues.  Its own warp, so
     // the scalar bookkeeping of the D chunks never sits in the blend issuer's loop (a single issuer doing both
     // was the kernel's critical path: ~1300 clk of index math, waits and descriptor building per sub-block).
     // All counters are incremental: no division / modulo in the loop. =====
+    FZ_DECL;
     const uint32_t basis_addr = ptx::smem_u32(sBasis);
     const uint32_t coef_addr = ptx::smem_u32(sCoef);
     constexpr uint32_t kLboA = 128 * 16, kLboB = kFzBodies * 16, kSbo = 128;
@@ -201,63 +222,66 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
       const int a = i & 1;
       const bool last_of_tile = (i + 1 == nunits) || (blk + 1 == nblk);
       if (new_tile) { ptx::mbar_wait_nohint(bar_bfull, b_phase); b_phase ^= 1; }
-      ptx::mbar_wait_nohint(bar_dempty + a, ((i >> 1) & 1) ^ 1);     // epilogue drained this buffer (unit i-2)
+      { FZ_T0(); ptx::mbar_wait_nohint(bar_dempty + a, ((i >> 1) & 1) ^ 1); FZ_ACC(fz_a1); }     // epilogue drained this buffer (unit i-2)
       const uint32_t d_tmem0 = tmem_base + kFzTmemD + a * 3 * kFzBodies;
-      // The unit's 54 MMAs go out as 16 groups of 3 (one MMA per plane; chunk 0 = 4 groups, chunks 1..6 = 2
-      // each).  The tensor pipe executes in issue order, so a whole unit of D MMAs issued at once (2.8 kclk)
-      // would stall every blend MMA -- and with it the epilogue -- behind it.  Group g of unit i is therefore
-      // held back until the blend issuer has issued sub-block g of unit i-1 (`pace`, a monotonic counter in
-      // shared memory): the two MMA streams interleave one group per sub-block.
+      // The unit's 54 MMAs go out chunk by chunk (12 MMAs for chunk 0, 6 for chunks 1..6).  The tensor pipe
+      // executes in issue order, so a whole unit of D MMAs issued at once (2.8 kclk) would stall every blend
+      // MMA -- and with it the epilogue -- behind it.  A chunk is therefore held back until the blend issuers
+      // have reached the matching sub-block of unit i-1, less a lead (`pace`, a monotonic counter in shared
+      // memory): the two MMA streams interleave, and the unit's accumulators are complete a few sub-blocks
+      // BEFORE the epilogue asks for them.  The issue code is straight-line per chunk: this warp's own
+      // instruction latency (branches, descriptor arithmetic) was what made D late.
       const uint32_t pace_base = (uint32_t)(i - 1) * kFzSubs;
-      int g = 0;
 #pragma unroll 1
       for (int c = 0; c < kFzChunks; ++c) {
-        ptx::mbar_wait_nohint(bar_cfull + cs, c_phase);
+        { FZ_T0(); ptx::mbar_wait_nohint(bar_cfull + cs, c_phase); FZ_ACC(fz_a0); }
+        if (i > 0) {      // pacing, once per chunk: chunk c goes out when sub-block 2c - kFzDLead of unit i-1 has
+          const int g0 = c == 0 ? 0 : 2 * c + 2;
+          const uint32_t need = pace_base + (uint32_t)(g0 > kFzDLead ? g0 - kFzDLead : 0) + 1u;
+          FZ_T0(); while ((int32_t)(*pace - need) < 0) __nanosleep(64); FZ_ACC(fz_a2);
+        }
         ptx::tc_fence_after();
         const uint32_t c_addr = coef_addr + cs * kFzCoefStage;
-        const int ngroups = c == 0 ? 4 : 2;
-#pragma unroll 1
-        for (int m = 0; m < ngroups; ++m, ++g) {
-          SMPLB200_PROGRESS((i << 8) | g);
-          if (i > 0) {
-            const uint32_t need = pace_base + (uint32_t)g + 1u;
-            while ((int32_t)(*pace - need) < 0) __nanosleep(64);
-          }
-          if (ptx::elect_one()) {
-            uint32_t a_off, b_off, acc = 1u;      // byte offsets of the A (basis) / B (coef) k-step of this group
-            if (c == 0) {
-              // m: 0 hi*hi (shape rows)  1 hi(basis)*lo(coef)  2 lo(basis)*hi(coef)  3 first pose k-step
-              a_off = m == 2 ? 3 * kFzPlaneHi : (m == 3 ? 2 * kLboA : 0u);
-              b_off = m == 1 ? 0u : (m == 3 ? kFzCoefLo + 2048u : kFzCoefLo);
-              acc = m != 0;
-            } else {
-              a_off = (uint32_t)(2 * c + m) * 2 * kLboA;
-              b_off = (uint32_t)m * 2048u;
-            }
-            const uint32_t plane_stride = (c == 0 && m == 2) ? kFzPlaneLo : kFzPlaneHi;
-            const uint64_t bd = dB(c_addr + b_off);
+        if (ptx::elect_one()) {
+          // straight-line issue: every descriptor is (a base computed once per chunk) | (a compile-time offset)
+          const uint64_t a_hi = dA(basis_addr), b_0 = dB(c_addr);
+          constexpr uint64_t kPlaneA = kFzPlaneHi >> 4, kStepA = (2 * kLboA) >> 4, kLoA = (3 * kFzPlaneHi) >> 4,
+                             kPlaneLoA = kFzPlaneLo >> 4, kLoB = kFzCoefLo >> 4, kStepB = 2048 >> 4;
+          if (c == 0) {
 #pragma unroll
-            for (int p = 0; p < 3; ++p)
-              ptx::mma_bf16(d_tmem0 + p * kFzBodies, dA(basis_addr + a_off + p * plane_stride), bd, kFzIdescD, acc);
-            if (m == ngroups - 1) {
-              ptx::tc_commit(bar_cempty + cs);
-              if (c == kFzChunks - 1) {
-                ptx::tc_commit(bar_dfull + a);
-                if (last_of_tile) ptx::tc_commit(bar_bfree);     // the producer may overwrite the basis tile
-              }
+            for (int p = 0; p < 3; ++p) {     // shape rows: hi*hi, hi(basis)*lo(coef), lo(basis)*hi(coef); first pose k-step
+              const uint32_t d_tmem = d_tmem0 + p * kFzBodies;
+              ptx::mma_bf16(d_tmem, a_hi + p * kPlaneA, b_0 + kLoB, kFzIdescD, 0u);
+              ptx::mma_bf16(d_tmem, a_hi + p * kPlaneA, b_0, kFzIdescD, 1u);
+              ptx::mma_bf16(d_tmem, a_hi + kLoA + p * kPlaneLoA, b_0 + kLoB, kFzIdescD, 1u);
+              ptx::mma_bf16(d_tmem, a_hi + p * kPlaneA + kStepA, b_0 + kLoB + kStepB, kFzIdescD, 1u);
             }
+          } else {
+            const uint64_t a_c = a_hi + (uint64_t)(2 * c) * kStepA;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+              for (int p = 0; p < 3; ++p)
+                ptx::mma_bf16(d_tmem0 + p * kFzBodies, a_c + ks * kStepA + p * kPlaneA, b_0 + ks * kStepB, kFzIdescD, 1u);
           }
-          __syncwarp();
+          ptx::tc_commit(bar_cempty + cs);
+          if (c == kFzChunks - 1) {
+            ptx::tc_commit(bar_dfull + a);
+            if (last_of_tile) ptx::tc_commit(bar_bfree);     // the producer may overwrite the basis tile
+          }
         }
+        __syncwarp();
         if (++cs == kFzCoefStages) { cs = 0; c_phase ^= 1; }
       }
       new_tile = (blk + 1 == nblk);
       blk = new_tile ? 0 : blk + 1;
     }
+    FZ_OUT(16, fz_a0); FZ_OUT(17, fz_a1); FZ_OUT(18, fz_a2);
   } else if (warp == 1 || warp == kFzWarpT1) {
     // ===== blend-MMA issuers (skinning): one 6-MMA group per 4-body sub-block.  One issuer warp PER T buffer
     // (slot e: sub-blocks e, e+2, ...): a slot's chain "blend MMAs -> epilogue reads T -> buffer free -> next
     // blend" then never waits behind the other slot's bookkeeping in a shared instruction stream. =====
+    FZ_DECL;
     const int e = warp == 1 ? 0 : 1;
     const uint32_t tmem_w = tmem_base + kFzTmemW;
     const uint32_t a_addr0 = ptx::smem_u32(sA);
@@ -275,8 +299,8 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
 #pragma unroll 1
       for (int sb = e; sb < kFzSubs; sb += 2) {
         SMPLB200_PROGRESS((i << 8) | sb);
-        ptx::mbar_wait_nohint(bar_tempty + e, te_phase);
-        ptx::mbar_wait_nohint(bar_afull + e * kFzAStages + as, a_phase);
+        { FZ_T0(); ptx::mbar_wait_nohint(bar_tempty + e, te_phase); FZ_ACC(fz_a0); }
+        { FZ_T0(); ptx::mbar_wait_nohint(bar_afull + e * kFzAStages + as, a_phase); FZ_ACC(fz_a1); }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t a_addr = a_addr0 + (e * kFzAStages + as) * kFzAImage;
@@ -284,12 +308,14 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
           const uint64_t s1 = dS(a_addr + 2 * kLbo);   // A_hi 16..23 | (A_lo 0..7 x 0)
           const uint64_t s2 = dS(a_addr + 3 * kLbo);   // A_lo joints 0..15
           const uint64_t s3 = dS(a_addr + 5 * kLbo);   // A_lo 16..23 | zeros
+          if (!(dbg & 2)) {
           ptx::mma_bf16_ts(t_tmem, tmem_w, s0, kFzIdescT, 0u);        // W_hi * A_hi
           ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s1, kFzIdescT, 1u);
           ptx::mma_bf16_ts(t_tmem, tmem_w, s2, kFzIdescT, 1u);        // W_hi * A_lo
           ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s3, kFzIdescT, 1u);
           ptx::mma_bf16_ts(t_tmem, tmem_w + 16, s0, kFzIdescT, 1u);   // W_lo * A_hi
           ptx::mma_bf16_ts(t_tmem, tmem_w + 24, s1, kFzIdescT, 1u);
+          }
           ptx::tc_commit(bar_aempty + e * kFzAStages + as);
           ptx::tc_commit(bar_tfull + e);
           if (e == 1) *pace = (uint32_t)i * kFzSubs + (uint32_t)sb + 1u;      // lets the D issuer release its next groups
@@ -301,12 +327,17 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
       new_tile = (blk + 1 == nblk);
       blk = new_tile ? 0 : blk + 1;
     }
+    FZ_OUT(2 + e * 4, fz_a0); FZ_OUT(3 + e * 4, fz_a1);
   } else if (warp >= kFzEpiWarp0 && warp < kFzEpiWarp0 + kFzEpiWarps) {
-    // ===== epilogue: slot e, lane quarter q =====
+    // ===== epilogue: slot e (T buffer), lane quarter q, body half h (bodies 2h, 2h+1 of each sub-block).
+    // Sixteen warps: one sub-block's transform + transpose + store is a long dependent chain (TMEM load ->
+    // FMAs -> shared-memory transpose -> stores), and with one warp per (slot, quarter) that chain, not any
+    // throughput limit, set the pace of the kernel. =====
+    FZ_DECL;
     const int ew = warp - kFzEpiWarp0;
-    const int q = warp & 3, e = ew >> 2;
+    const int q = warp & 3, e = (ew >> 2) & 1, h = ew >> 3;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* so = sOut + ew * (2 * 96);
+    float* so = sOut + ew * 96;
     long long cur_tile = -1;
     int t_cnt = 0;                    // sub-blocks this warp has consumed (phase of its T buffer)
     uint32_t wf_phase = 0;            // parity of the next bar_wfree wait (slot 0 only)
@@ -318,8 +349,8 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
         // New tile: its W' rows replace the old ones in TMEM.  Every blend MMA of the old tile has retired
         // once BOTH slots have consumed the last blend results of the previous unit: slot 0's warps have
         // (program order); slot 1's warps say so on bar_wfree.
-        if (e == 1) {
-          if (i > 0) {          // this slot has consumed its last blend result of the old tile (program order)
+        if (e == 1 || h == 1) {
+          if (e == 1 && i > 0) {  // this slot has consumed its last blend result of the old tile (program order)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_wfree);
             __syncwarp();
@@ -348,22 +379,21 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
       }
       const int warp_v0 = (int)tile * 128 + q * 32;
       const int nf = max(0, min(32, V - warp_v0)) * 3;    // floats this warp may store per body
-      ptx::mbar_wait_nohint(bar_dfull + a, (i >> 1) & 1);
+      { FZ_T0(); ptx::mbar_wait_nohint(bar_dfull + a, (i >> 1) & 1); FZ_ACC(fz_a0); }
       for (int sb = e; sb < kFzSubs; sb += 2) {
         const long long b0 = (long long)blk * kFzBodies + sb * kFzSub;
         SMPLB200_PROGRESS((i << 8) | sb);
-        ptx::mbar_wait_nohint(bar_tfull + e, t_cnt & 1);
+        { FZ_T0(); ptx::mbar_wait_nohint(bar_tfull + e, t_cnt & 1); FZ_ACC(fz_a1); }
         ++t_cnt;
         ptx::tc_fence_after();
-        uint32_t r0[16], r1[16], r2[16], dx[4], dy[4], dz[4];
-        const uint32_t t_addr = tmem_base + kFzTmemT + lane_addr + e * kFzNT;
-        const uint32_t d_addr = tmem_base + kFzTmemD + lane_addr + a * 3 * kFzBodies + sb * kFzSub;
+        uint32_t r0[16], r1[8], dx[2], dy[2], dz[2];
+        const uint32_t t_addr = tmem_base + kFzTmemT + lane_addr + e * kFzNT + h * 24;
+        const uint32_t d_addr = tmem_base + kFzTmemD + lane_addr + a * 3 * kFzBodies + sb * kFzSub + 2 * h;
         ptx::tmem_ld16(t_addr, r0);
-        ptx::tmem_ld16(t_addr + 16, r1);
-        ptx::tmem_ld16(t_addr + 32, r2);
-        ptx::tmem_ld4(d_addr, dx);
-        ptx::tmem_ld4(d_addr + kFzBodies, dy);
-        ptx::tmem_ld4(d_addr + 2 * kFzBodies, dz);
+        ptx::tmem_ld8(t_addr + 16, r1);
+        ptx::tmem_ld2(d_addr, dx);
+        ptx::tmem_ld2(d_addr + kFzBodies, dy);
+        ptx::tmem_ld2(d_addr + 2 * kFzBodies, dz);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
@@ -372,57 +402,51 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
           if (sb + 2 >= kFzSubs) ptx::mbar_arrive(bar_dempty + a);    // this warp's last read of the unit's D
         }
         __syncwarp();
-        float T[48];
+        float T[24];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          T[k] = __uint_as_float(r0[k]); T[16 + k] = __uint_as_float(r1[k]); T[32 + k] = __uint_as_float(r2[k]);
-        }
-        float res[12];
+        for (int k = 0; k < 16; ++k) T[k] = __uint_as_float(r0[k]);
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
+        for (int k = 0; k < 8; ++k) T[16 + k] = __uint_as_float(r1[k]);
+        float res[6];
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
           const float* tt = T + bb * 12;
           const float x = __uint_as_float(dx[bb]), y = __uint_as_float(dy[bb]), z = __uint_as_float(dz[bb]);
           res[3 * bb] = fmaf(tt[2], z, fmaf(tt[1], y, fmaf(tt[0], x, tt[3])));
           res[3 * bb + 1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
           res[3 * bb + 2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
         }
-        float* dst = verts + ((size_t)b0 * V + warp_v0) * 3 + lane;
-        const bool full = b0 + kFzSub <= n && nf == 96;      // whole sub-block, whole warp: unpredicated stores
-        // xyz interleave through a per-warp shared-memory tile, two bodies per pass (the tile is 768 B: the
-        // shared-memory budget goes to the basis), then coalesced 128-byte stores
+        const long long bh = b0 + 2 * h;                       // first of this warp's two bodies
+        float* dst = verts + ((size_t)bh * V + warp_v0) * 3 + lane;
+        const bool full = bh + 2 <= n && nf == 96;             // both bodies, whole warp: unpredicated stores
+        // xyz interleave through a per-warp shared-memory row (one body per pass: the shared-memory budget
+        // goes to the basis), then coalesced 128-byte stores
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int bb = 0; bb < 2; ++bb) {
           float* sbuf = so + 3 * lane;
-          sbuf[0] = res[6 * h]; sbuf[1] = res[6 * h + 1]; sbuf[2] = res[6 * h + 2];
-          sbuf[96] = res[6 * h + 3]; sbuf[97] = res[6 * h + 4]; sbuf[98] = res[6 * h + 5];
+          sbuf[0] = res[3 * bb]; sbuf[1] = res[3 * bb + 1]; sbuf[2] = res[3 * bb + 2];
           __syncwarp();
-          float o[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) o[k] = so[(k / 3) * 96 + lane + 32 * (k % 3)];
-          if (full) {
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-              float* d = dst + (2 * h + bb) * body_stride;
-              d[0] = o[3 * bb]; d[32] = o[3 * bb + 1]; d[64] = o[3 * bb + 2];
-            }
-          } else {
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-              if (b0 + 2 * h + bb < n) {
-                float* d = dst + (2 * h + bb) * body_stride;
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                  if (lane + 32 * k < nf) d[32 * k] = o[3 * bb + k];
-              }
-            }
+          const float o0 = so[lane], o1 = so[lane + 32], o2 = so[lane + 64];
+          float* d = dst + bb * body_stride;
+          if (dbg & 4) {
+          } else if (full) {
+            d[0] = o0; d[32] = o1; d[64] = o2;
+          } else if (bh + bb < n) {
+            if (lane < nf) d[0] = o0;
+            if (lane + 32 < nf) d[32] = o1;
+            if (lane + 64 < nf) d[64] = o2;
           }
-          __syncwarp();          // the tile is reused by the next pass
+          __syncwarp();          // the row is reused by the next pass
         }
       }
     }
+    if (q == 0 && h == 0) { FZ_OUT(10 + 2 * e, fz_a0); FZ_OUT(11 + 2 * e, fz_a1); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+#ifdef SMPLB200_FZ_TIMING
+  if (threadIdx.x == 0) g_fz_time[blockIdx.x * 32 + 31] += clock64() - t_kernel0;
+#endif
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -478,7 +502,9 @@ inline cudaError_t launch_fused_tc(const DeviceModel& m, int num_sms, const uint
   const int nblk = (int)((n + kFzBodies - 1) / kFzBodies);
   const long long total = (long long)ntile * nblk;
   const unsigned grid = (unsigned)std::min<long long>(num_sms, total);
-  k_fused_tc<<<grid, kFzThreads, kFzSmemBytes, s>>>(m.fz_basis, m.fz_w, coef_img, a_img, n, nblk, total, m.V, verts);
+  const char* dbg_env = std::getenv("SMPLB200_FZ_DBG");      // ablation knobs (1: no D MMAs, 2: no blend MMAs, 4: no stores)
+  k_fused_tc<<<grid, kFzThreads, kFzSmemBytes, s>>>(m.fz_basis, m.fz_w, coef_img, a_img, n, nblk, total, m.V, verts,
+                                                    dbg_env ? std::atoi(dbg_env) : 0);
   return cudaGetLastError();
 }
 

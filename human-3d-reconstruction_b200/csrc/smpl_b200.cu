@@ -1372,6 +1372,15 @@ int smplb200_probe_fp32_fma(int32_t device, int32_t iters, void* scratch, double
   return SMPLB200_OK;
 }
 
+#ifdef SMPLB200_FZ_TIMING
+int smplb200_debug_fz_timing(long long* out /* [148*32] */) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(out, smplb200::g_fz_time, sizeof(long long) * 148 * 32);
+  static long long zero[148 * 32];
+  cudaMemcpyToSymbol(smplb200::g_fz_time, zero, sizeof(zero));
+  return e == cudaSuccess ? 0 : 5;
+}
+#endif
 #ifdef SMPLB200_DEBUG_WAIT
 int smplb200_debug_progress_buffer(unsigned int** host_ptr) {
   unsigned int* h = nullptr;
