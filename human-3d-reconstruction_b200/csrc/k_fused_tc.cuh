@@ -299,8 +299,10 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
 #pragma unroll 1
       for (int sb = e; sb < kFzSubs; sb += 2) {
         SMPLB200_PROGRESS((i << 8) | sb);
-        { FZ_T0(); ptx::mbar_wait_nohint(bar_tempty + e, te_phase); FZ_ACC(fz_a0); }
+        // operand first (it has usually landed long ago), then the accumulator: when the epilogue frees the T
+        // buffer nothing but the issue itself stands between that arrival and the next blend
         { FZ_T0(); ptx::mbar_wait_nohint(bar_afull + e * kFzAStages + as, a_phase); FZ_ACC(fz_a1); }
+        { FZ_T0(); ptx::mbar_wait_nohint(bar_tempty + e, te_phase); FZ_ACC(fz_a0); }
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t a_addr = a_addr0 + (e * kFzAStages + as) * kFzAImage;
@@ -391,17 +393,21 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
         const uint32_t d_addr = tmem_base + kFzTmemD + lane_addr + a * 3 * kFzBodies + sb * kFzSub + 2 * h;
         ptx::tmem_ld16(t_addr, r0);
         ptx::tmem_ld8(t_addr + 16, r1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_tempty + e);      // T buffer free: the next blend of this slot may start
+        __syncwarp();
         ptx::tmem_ld2(d_addr, dx);
         ptx::tmem_ld2(d_addr + kFzBodies, dy);
         ptx::tmem_ld2(d_addr + 2 * kFzBodies, dz);
         ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(bar_tempty + e);
-          if (sb + 2 >= kFzSubs) ptx::mbar_arrive(bar_dempty + a);    // this warp's last read of the unit's D
+        if (sb + 2 >= kFzSubs) {                                // this warp's last read of the unit's D
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_dempty + a);
+          __syncwarp();
         }
-        __syncwarp();
         float T[24];
 #pragma unroll
         for (int k = 0; k < 16; ++k) T[k] = __uint_as_float(r0[k]);
