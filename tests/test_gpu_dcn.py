@@ -3,8 +3,8 @@ torchvision and the reference's own known-answer test in tests/test_dcn_oracle.p
 fixture generated from torchvision.
 
 Tolerance: the kernel multiplies split-bf16 operands (hi*hi + lo*hi + hi*lo, ~2^-16 relative per
-product, fp32 accumulate): every output must agree with the float64 oracle to 2e-4 of the largest
-|output| of the case (DCN_RTOL); measured errors are printed by bench.py / smoke().
+product, fp32 accumulate): every output must agree with the float64 oracle to 5e-5 of the largest
+|output| of the case (DCN_RTOL; measured 0.3-1.7e-5); measured errors are printed by bench.py / smoke().
 """
 import os
 
@@ -16,7 +16,7 @@ from human_3d_reconstruction_b200 import DCN, DCNv2, capi, dcn_v2_conv
 from oracle.dcn_ref import dcn_forward, dcn_v2_forward
 
 pytestmark = pytest.mark.gpu
-DCN_RTOL = 2e-4
+DCN_RTOL = 5e-5
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dcn_golden_v1.npz")
 
 
