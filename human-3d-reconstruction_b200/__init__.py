@@ -10,10 +10,10 @@ Public surface:
 from . import synthetic  # noqa: F401
 from . import model_io  # noqa: F401
 from . import capi  # noqa: F401
-from .smpl import SMPL, GraphedSMPL, HostRunner  # noqa: F401
+from .smpl import SMPL, GraphedSMPL, HostRunner, StaticSMPL  # noqa: F401
 from . import sharding  # noqa: F401
 from .decode import decode_gather  # noqa: F401
 from .dcn import DCN, DCNv2, dcn_v2_conv  # noqa: F401
 
-__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "decode_gather", "DCN", "DCNv2", "dcn_v2_conv", "capi", "synthetic",
+__all__ = ["SMPL", "GraphedSMPL", "HostRunner", "StaticSMPL", "decode_gather", "DCN", "DCNv2", "dcn_v2_conv", "capi", "synthetic",
            "sharding", "model_io"]

@@ -61,7 +61,7 @@ def forward_opts(joints_ready_event=None):
     handle = joints_ready_event.cuda_event
     if not handle:
         raise RuntimeError("joints_ready event has no CUDA handle yet: call event.record() once before passing it")
-    return C.byref(ForwardOpts(C.sizeof(ForwardOpts), handle))
+    return C.pointer(ForwardOpts(C.sizeof(ForwardOpts), handle))      # pointer() keeps the struct alive
 
 
 # every symbol include/smpl_b200.h declares: name -> (restype, argtypes)

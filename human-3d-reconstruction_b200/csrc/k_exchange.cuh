@@ -17,7 +17,7 @@ namespace smplb200 {
 
 constexpr int kXchgMaxRanks = 16;
 constexpr int kXchgRow = kJ * 3 + kJ * 2;      // 120 floats = 30 float4
-constexpr int kXchgThreads = 256;
+constexpr int kXchgThreads = 128;
 
 struct XchgPeers {
   float* buf[kXchgMaxRanks];                   // peer-mapped gathered buffers (entry `rank` = local)

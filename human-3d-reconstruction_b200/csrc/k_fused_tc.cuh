@@ -47,6 +47,7 @@
 namespace smplb200 {
 
 constexpr int kFzBodies = 64;                       // bodies per unit (N of the D MMAs)
+constexpr long long kFzMaxBodiesPerLaunch = 8192;   // operand images of one launch stay L2-resident (15 MB)
 constexpr int kFzSub = 4;                           // bodies per blend sub-block
 constexpr int kFzSubs = kFzBodies / kFzSub;         // 16
 constexpr int kFzNT = kFzSub * 12;                  // 48: N of the blend MMAs

@@ -724,7 +724,8 @@ int smplb200_forward_launch_count(const SmplB200Model* model, int64_t n, uint32_
   Plan p;
   if (!model || n <= 0 || !resolve_plan(model, n, flags, &p)) return 0;
   (void)with_projection;
-  if (p.prec == SMPLB200_PREC_F16) return 2 + (p.regressed ? 1 : 0);     // k2, fused [, regression]
+  if (p.prec == SMPLB200_PREC_F16)       // k2, fused (one launch per 8192 bodies) [, regression]
+    return 1 + (int)((n + kFzMaxBodiesPerLaunch - 1) / kFzMaxBodiesPerLaunch) + (p.regressed ? 1 : 0);
   const bool chunked = model->chunk > 0 && p.prec != SMPLB200_PREC_FP32 && p.lbs == SMPLB200_LBS_TC &&
                        n > model->chunk;
   const int passes = chunked ? (int)((n + model->chunk - 1) / model->chunk) : 1;
@@ -898,7 +899,15 @@ int smplb200_forward_opts(const SmplB200Model* model, const float* betas, const 
     int st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
     if (st) return st;
     if (ev_joints && !p.regressed) CU_TRY(cudaEventRecord(ev_joints, s));
-    CU_TRY(launch_fused_tc(model->d, model->num_sms, out.fz_coef, out.fz_a, n, vertices, s));
+    // One launch per <= kFzMaxBodiesPerLaunch bodies: every vertex tile re-reads the launch's coef and A'
+    // images (119 KB per 64 bodies), which must stay L2-resident under the stream of vertex writes -- at
+    // 65,536 bodies in one launch they did not (7.6 GB of operand re-reads from HBM, 24 M instead of 29 M bodies/s).
+    for (long long c0 = 0; c0 < n; c0 += kFzMaxBodiesPerLaunch) {
+      const long long nc = std::min<long long>(kFzMaxBodiesPerLaunch, n - c0);
+      CU_TRY(launch_fused_tc(model->d, model->num_sms, out.fz_coef + (size_t)(c0 / kFzBodies) * kFzCoefBlock,
+                             out.fz_a + (size_t)(c0 / kFzBodies) * kFzSubs * kFzAImage, nc,
+                             vertices + (size_t)c0 * model->d.V * 3, s));
+    }
     if (p.regressed && (joints || kp2d)) {
       st = launch_regress(model, vertices, n, jbuf, cam, kp2d, s);
       if (st) return st;
@@ -1342,8 +1351,12 @@ int smplb200_push_rows(int32_t device, const float* joints, const float* kp2d, i
   }
   DeviceGuard guard(device);
   if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  // Spread thin over ALL SMs: the compute kernels this overlaps are persistent with a static work split, so
+  // what matters is the largest disturbance on any one SM, not the total.
+  int num_sms = 0;
+  CU_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
   const long long items = (long long)n * (kXchgRow / 4);
-  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((items + kXchgThreads - 1) / kXchgThreads, 64));
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((items + kXchgThreads - 1) / kXchgThreads, num_sms));
   k_push_rows<<<grid, kXchgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       peers, world, rank, joints, kp2d, n, row_offset, epoch, static_cast<unsigned int*>(counter));
   CU_TRY(cudaGetLastError());

@@ -27,6 +27,8 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
+import os
+_NOWAIT = os.environ.get("SMPLB200_XCHG_NOWAIT") == "1"      # measurement knob: push only, nobody waits for the peers
 ROW = 120   # floats per body in the gathered buffer: joints 72 | kp2d 48
 
 
@@ -100,6 +102,7 @@ class PeerExchange:
                 self.why_not_peer = f"{type(e).__name__}: {e}"
         if self.transport == "collective":
             self.buf = torch.zeros((self.slots, self.rows, ROW), dtype=torch.float32, device=self.device)
+        self._done = [torch.cuda.Event() for _ in range(self.slots)] if cuda else None
 
     def _setup_peer(self):
         import torch.distributed._symmetric_memory as symm_mem
@@ -121,6 +124,8 @@ class PeerExchange:
         self.buf = t[: self.slots * self.rows * ROW].view(self.slots, self.rows, ROW)
         self._lib = capi.lib()
         self._check = capi.check
+        self._push, self._wait = self._lib.smplb200_push_rows, self._lib.smplb200_wait_rows
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
 
     def exchange(self, joints: torch.Tensor, kp2d, ready=None):
         self.epoch += 1
@@ -134,26 +139,28 @@ class PeerExchange:
                 self.stream.wait_event(ready)
             else:
                 self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self.transport == "peer":          # two C calls on the side stream; no torch stream context needed
+            idx, s, ep = self._dev_index, self.stream.cuda_stream, self.epoch & 0xFFFFFFFF
+            st = self._push(idx, joints.data_ptr(), None if kp2d is None else kp2d.data_ptr(), n, lo,
+                            self._peer_slots[slot], self._peer_flags, self.world, self.rank, ep, self._counter, s)
+            if not _NOWAIT:
+                st = st or self._wait(idx, self._my_flags, self.world, ep, s)
+            if st:
+                self._check(st, "smplb200_push_rows / smplb200_wait_rows")
+            done = self._done[slot]
+            done.record(self.stream)
+            rows = out[: self.n_total] if self.per * self.world != self.n_total else out
+            return rows[:, :72].unflatten(1, (24, 3)), rows[:, 72:].unflatten(1, (24, 2)), done
         ctx = torch.cuda.stream(self.stream) if self.stream is not None else _Null()
         with ctx:
-            if self.transport == "peer":
-                idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-                s = self.stream.cuda_stream
-                self._check(self._lib.smplb200_push_rows(
-                    idx, joints.data_ptr(), None if kp2d is None else kp2d.data_ptr(), n, lo,
-                    self._peer_slots[slot], self._peer_flags, self.world, self.rank, self.epoch & 0xFFFFFFFF,
-                    self._counter, s), "smplb200_push_rows")
-                self._check(self._lib.smplb200_wait_rows(idx, self._my_flags, self.world, self.epoch & 0xFFFFFFFF, s),
-                            "smplb200_wait_rows")
+            send = joints.new_zeros((self.per, ROW))
+            send[:n, :72] = joints.reshape(n, 72)
+            if kp2d is not None:
+                send[:n, 72:] = kp2d.reshape(n, 48)
+            if self.world > 1:
+                dist.all_gather_into_tensor(out.view(-1), send.view(-1), group=self.group)
             else:
-                send = joints.new_zeros((self.per, ROW))
-                send[:n, :72] = joints.reshape(n, 72)
-                if kp2d is not None:
-                    send[:n, 72:] = kp2d.reshape(n, 48)
-                if self.world > 1:
-                    dist.all_gather_into_tensor(out.view(-1), send.view(-1), group=self.group)
-                else:
-                    out.copy_(send)
+                out.copy_(send)
             if self.stream is not None:
                 done = torch.cuda.Event()
                 done.record(self.stream)

@@ -291,6 +291,49 @@ class GraphedSMPL:
         return (self.vertices, self.joints) if self.kp2d is None else (self.vertices, self.joints, self.kp2d)
 
 
+class StaticSMPL:
+    """Inference runner with STATIC device buffers for a fixed batch size: inputs (``betas``, ``pose``, ``cam``),
+    outputs and workspace are allocated once, so ``run()`` is a single C call (``smplb200_forward_opts``) --
+    ~10 us of host time instead of the ~60 us the general ``SMPL.forward`` spends validating, allocating and
+    marshalling.  A serving loop at 4096 bodies is otherwise HOST-bound (the device step is 0.14 ms).
+    Write new parameters into the input tensors (``copy_``), call ``run()``, read the outputs in stream order.
+    """
+
+    def __init__(self, smpl: "SMPL", n: int, device, with_cam: bool = True):
+        self.smpl, self.n = smpl, int(n)
+        self.device = dev = torch.device(device)
+        self.h = smpl.handle(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.betas = torch.zeros((n, smpl.num_betas), **f32)
+        self.pose = torch.zeros((n, 3 * smpl.num_joints), **f32)
+        self.cam = torch.zeros((n, 3), **f32) if with_cam else None
+        self.vertices = torch.empty((n, smpl.num_verts, 3), **f32)
+        self.joints = torch.empty((n, smpl.num_joints, 3), **f32)
+        self.kp2d = torch.empty((n, smpl.num_joints, 2), **f32) if with_cam else None
+        self.ws_bytes = self.h.workspace_bytes(n, smpl.flags)
+        if self.ws_bytes == 0:
+            raise RuntimeError("smplb200_workspace_bytes rejected the flag combination")
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self._fn = capi.lib().smplb200_forward_opts
+        self._args = (self.h.ptr, _ptr(self.betas), _ptr(self.pose), _ptr(self.cam), self.n, _ptr(self.vertices),
+                      _ptr(self.joints), _ptr(self.kp2d), _ptr(self.ws), self.ws_bytes, smpl.flags)
+        self._opts = {}
+
+    def run(self, stream=None, joints_ready=None):
+        s = _stream_ptr(self.device) if stream is None else stream.cuda_stream
+        opts = None
+        if joints_ready is not None:
+            key = id(joints_ready)
+            opts = self._opts.get(key)
+            if opts is None:          # the ctypes struct is built once per event object
+                opts = self._opts[key] = (capi.forward_opts(joints_ready), joints_ready)
+            opts = opts[0]
+        st = self._fn(*self._args, s, opts)
+        if st:
+            capi.check(st, "smplb200_forward")
+        return (self.vertices, self.joints) if self.kp2d is None else (self.vertices, self.joints, self.kp2d)
+
+
 class HostRunner:
     """End-to-end runner over HOST buffers through ``smplb200_forward_host``.
 
