@@ -682,8 +682,11 @@ def bench_n64(torch, SMPL, GraphedSMPL, synthetic, model, dev, run_peaks):
     n = 64
     b, p, c = synthetic.make_inputs(n, 21)
     ref = smpl_forward(model, b, p, c, dtype=torch.float32)
-    out = {"workload": "SMPL forward batch 64 (BASELINE.json configs[1]), CUDA-graph replay of one smplb200_forward, L2-warm"}
-    for name, kw in (("fp32", dict(precision="fp32", lbs="auto")), ("auto", dict(precision="auto", lbs="auto"))):
+    out = {"workload": "SMPL forward batch 64 (BASELINE.json configs[1]), CUDA-graph replay of one smplb200_forward, L2-warm",
+           "modes": "fp32 = FMA blendshapes + FMA skinning (the config's regime); auto = split-bf16 tcgen05 blendshapes + FMA "
+                    "skinning (<= 1e-5 m); f16 = the fused tcgen05 kernel (<= 5e-5 m)"}
+    for name, kw in (("fp32", dict(precision="fp32", lbs="auto")), ("auto", dict(precision="auto", lbs="auto")),
+                     ("f16", dict(precision="f16"))):
         lay = SMPL(model, **kw).to(dev)
         g = GraphedSMPL(lay, n, dev)
         g.betas.copy_(torch.from_numpy(b)); g.pose.copy_(torch.from_numpy(p)); g.cam.copy_(torch.from_numpy(c))
@@ -692,7 +695,7 @@ def bench_n64(torch, SMPL, GraphedSMPL, synthetic, model, dev, run_peaks):
         dt = min(time_loop(g.replay, 200, torch) / 200 for _ in range(3))
         v, j, k = g.replay()
         torch.cuda.synchronize()
-        atol = 1e-6 if name == "fp32" else 1e-5
+        atol = {"fp32": 1e-6, "auto": 1e-5, "f16": 5e-5}[name]
         ok = (torch.allclose(v.cpu(), ref[0], rtol=1e-5, atol=atol) and torch.allclose(j.cpu(), ref[1], rtol=1e-5, atol=1e-6)
               and torch.allclose(k.cpu(), ref[2], rtol=1e-5, atol=2e-6))
         assert ok, f"configs[1] parity failed ({name})"

@@ -24,7 +24,7 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def short(name):
-    for k in ("k_blend_tc", "k_lbs_tc", "k_pose_chain", "k_blend_fma", "k_lbs_fma", "k_regress_joints", "k_pack"):
+    for k in ("k_fused_tc", "k_blend_tc", "k_lbs_tc", "k_pose_chain", "k_blend_fma", "k_lbs_fma", "k_regress_joints", "k_pack"):
         if k in name:
             return k
     return name[:40]
@@ -37,6 +37,12 @@ def main(tag):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    rep2 = os.path.join(ROOT, "gpurun_out", f"{tag}_full_unfused.ncu-rep")       # second capture: the unfused kernels
+    if os.path.exists(rep2):
+        raw2 = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows2 = list(csv.reader(io.StringIO(raw2)))
+        if rows2 and rows2[0] == hdr:
+            data = data + rows2[2:]
     idx = {h: i for i, h in enumerate(hdr)}
     summary = {"tag": tag, "source": f"ncu --set full --clock-control none ({os.path.basename(rep)})", "kernels": {}}
     sel = [["kernel"] + KEEP, ["unit"] + [units[idx[k]] if k in idx else "" for k in KEEP]]
