@@ -15,7 +15,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmpl_b200.so")
+# SMPLB200_LIB: A/B timing of two builds of the same source inside one GPU session (scripts/ab_fused.sh)
+LIB_PATH = os.environ.get("SMPLB200_LIB") or os.path.join(_HERE, "libsmpl_b200.so")
 
 # ---- constants mirrored from smpl_b200.h -------------------------------------------------------
 OK = 0

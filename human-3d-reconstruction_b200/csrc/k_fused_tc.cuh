@@ -44,6 +44,22 @@
 #include "k_chain.cuh"
 #include "ptx.cuh"
 
+// epilogue variants (A/B-timed on one box, scripts/build_variant.sh)
+#ifndef FZ_STORE
+#define FZ_STORE 1        // 0: shared-memory transpose row  1: direct 12-byte-stride stores  2: register shuffles
+#endif
+#ifndef FZ_SPIN
+#define FZ_SPIN 0         // busy-poll (test_wait) instead of try_wait on the two accumulator hand-off waits
+#endif
+#if FZ_SPIN
+#define FZ_CHAIN_WAIT ptx::mbar_wait_spin
+#else
+#define FZ_CHAIN_WAIT ptx::mbar_wait_nohint
+#endif
+#ifndef FZ_DPREFETCH
+#define FZ_DPREFETCH 0    // fetch the D columns one sub-block ahead
+#endif
+
 namespace smplb200 {
 
 constexpr int kFzBodies = 64;                       // bodies per unit (N of the D MMAs)
@@ -59,7 +75,10 @@ constexpr uint32_t kFzPlaneLo = kFzShapeK * 128 * 2;            // 4,096
 constexpr uint32_t kFzBasisBytes = 3 * (kFzPlaneHi + kFzPlaneLo);   // 184,320 per vertex tile
 constexpr uint32_t kFzCoefLo = kFzShapeK * kFzBodies * 2;       // 2,048
 constexpr uint32_t kFzCoefBlock = kFzCoefLo + kCoefK * kFzBodies * 2;   // 30,720 per 64-body block
-constexpr int kFzDLead = 6;                                     // D groups run this many sub-blocks ahead of the pacing
+#ifndef FZ_LEAD
+#define FZ_LEAD 6
+#endif
+constexpr int kFzDLead = FZ_LEAD;                                     // D groups run this many sub-blocks ahead of the pacing
 constexpr int kFzChunks = 7;                                    // K chunks per unit: 2 k-steps each
 constexpr uint32_t kFzCoefStage = kFzCoefLo + 2 * 2048;         // 6,144 (chunk 0 carries the lo rows too)
 constexpr int kFzCoefStages = 3;
@@ -293,39 +312,53 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
     int blk = (int)(u0 % nblk);
     bool new_tile = true;
     uint32_t w_phase = 0;
-    int as = 0; uint32_t a_phase = 0;           // this slot's A' ring: stage / parity of its next image
+    // This loop is ON the accumulator hand-off chain (epilogue frees T -> this warp issues -> MMAs -> epilogue),
+    // so it is written to be short: the ring has two stages and a slot takes eight sub-blocks per unit, so the
+    // stage is (iteration & 1) -- the loop is unrolled by two and all eight shared-memory descriptors (2 stages x
+    // 4 K steps), the barrier addresses and the pace word's address are loop-invariant registers.
+    uint64_t dsc[kFzAStages][4];
+#pragma unroll
+    for (int st = 0; st < kFzAStages; ++st) {
+      const uint32_t a_addr = a_addr0 + (e * kFzAStages + st) * kFzAImage;
+      dsc[st][0] = dS(a_addr);              // A_hi joints 0..15
+      dsc[st][1] = dS(a_addr + 2 * kLbo);   // A_hi 16..23 | (A_lo 0..7 x 0)
+      dsc[st][2] = dS(a_addr + 3 * kLbo);   // A_lo joints 0..15
+      dsc[st][3] = dS(a_addr + 5 * kLbo);   // A_lo 16..23 | zeros
+    }
+    const uint32_t pace_addr = ptx::smem_u32(const_cast<uint32_t*>(pace));
+    uint32_t a_phase = 0;                       // parity of this slot's A' ring (flips every two sub-blocks)
     uint32_t te_phase = 1;                      // parity of the bar_tempty wait: the buffer starts free
     for (int i = 0; i < nunits; ++i) {
       if (new_tile) { ptx::mbar_wait_nohint(bar_w, w_phase); w_phase ^= 1; }     // the tile's W' rows are in TMEM
 #pragma unroll 1
-      for (int sb = e; sb < kFzSubs; sb += 2) {
-        SMPLB200_PROGRESS((i << 8) | sb);
-        // operand first (it has usually landed long ago), then the accumulator: when the epilogue frees the T
-        // buffer nothing but the issue itself stands between that arrival and the next blend
-        { FZ_T0(); ptx::mbar_wait_nohint(bar_afull + e * kFzAStages + as, a_phase); FZ_ACC(fz_a1); }
-        { FZ_T0(); ptx::mbar_wait_nohint(bar_tempty + e, te_phase); FZ_ACC(fz_a0); }
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t a_addr = a_addr0 + (e * kFzAStages + as) * kFzAImage;
-          const uint64_t s0 = dS(a_addr);              // A_hi joints 0..15
-          const uint64_t s1 = dS(a_addr + 2 * kLbo);   // A_hi 16..23 | (A_lo 0..7 x 0)
-          const uint64_t s2 = dS(a_addr + 3 * kLbo);   // A_lo joints 0..15
-          const uint64_t s3 = dS(a_addr + 5 * kLbo);   // A_lo 16..23 | zeros
-          if (!(dbg & 2)) {
-          ptx::mma_bf16_ts(t_tmem, tmem_w, s0, kFzIdescT, 0u);        // W_hi * A_hi
-          ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s1, kFzIdescT, 1u);
-          ptx::mma_bf16_ts(t_tmem, tmem_w, s2, kFzIdescT, 1u);        // W_hi * A_lo
-          ptx::mma_bf16_ts(t_tmem, tmem_w + 8, s3, kFzIdescT, 1u);
-          ptx::mma_bf16_ts(t_tmem, tmem_w + 16, s0, kFzIdescT, 1u);   // W_lo * A_hi
-          ptx::mma_bf16_ts(t_tmem, tmem_w + 24, s1, kFzIdescT, 1u);
+      for (int sb = e; sb < kFzSubs; sb += 4) {
+#pragma unroll
+        for (int st = 0; st < kFzAStages; ++st) {
+          SMPLB200_PROGRESS((i << 8) | (sb + 2 * st));
+          // operand first (it has usually landed long ago), then the accumulator: when the epilogue frees the
+          // T buffer nothing but the issue itself stands between that arrival and the next blend
+          { FZ_T0(); ptx::mbar_wait_nohint(bar_afull + e * kFzAStages + st, a_phase); FZ_ACC(fz_a1); }
+          { FZ_T0(); FZ_CHAIN_WAIT(bar_tempty + e, te_phase); FZ_ACC(fz_a0); }
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            if (!(dbg & 2)) {
+              ptx::mma_bf16_ts(t_tmem, tmem_w, dsc[st][0], kFzIdescT, 0u);        // W_hi * A_hi
+              ptx::mma_bf16_ts(t_tmem, tmem_w + 8, dsc[st][1], kFzIdescT, 1u);
+              ptx::mma_bf16_ts(t_tmem, tmem_w, dsc[st][2], kFzIdescT, 1u);        // W_hi * A_lo
+              ptx::mma_bf16_ts(t_tmem, tmem_w + 8, dsc[st][3], kFzIdescT, 1u);
+              ptx::mma_bf16_ts(t_tmem, tmem_w + 16, dsc[st][0], kFzIdescT, 1u);   // W_lo * A_hi
+              ptx::mma_bf16_ts(t_tmem, tmem_w + 24, dsc[st][1], kFzIdescT, 1u);
+            }
+            ptx::tc_commit(bar_aempty + e * kFzAStages + st);
+            ptx::tc_commit(bar_tfull + e);
+            if (e == 1)       // lets the D issuer release its next chunks
+              asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(pace_addr),
+                           "r"((uint32_t)i * kFzSubs + (uint32_t)(sb + 2 * st) + 1u) : "memory");
           }
-          ptx::tc_commit(bar_aempty + e * kFzAStages + as);
-          ptx::tc_commit(bar_tfull + e);
-          if (e == 1) *pace = (uint32_t)i * kFzSubs + (uint32_t)sb + 1u;      // lets the D issuer release its next groups
+          __syncwarp();
+          te_phase ^= 1;
         }
-        __syncwarp();
-        te_phase ^= 1;
-        if (++as == kFzAStages) { as = 0; a_phase ^= 1; }
+        a_phase ^= 1;
       }
       new_tile = (blk + 1 == nblk);
       blk = new_tile ? 0 : blk + 1;
@@ -341,6 +374,12 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
     const int q = warp & 3, e = (ew >> 2) & 1, h = ew >> 3;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     float* so = sOut + ew * 96;
+    (void)so;
+#if FZ_STORE == 2
+    int src_lane[3], src_comp[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { src_lane[j] = (32 * j + lane) / 3; src_comp[j] = (32 * j + lane) % 3; }
+#endif
     long long cur_tile = -1;
     int t_cnt = 0;                    // sub-blocks this warp has consumed (phase of its T buffer)
     uint32_t wf_phase = 0;            // parity of the next bar_wfree wait (slot 0 only)
@@ -383,32 +422,37 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
       const int warp_v0 = (int)tile * 128 + q * 32;
       const int nf = max(0, min(32, V - warp_v0)) * 3;    // floats this warp may store per body
       { FZ_T0(); ptx::mbar_wait_nohint(bar_dfull + a, (i >> 1) & 1); FZ_ACC(fz_a0); }
+      const uint32_t d_addr0 = tmem_base + kFzTmemD + lane_addr + a * 3 * kFzBodies + 2 * h;
+      uint32_t dx[2], dy[2], dz[2];
+#if FZ_DPREFETCH
+      // this warp's D values (two bodies x three planes) are fetched one sub-block ahead: the unit's D is
+      // complete (bar_dfull), so the load for sub-block sb+2 overlaps the work on sub-block sb
+      ptx::tc_fence_after();
+      ptx::tmem_ld2(d_addr0 + e * kFzSub, dx);
+      ptx::tmem_ld2(d_addr0 + e * kFzSub + kFzBodies, dy);
+      ptx::tmem_ld2(d_addr0 + e * kFzSub + 2 * kFzBodies, dz);
+#endif
       for (int sb = e; sb < kFzSubs; sb += 2) {
         const long long b0 = (long long)blk * kFzBodies + sb * kFzSub;
         SMPLB200_PROGRESS((i << 8) | sb);
-        { FZ_T0(); ptx::mbar_wait_nohint(bar_tfull + e, t_cnt & 1); FZ_ACC(fz_a1); }
+        { FZ_T0(); FZ_CHAIN_WAIT(bar_tfull + e, t_cnt & 1); FZ_ACC(fz_a1); }
         ++t_cnt;
         ptx::tc_fence_after();
-        uint32_t r0[16], r1[8], dx[2], dy[2], dz[2];
+        uint32_t r0[16], r1[8];
         const uint32_t t_addr = tmem_base + kFzTmemT + lane_addr + e * kFzNT + h * 24;
-        const uint32_t d_addr = tmem_base + kFzTmemD + lane_addr + a * 3 * kFzBodies + sb * kFzSub + 2 * h;
         ptx::tmem_ld16(t_addr, r0);
         ptx::tmem_ld8(t_addr + 16, r1);
-        ptx::tmem_ld_wait();
+        ptx::tmem_ld_wait();                                   // (also completes a pending D prefetch)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_tempty + e);      // T buffer free: the next blend of this slot may start
         __syncwarp();
-        ptx::tmem_ld2(d_addr, dx);
-        ptx::tmem_ld2(d_addr + kFzBodies, dy);
-        ptx::tmem_ld2(d_addr + 2 * kFzBodies, dz);
+#if !FZ_DPREFETCH
+        ptx::tmem_ld2(d_addr0 + sb * kFzSub, dx);
+        ptx::tmem_ld2(d_addr0 + sb * kFzSub + kFzBodies, dy);
+        ptx::tmem_ld2(d_addr0 + sb * kFzSub + 2 * kFzBodies, dz);
         ptx::tmem_ld_wait();
-        if (sb + 2 >= kFzSubs) {                                // this warp's last read of the unit's D
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bar_dempty + a);
-          __syncwarp();
-        }
+#endif
         float T[24];
 #pragma unroll
         for (int k = 0; k < 16; ++k) T[k] = __uint_as_float(r0[k]);
@@ -423,28 +467,72 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
           res[3 * bb + 1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
           res[3 * bb + 2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
         }
+#if FZ_DPREFETCH
+        if (sb + 2 < kFzSubs) {                                 // prefetch the next sub-block's D columns
+          ptx::tmem_ld2(d_addr0 + (sb + 2) * kFzSub, dx);
+          ptx::tmem_ld2(d_addr0 + (sb + 2) * kFzSub + kFzBodies, dy);
+          ptx::tmem_ld2(d_addr0 + (sb + 2) * kFzSub + 2 * kFzBodies, dz);
+        } else
+#else
+        if (sb + 2 >= kFzSubs)
+#endif
+        {                                                       // this warp has read all it needs of the unit's D
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar_dempty + a);
+          __syncwarp();
+        }
         const long long bh = b0 + 2 * h;                       // first of this warp's two bodies
+#if FZ_STORE == 1
+        // DIRECT stores: lane = vertex writes its own x, y, z (12-byte stride across the warp); the three store
+        // instructions of a body together cover the warp's 384 contiguous bytes
+        if (lane < nf / 3) {
+          float* d = verts + ((size_t)bh * V + warp_v0 + lane) * 3;
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            if (bh + bb < n) { d[0] = res[3 * bb]; d[1] = res[3 * bb + 1]; d[2] = res[3 * bb + 2]; }
+            d += body_stride;
+          }
+        }
+#else
         float* dst = verts + ((size_t)bh * V + warp_v0) * 3 + lane;
         const bool full = bh + 2 <= n && nf == 96;             // both bodies, whole warp: unpredicated stores
-        // xyz interleave through a per-warp shared-memory row (one body per pass: the shared-memory budget
-        // goes to the basis), then coalesced 128-byte stores
 #pragma unroll
         for (int bb = 0; bb < 2; ++bb) {
+          float o0, o1, o2;
+#if FZ_STORE == 2
+          // xyz interleave IN REGISTERS: element 32j + lane of the warp's 96 output floats is component
+          // (32j + lane) % 3 of vertex (32j + lane) / 3: three shuffles (one per component) and a select each
+          float o[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float t0 = __shfl_sync(0xffffffffu, res[3 * bb], src_lane[j]);
+            const float t1 = __shfl_sync(0xffffffffu, res[3 * bb + 1], src_lane[j]);
+            const float t2 = __shfl_sync(0xffffffffu, res[3 * bb + 2], src_lane[j]);
+            o[j] = src_comp[j] == 0 ? t0 : (src_comp[j] == 1 ? t1 : t2);
+          }
+          o0 = o[0]; o1 = o[1]; o2 = o[2];
+#else
+          // xyz interleave through a per-warp shared-memory row (one body per pass: the shared-memory budget
+          // goes to the basis), then coalesced 128-byte stores
           float* sbuf = so + 3 * lane;
           sbuf[0] = res[3 * bb]; sbuf[1] = res[3 * bb + 1]; sbuf[2] = res[3 * bb + 2];
           __syncwarp();
-          const float o0 = so[lane], o1 = so[lane + 32], o2 = so[lane + 64];
+          o0 = so[lane]; o1 = so[lane + 32]; o2 = so[lane + 64];
+#endif
           float* d = dst + bb * body_stride;
-          if (dbg & 4) {
-          } else if (full) {
+          if (full) {
             d[0] = o0; d[32] = o1; d[64] = o2;
           } else if (bh + bb < n) {
             if (lane < nf) d[0] = o0;
             if (lane + 32 < nf) d[32] = o1;
             if (lane + 64 < nf) d[64] = o2;
           }
+#if FZ_STORE == 0
           __syncwarp();          // the row is reused by the next pass
+#endif
         }
+#endif
       }
     }
     if (q == 0 && h == 0) { FZ_OUT(10 + 2 * e, fz_a0); FZ_OUT(11 + 2 * e, fz_a1); }

@@ -102,6 +102,28 @@ __device__ __forceinline__ void mbar_wait_nohint(uint64_t* bar, uint32_t parity)
     }
   }
 }
+// Busy poll (mbarrier.test_wait, never suspends): the lowest-latency way to see a phase flip, at the price of
+// issue slots.  For the two waits on the fused kernel's accumulator hand-off chain only.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t it = 0;; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((it & 4095u) == 4095u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
 // Orders this thread's earlier generic-proxy shared-memory accesses (made visible to it by a
 // barrier) before later async-proxy operations (bulk copies) on the same locations.
 __device__ __forceinline__ void fence_proxy_async() {
