@@ -20,18 +20,18 @@ LIB_PATH = os.environ.get("SMPLB200_LIB") or os.path.join(_HERE, "libsmpl_b200.s
 
 # ---- constants mirrored from smpl_b200.h -------------------------------------------------------
 OK = 0
-PREC_AUTO, PREC_FP32, PREC_BF16, PREC_TF32, PREC_BF16X3, PREC_F16 = 0, 1, 2, 3, 4, 5
+PREC_AUTO, PREC_FP32, PREC_BF16, PREC_TF32, PREC_BF16X3, PREC_F16, PREC_F16X3 = 0, 1, 2, 3, 4, 5, 6
 PREC_MASK = 0x7
 JOINTS_KINEMATIC, JOINTS_REGRESSED = 0, 1 << 3
 ROTATE_BASE = 1 << 4
 LBS_AUTO, LBS_FMA, LBS_TC, LBS_DENSE = 0, 1 << 5, 2 << 5, 3 << 5
-TC_MIN_BATCH = 32        # AUTO: tcgen05 (bf16x3) blendshapes from this many bodies
+TC_MIN_BATCH = 32        # AUTO: tcgen05 (f16x3) blendshapes from this many bodies
 TC_LBS_MIN_BATCH = 384   # AUTO: tcgen05 skinning blend from this many bodies
 DCN_INPUT_NHWC = 1       # smplb200_dcn_v2_forward flag: the input tensor is already channels-last
 COEF_K = 224
 
 PRECISIONS = {"auto": PREC_AUTO, "fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32,
-              "bf16x3": PREC_BF16X3, "f16": PREC_F16}
+              "bf16x3": PREC_BF16X3, "f16": PREC_F16, "f16x3": PREC_F16X3}
 LBS_PATHS = {"auto": LBS_AUTO, "fma": LBS_FMA, "tc": LBS_TC, "dense": LBS_DENSE}
 
 

@@ -32,6 +32,8 @@ struct DeviceModel {
   // tensor-core operands (see k_blend_tc.cuh / k_lbs_tc.cuh)
   const uint32_t* basis_rows_bf16_hi;  // [NC][112] basis^T rows, 2 bf16 per word (TMEM A operand)
   const uint32_t* basis_rows_bf16_lo;  // same, low part of the 2-term bf16 split
+  const uint32_t* basis_rows_f16_hi;   // [NC][112] the same rows in fp16 (template split in three fp16 pieces)
+  const uint32_t* basis_rows_f16_lo;
   const uint32_t* basis_rows_tf32;     // [NC][224] tf32
   const uint32_t* w_tf32;              // [VP][48] skinning-weight rows, tf32 W_hi(24) | W_lo(24)
   // backward pass (k_backward.cuh)

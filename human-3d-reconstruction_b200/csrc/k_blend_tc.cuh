@@ -31,6 +31,7 @@
 // Precisions (operands; accumulation is always fp32 in TMEM):
 //   BF16    1 MMA group   hi*hi
 //   BF16X3  3 MMA groups  hi*hi + hi*lo + lo*hi   (~16 mantissa bits on each operand)
+//   F16X3   the same three groups with fp16 operands (~22 bits each): fp32-class, measured < 1e-6 m
 //   TF32    1 MMA group   kind::tf32
 #pragma once
 #include "common.cuh"
@@ -48,7 +49,8 @@ template <uint32_t PREC>
 struct BlendTcCfg {
   static constexpr bool kTf32 = PREC == SMPLB200_PREC_TF32;
   static constexpr int kElem = kTf32 ? 4 : 2;
-  static constexpr int kParts = PREC == SMPLB200_PREC_BF16X3 ? 2 : 1;   // hi (+ lo) operands
+  static constexpr bool kF16 = PREC == SMPLB200_PREC_F16X3;
+  static constexpr int kParts = (PREC == SMPLB200_PREC_BF16X3 || kF16) ? 2 : 1;   // hi (+ lo) operands
   static constexpr int kStages = 3;                                      // ring of K-half stages
   static constexpr int kKSteps = kCoefK * kElem / 32;                    // 14 (bf16) or 28 (tf32)
   static constexpr int kKHalf = kKSteps / 2;                             // MMA k-steps per stage
@@ -61,7 +63,7 @@ struct BlendTcCfg {
   static constexpr uint32_t kSmemBytes = kBarOffset + 256;
   static constexpr uint32_t kLboB = kCoefBlock * 16, kSbo = 128;
   static constexpr uint32_t kIdesc =
-      ptx::make_idesc(kTf32 ? ptx::kFmtTF32 : ptx::kFmtBF16, 128, kCoefBlock);
+      ptx::make_idesc(kTf32 ? ptx::kFmtTF32 : (kF16 ? ptx::kFmtF16 : ptx::kFmtBF16), 128, kCoefBlock);
   static_assert(kTcAccCols + kAColsPart * kParts <= kTcTmemCols, "TMEM budget");
   static_assert(kKSteps % 2 == 0, "K halves");
 };
@@ -260,7 +262,7 @@ k_blend_tc(const uint32_t* __restrict__ basis_hi, const uint32_t* __restrict__ b
 // k2 write the images directly).
 __global__ void __launch_bounds__(256)
 k_pack_coef(const float* __restrict__ coef, long long n, uint16_t* __restrict__ hi,
-            uint16_t* __restrict__ lo, uint32_t* __restrict__ tf) {
+            uint16_t* __restrict__ lo, uint32_t* __restrict__ tf, int f16) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * kCoefK) return;
   const long long b = idx / kCoefK;
@@ -269,10 +271,16 @@ k_pack_coef(const float* __restrict__ coef, long long n, uint16_t* __restrict__ 
   const long long blk = b / kCoefBlock;
   const int row = int(b % kCoefBlock);
   if (hi) {
-    const uint16_t h = f32_to_bf16_rn(v);
     const size_t off = (size_t)blk * (kCoefK * kCoefBlock) + (size_t)(k >> 3) * (kCoefBlock * 8) + row * 8 + (k & 7);
-    hi[off] = h;
-    if (lo) lo[off] = f32_to_bf16_rn(__fsub_rn(v, bf16_to_f32(h)));
+    if (f16) {
+      const __half h = __float2half_rn(v);
+      hi[off] = __half_as_ushort(h);
+      if (lo) lo[off] = __half_as_ushort(__float2half_rn(__fsub_rn(v, __half2float(h))));
+    } else {
+      const uint16_t h = f32_to_bf16_rn(v);
+      hi[off] = h;
+      if (lo) lo[off] = f32_to_bf16_rn(__fsub_rn(v, bf16_to_f32(h)));
+    }
   }
   if (tf)
     tf[(size_t)blk * (kCoefK * kCoefBlock) + (size_t)(k >> 2) * (kCoefBlock * 4) + row * 4 + (k & 3)] =
@@ -294,9 +302,9 @@ inline void blend_tc_launch(const DeviceModel& m, int num_sms, const void* chi, 
   const int nblocks = (int)((n + kCoefBlock - 1) / kCoefBlock);
   const long long total = (long long)npair * nblocks;                 // (tile pair, body block) units
   const unsigned grid = 2u * (unsigned)std::min<long long>(num_sms / 2, total);   // CTA pairs
-  const uint32_t* bh = C::kTf32 ? m.basis_rows_tf32 : m.basis_rows_bf16_hi;
+  const uint32_t* bh = C::kTf32 ? m.basis_rows_tf32 : (C::kF16 ? m.basis_rows_f16_hi : m.basis_rows_bf16_hi);
   k_blend_tc<PREC><<<grid, kTcThreads, C::kSmemBytes, s>>>(
-      bh, m.basis_rows_bf16_lo, static_cast<const uint8_t*>(chi), static_cast<const uint8_t*>(clo), n,
+      bh, C::kF16 ? m.basis_rows_f16_lo : m.basis_rows_bf16_lo, static_cast<const uint8_t*>(chi), static_cast<const uint8_t*>(clo), n,
       nblocks, total, m.NC, vposed);
 }
 
@@ -308,6 +316,7 @@ inline cudaError_t launch_blend_tc(const DeviceModel& m, int num_sms, uint32_t p
     case SMPLB200_PREC_BF16: blend_tc_launch<SMPLB200_PREC_BF16>(m, num_sms, chi, nullptr, n, vposed, s); break;
     case SMPLB200_PREC_BF16X3: blend_tc_launch<SMPLB200_PREC_BF16X3>(m, num_sms, chi, clo, n, vposed, s); break;
     case SMPLB200_PREC_TF32: blend_tc_launch<SMPLB200_PREC_TF32>(m, num_sms, ctf, nullptr, n, vposed, s); break;
+    case SMPLB200_PREC_F16X3: blend_tc_launch<SMPLB200_PREC_F16X3>(m, num_sms, chi, clo, n, vposed, s); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

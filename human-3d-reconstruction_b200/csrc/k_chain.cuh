@@ -23,6 +23,7 @@ struct ChainOut {
   float* joints;          // [n, 24, 3] or null
   uint16_t* coef_bf16_hi; // tensor-core operand images (null unless a tcgen05 path follows)
   uint16_t* coef_bf16_lo;
+  int coef_is_f16;        // the two 16-bit images hold fp16 (SMPLB200_PREC_F16X3) instead of bf16
   uint32_t* coef_tf32;
   uint32_t* a_tf32;       // [n/8 blocks][12 chunks][96 rows][4] tf32 hi|lo image of A (LBS blend)
   uint8_t* fz_coef;       // fused kernel: fp16 coef images per 64-body block (k_fused_tc.cuh), or null
@@ -217,10 +218,17 @@ k_pose_chain(DeviceModel m, const float* __restrict__ betas, const float* __rest
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float v0 = sc[8 * lane + 2 * u], v1 = sc[8 * lane + 2 * u + 1];
-        const uint16_t h0 = f32_to_bf16_rn(v0), h1 = f32_to_bf16_rn(v1);
-        wh[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-        wl[u] = (uint32_t)f32_to_bf16_rn(__fsub_rn(v0, bf16_to_f32(h0))) |
-                ((uint32_t)f32_to_bf16_rn(__fsub_rn(v1, bf16_to_f32(h1))) << 16);
+        if (out.coef_is_f16) {
+          const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+          wh[u] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          wl[u] = (uint32_t)__half_as_ushort(__float2half_rn(__fsub_rn(v0, __half2float(h0)))) |
+                  ((uint32_t)__half_as_ushort(__float2half_rn(__fsub_rn(v1, __half2float(h1)))) << 16);
+        } else {
+          const uint16_t h0 = f32_to_bf16_rn(v0), h1 = f32_to_bf16_rn(v1);
+          wh[u] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          wl[u] = (uint32_t)f32_to_bf16_rn(__fsub_rn(v0, bf16_to_f32(h0))) |
+                  ((uint32_t)f32_to_bf16_rn(__fsub_rn(v1, bf16_to_f32(h1))) << 16);
+        }
       }
       const size_t off = (size_t)lane * kCoefBlock + row;    // in 16-byte chunks
       hi[off] = make_uint4(wh[0], wh[1], wh[2], wh[3]);

@@ -21,7 +21,6 @@
 #include "k_blend_fma.cuh"
 #include "k_lbs_fma.cuh"
 #include "k_blend_tc.cuh"
-#include "k_blend_tc2.cuh"
 #include "k_lbs_tc.cuh"
 #include "k_fused_tc.cuh"
 #include "k_decode.cuh"
@@ -36,7 +35,6 @@ struct SmplB200Model {
   DeviceModel d;
   int device = 0;
   int num_sms = 0;
-  int k1_variant = 1;   // tensor-core blendshape kernel: 1 = 1-SM MMA (multicast pairs), 2 = 2-SM MMA
   int chunk = 0;        // bodies per k1->k3 pass (tensor-core paths); 0 = whole batch in one pass
   bool lbs_bwd_staged = false;   // backward skinning kernel stages a body's g_v + vposed in smem
   void* blob = nullptr;
@@ -48,7 +46,6 @@ namespace {
 thread_local int tl_last_cuda_error = 0;
 
 constexpr int kDefaultChunk = 0;
-constexpr int kDefaultK1Variant = 1;
 constexpr long long kMaxGridYBodies16 = 65535LL * 16;   // FMA kernels: 16 bodies per grid.y slot
 
 inline int cuda_fail(cudaError_t e) {
@@ -62,6 +59,8 @@ inline int cuda_fail(cudaError_t e) {
   } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline bool prec_16bit(uint32_t p) { return p == SMPLB200_PREC_BF16 || p == SMPLB200_PREC_BF16X3 || p == SMPLB200_PREC_F16X3; }
+inline bool prec_split16(uint32_t p) { return p == SMPLB200_PREC_BF16X3 || p == SMPLB200_PREC_F16X3; }
 
 // RAII device switch: the library always runs on the model's device and restores the caller's.
 struct DeviceGuard {
@@ -169,10 +168,10 @@ struct Plan {
 
 bool resolve_plan(const SmplB200Model* m, long long n, uint32_t flags, Plan* p) {
   uint32_t prec = flags & SMPLB200_PREC_MASK;
-  if (prec > SMPLB200_PREC_F16) return false;
+  if (prec > SMPLB200_PREC_F16X3) return false;
   if (prec == SMPLB200_PREC_F16 && !m->d.fz_basis) return false;      // model has too many betas for the fused kernel
   if (prec == SMPLB200_PREC_AUTO)
-    prec = n >= SMPLB200_TC_MIN_BATCH ? SMPLB200_PREC_BF16X3 : SMPLB200_PREC_FP32;
+    prec = n >= SMPLB200_TC_MIN_BATCH ? SMPLB200_PREC_F16X3 : SMPLB200_PREC_FP32;
   uint32_t lbs = flags & SMPLB200_LBS_MASK;
   if (lbs == SMPLB200_LBS_AUTO)
     lbs = n >= SMPLB200_TC_LBS_MIN_BATCH ? SMPLB200_LBS_TC : SMPLB200_LBS_FMA;
@@ -215,9 +214,8 @@ Workspace carve(const SmplB200Model* m, long long n, const Plan& p) {
   w.joints = take(nn * kJ * 3 * sizeof(float));
   const size_t coef_blocks = (nn + kCoefBlock - 1) / kCoefBlock;
   const size_t lbs_blocks = (nn + kLbsBlock - 1) / kLbsBlock;
-  if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
-    w.coef_hi = take(coef_blocks * kCoefBlock * kCoefK * 2);
-  if (p.prec == SMPLB200_PREC_BF16X3) w.coef_lo = take(coef_blocks * kCoefBlock * kCoefK * 2);
+  if (prec_16bit(p.prec)) w.coef_hi = take(coef_blocks * kCoefBlock * kCoefK * 2);
+  if (prec_split16(p.prec)) w.coef_lo = take(coef_blocks * kCoefBlock * kCoefK * 2);
   if (p.prec == SMPLB200_PREC_TF32) w.coef_tf32 = take(coef_blocks * kCoefBlock * kCoefK * 4);
   if (p.lbs == SMPLB200_LBS_TC) w.a_tf32 = take(lbs_blocks * kLbsBlock * 12 * kLbsK * 4);
   w.total = off;
@@ -295,9 +293,7 @@ cudaError_t configure_tc_kernels() {
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
   if ((e = blend_tc_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
-  if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16>()) != cudaSuccess) return e;
-  if ((e = blend_tc2_set_smem<SMPLB200_PREC_BF16X3>()) != cudaSuccess) return e;
-  if ((e = blend_tc2_set_smem<SMPLB200_PREC_TF32>()) != cudaSuccess) return e;
+  if ((e = blend_tc_set_smem<SMPLB200_PREC_F16X3>()) != cudaSuccess) return e;
   if ((e = blend_bwd_tc_set_smem<kBwdTf32>()) != cudaSuccess) return e;
   if ((e = blend_bwd_tc_set_smem<kBwdTf32x3>()) != cudaSuccess) return e;
   if ((e = blend_bwd_tc_set_smem<kBwdBf16x3>()) != cudaSuccess) return e;
@@ -308,11 +304,9 @@ cudaError_t configure_tc_kernels() {
                               (int)kLbsSmemBytes);
 }
 
-// k1 tensor-core variant: 1 = 1-SM MMA + multicast pairs, 2 = 2-SM (cta_group::2) MMA
 cudaError_t launch_blend_tc_any(const SmplB200Model* m, uint32_t prec, const uint16_t* chi,
                                 const uint16_t* clo, const uint32_t* ctf, long long n, float* vposed,
                                 cudaStream_t s) {
-  if (m->k1_variant == 2) return launch_blend_tc2(m->d, m->num_sms, prec, chi, clo, ctf, n, vposed, s);
   return launch_blend_tc(m->d, m->num_sms, prec, chi, clo, ctf, n, vposed, s);
 }
 
@@ -320,7 +314,7 @@ size_t coef_image_bytes(long long n, uint32_t prec) {
   const size_t blocks = ((size_t)std::max<long long>(n, 1) + kCoefBlock - 1) / kCoefBlock;
   const size_t one = blocks * kCoefBlock * kCoefK;
   if (prec == SMPLB200_PREC_BF16) return align_up(one * 2, 256);
-  if (prec == SMPLB200_PREC_BF16X3) return 2 * align_up(one * 2, 256);
+  if (prec_split16(prec)) return 2 * align_up(one * 2, 256);
   if (prec == SMPLB200_PREC_TF32) return align_up(one * 4, 256);
   return 0;
 }
@@ -534,6 +528,20 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
         blo[(size_t)col * kCoefK + k] = host_bf16(x - host_bf16_to_f32(h));
         btf[(size_t)col * kCoefK + k] = host_tf32(xt);
       }
+    // the same rows in fp16 (SMPLB200_PREC_F16X3): hi + residual, template as three fp16 pieces
+    std::vector<uint16_t> fhi((size_t)NC * kCoefK, 0), flo((size_t)NC * kCoefK, 0);
+    for (int col = 0; col < NC; ++col)
+      for (int k = 0; k < kCoefK; ++k) {
+        const int tp = k - (NB + kP);
+        float x = k < NB + kP ? basis[(size_t)k * NC + col] : 0.f;
+        if (tp >= 0 && tp < 3) {
+          float rem = basis[(size_t)(NB + kP) * NC + col];
+          for (int q = 0; q <= tp; ++q) { x = host_f16_to_f32(host_f16(rem)); rem -= x; }
+        }
+        const uint16_t h = host_f16(x);
+        fhi[(size_t)col * kCoefK + k] = h;
+        flo[(size_t)col * kCoefK + k] = host_f16(x - host_f16_to_f32(h));
+      }
     // skinning weights as the TMEM A operand of the LBS blend: rows [VP][48] = W_hi(24) | W_lo(24)
     std::vector<uint32_t> wtf((size_t)VP * kLbsK, 0);
     for (int v = 0; v < VP; ++v)
@@ -615,6 +623,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     const size_t o_bhi = bb.add(bhi.data(), bhi.size() * 2);
     const size_t o_blo = bb.add(blo.data(), blo.size() * 2);
     const size_t o_btf = bb.add(btf.data(), btf.size() * 4);
+    const size_t o_fhi = bb.add(fhi.data(), fhi.size() * 2);
+    const size_t o_flo = bb.add(flo.data(), flo.size() * 2);
     const size_t o_wtf = bb.add(wtf.data(), wtf.size() * 4);
     const size_t o_wp = bb.add(wptr.data(), wptr.size() * 4);
     const size_t o_wi = bb.add(widx.data(), widx.size() * 4);
@@ -658,7 +668,6 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     DeviceModel& d = m->d;
     d.V = V; d.VP = VP; d.NB = NB; d.KB = KB; d.NC = NC;
     d.max_nnz = max_nnz; d.max_depth = max_depth; d.jreg_nnz = (int)jval.size();
-    { const char* t = std::getenv("SMPLB200_K1"); m->k1_variant = (t && std::atoi(t) == 2) ? 2 : kDefaultK1Variant; }
     {  // bodies per k1->k3 pass: keeps the vposed intermediate L2-resident (multiple of 128)
       const char* t = std::getenv("SMPLB200_CHUNK");
       int c = t ? std::atoi(t) : kDefaultChunk;
@@ -678,6 +687,8 @@ int smplb200_model_create(const SmplB200ModelDesc* desc, SmplB200Model** out_mod
     d.basis_rows_bf16_hi = reinterpret_cast<const uint32_t*>(base + o_bhi);
     d.basis_rows_bf16_lo = reinterpret_cast<const uint32_t*>(base + o_blo);
     d.basis_rows_tf32 = reinterpret_cast<const uint32_t*>(base + o_btf);
+    d.basis_rows_f16_hi = reinterpret_cast<const uint32_t*>(base + o_fhi);
+    d.basis_rows_f16_lo = reinterpret_cast<const uint32_t*>(base + o_flo);
     d.w_tf32 = reinterpret_cast<const uint32_t*>(base + o_wtf);
     d.wcsr_ptr = reinterpret_cast<const int*>(base + o_wp);
     d.wcsr_idx = reinterpret_cast<const int*>(base + o_wi);
@@ -770,9 +781,9 @@ int smplb200_blendshapes(const SmplB200Model* model, const float* coef, int64_t 
   uint16_t* hi = nullptr; uint16_t* lo = nullptr; uint32_t* tf = nullptr;
   if (p.prec == SMPLB200_PREC_TF32) tf = reinterpret_cast<uint32_t*>(ws);
   else hi = reinterpret_cast<uint16_t*>(ws);
-  if (p.prec == SMPLB200_PREC_BF16X3) lo = reinterpret_cast<uint16_t*>(ws + need / 2);
+  if (prec_split16(p.prec)) lo = reinterpret_cast<uint16_t*>(ws + need / 2);
   const long long total = n * kCoefK;
-  k_pack_coef<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(coef, n, hi, lo, tf);
+  k_pack_coef<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(coef, n, hi, lo, tf, p.prec == SMPLB200_PREC_F16X3 ? 1 : 0);
   CU_TRY(cudaGetLastError());
   CU_TRY(launch_blend_tc_any(model, p.prec, hi, lo, tf, n, vposed, s));
   return SMPLB200_OK;
@@ -916,9 +927,9 @@ int smplb200_forward_opts(const SmplB200Model* model, const float* betas, const 
     return SMPLB200_OK;
   }
   if (p.prec == SMPLB200_PREC_FP32) out.coef = coef;
-  if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
-    out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.coef_hi);
-  if (p.prec == SMPLB200_PREC_BF16X3) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.coef_lo);
+  if (prec_16bit(p.prec)) out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.coef_hi);
+  if (prec_split16(p.prec)) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.coef_lo);
+  out.coef_is_f16 = p.prec == SMPLB200_PREC_F16X3 ? 1 : 0;
   if (p.prec == SMPLB200_PREC_TF32) out.coef_tf32 = reinterpret_cast<uint32_t*>(ws + w.coef_tf32);
   if (p.lbs == SMPLB200_LBS_TC) out.a_tf32 = reinterpret_cast<uint32_t*>(ws + w.a_tf32);
   // k4 for kinematic joints rides in k2 (the joints are final there); the skinning epilogue keeps its
@@ -999,13 +1010,13 @@ inline bool bwd_blend_tc(uint32_t flags, long long n) {
 // the unfused split-bf16 kernels (gradients do not depend on which forward precision produced the outputs).
 inline void bwd_plan(Plan* p, uint32_t* flags) {
   if (p->prec == SMPLB200_PREC_F16) {
-    p->prec = SMPLB200_PREC_BF16X3;
-    *flags = (*flags & ~SMPLB200_PREC_MASK) | SMPLB200_PREC_BF16X3;
+    p->prec = SMPLB200_PREC_F16X3;
+    *flags = (*flags & ~SMPLB200_PREC_MASK) | SMPLB200_PREC_F16X3;
   }
 }
 inline int bwd_blend_mode(uint32_t flags, const Plan& p) {
   if ((flags & SMPLB200_PREC_MASK) == SMPLB200_PREC_FP32) return kBwdTf32x3;
-  if (p.prec == SMPLB200_PREC_FP32 || p.prec == SMPLB200_PREC_BF16X3) return kBwdBf16x3;   // AUTO, BF16X3
+  if (p.prec == SMPLB200_PREC_FP32 || prec_split16(p.prec)) return kBwdBf16x3;   // AUTO, BF16X3, F16X3
   return kBwdTf32;
 }
 
@@ -1104,9 +1115,9 @@ int smplb200_backward(const SmplB200Model* model, const float* betas, const floa
     ChainOut out{};
     out.A = A;
     if (p.prec == SMPLB200_PREC_FP32) out.coef = coef;
-    if (p.prec == SMPLB200_PREC_BF16 || p.prec == SMPLB200_PREC_BF16X3)
-      out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_hi);
-    if (p.prec == SMPLB200_PREC_BF16X3) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_lo);
+    if (prec_16bit(p.prec)) out.coef_bf16_hi = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_hi);
+    if (prec_split16(p.prec)) out.coef_bf16_lo = reinterpret_cast<uint16_t*>(ws + w.fwd.coef_lo);
+    out.coef_is_f16 = p.prec == SMPLB200_PREC_F16X3 ? 1 : 0;
     if (p.prec == SMPLB200_PREC_TF32) out.coef_tf32 = reinterpret_cast<uint32_t*>(ws + w.fwd.coef_tf32);
     st = launch_chain(model, betas, pose, n, out, p.rotate_base, s);
     if (st) return st;

@@ -49,7 +49,7 @@ enum {
 
 /* ---- forward flags --------------------------------------------------------------------- */
 /* blendshape operand precision (accumulate and output are always fp32)                      */
-#define SMPLB200_PREC_AUTO   0u  /* fastest path within 1e-5 m: FP32 FMA below SMPLB200_TC_MIN_BATCH bodies, BF16X3 from there */
+#define SMPLB200_PREC_AUTO   0u  /* fastest path within 1e-5 m: FP32 FMA below SMPLB200_TC_MIN_BATCH bodies, F16X3 from there */
 #define SMPLB200_PREC_FP32   1u  /* vectorised FMA kernel, k-ascending single accumulator     */
 #define SMPLB200_PREC_BF16   2u  /* tcgen05 kind::f16, bf16 operands                          */
 #define SMPLB200_PREC_TF32   3u  /* tcgen05 kind::tf32                                        */
@@ -58,6 +58,8 @@ enum {
                                     operands: pose rows one MMA, shape rows + template exact 3-term split, skinning
                                     blend 3-term split.  Measured max vertex error 1.9e-5 m (stated bound 5e-5 m;
                                     TF32 operands: 1.9e-4).  Needs NB <= 13; the LBS flag must be AUTO or TC.     */
+#define SMPLB200_PREC_F16X3  6u  /* tcgen05, 3-term split FP16 (hi*hi + hi*lo + lo*hi; 11+11 significant bits per
+                                    operand): fp32-class blendshapes, measured < 1e-6 m; what AUTO resolves to        */
 #define SMPLB200_PREC_MASK   0x7u
 /* joint output: kinematic J_posed (default) or HMR-style regression from skinned vertices   */
 #define SMPLB200_JOINTS_KINEMATIC 0u

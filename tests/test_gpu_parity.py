@@ -3,6 +3,7 @@
 Tolerances (BASELINE.json north_star):
   fp32 path (FMA blendshapes; FMA or 3xTF32-tcgen05 skinning)   rtol 1e-5, atol 1e-6 vs fp32 oracle
   tensor-core blendshape operands, stated looser bounds on vertices (metres, abs):
+      f16x3  (split fp16, ~22 mantissa bits)  4e-6   (measured 1.9e-6; what 'auto' resolves to from 32 bodies)
       bf16x3 (split bf16, ~16 mantissa bits)  1e-5
       tf32                                      5e-4
       bf16                                      4e-3
@@ -23,7 +24,7 @@ from oracle.smpl_ref import smpl_forward, smpl_forward_chunked
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-5, 1e-6
-VERT_ATOL = {"fp32": None, "bf16x3": 1e-5, "tf32": 5e-4, "bf16": 4e-3}
+VERT_ATOL = {"fp32": None, "f16x3": 4e-6, "bf16x3": 1e-5, "tf32": 5e-4, "bf16": 4e-3}
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "smpl_golden_v1.npz")
 
 
@@ -76,7 +77,7 @@ def test_k2_pose_chain(dev, models, rotate_base):
     assert_close(joints, ref[1], what="J_posed")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "bf16x3", "tf32", "bf16"])
 @pytest.mark.parametrize("n", [1, 33, 70])
 def test_k1_blendshapes(dev, models, precision, n):
     betas, pose, _ = synthetic.make_inputs(n, 12)
@@ -127,7 +128,7 @@ def test_regressed_joints_kernel(dev, models):
 # the forward pass through smplb200_forward (nn.Module)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 31, 64, 257])
-@pytest.mark.parametrize("precision,lbs", [("fp32", "fma"), ("fp32", "tc"), ("bf16x3", "tc"),
+@pytest.mark.parametrize("precision,lbs", [("fp32", "fma"), ("fp32", "tc"), ("bf16x3", "tc"), ("f16x3", "tc"),
                                            ("tf32", "fma"), ("bf16", "tc"), ("auto", "auto")])
 def test_forward_vs_oracle(dev, models, n, precision, lbs):
     model = models["sparse"]
@@ -135,7 +136,7 @@ def test_forward_vs_oracle(dev, models, n, precision, lbs):
     ref_v, ref_j, ref_k = smpl_forward(model, betas, pose, cam)
     layer = SMPL(model, precision=precision, lbs=lbs).to(dev)
     v, j, k = layer(*to_dev(dev, betas, pose, cam))
-    eff = precision if precision != "auto" else ("bf16x3" if n >= capi.TC_MIN_BATCH else "fp32")
+    eff = precision if precision != "auto" else ("f16x3" if n >= capi.TC_MIN_BATCH else "fp32")
     check_verts(v, ref_v, eff, f"vertices n={n} {precision}/{lbs}")
     assert_close(j, ref_j, what="joints")
     assert_close(k, ref_k, atol=2e-6, what="kp2d")
@@ -185,7 +186,7 @@ def test_shard_equivalence_bitwise(dev, models):
     """A.9(viii): no cross-body term => forward(N) == concat(forward(shards)) bit for bit per path."""
     betas, pose, cam = synthetic.make_inputs(300, 33)
     tb, tp, tc = to_dev(dev, betas, pose, cam)
-    for precision, lbs in (("fp32", "fma"), ("bf16x3", "tc"), ("tf32", "tc")):
+    for precision, lbs in (("fp32", "fma"), ("bf16x3", "tc"), ("f16x3", "tc"), ("tf32", "tc")):
         layer = SMPL(models["sparse"], precision=precision, lbs=lbs).to(dev)
         full = layer(tb, tp, tc)
         parts = [layer(tb[a:b], tp[a:b], tc[a:b]) for a, b in ((0, 7), (7, 150), (150, 300))]
@@ -238,26 +239,12 @@ def test_other_model_shapes(dev, num_verts, num_betas):
     n = 200
     betas, pose, cam = synthetic.make_inputs(n, 61, num_betas=num_betas)
     ref_v, ref_j, ref_k = smpl_forward(model, betas, pose, cam)
-    for precision, lbs in (("fp32", "fma"), ("fp32", "tc"), ("bf16x3", "tc"), ("tf32", "tc")):
+    for precision, lbs in (("fp32", "fma"), ("fp32", "tc"), ("bf16x3", "tc"), ("f16x3", "tc"), ("tf32", "tc")):
         layer = SMPL(model, precision=precision, lbs=lbs).to(dev)
         v, j, k = layer(*to_dev(dev, betas, pose, cam))
         check_verts(v, ref_v, precision, f"V={num_verts} NB={num_betas} {precision}/{lbs}")
         assert_close(j, ref_j, what="joints")
         assert_close(k, ref_k, atol=2e-6, what="kp2d")
-
-
-def test_k1_two_sm_variant_is_bit_identical(dev, models, monkeypatch):
-    """The opt-in 2-SM (cta_group::2) blendshape kernel must equal the default 1-SM kernel bit for bit."""
-    n = 700
-    betas, pose, cam = synthetic.make_inputs(n, 71)
-    args = to_dev(dev, betas, pose, cam)
-    for precision in ("bf16x3", "bf16", "tf32"):
-        monkeypatch.delenv("SMPLB200_K1", raising=False)
-        ref = SMPL(models["sparse"], precision=precision, lbs="tc").to(dev)(*args)
-        monkeypatch.setenv("SMPLB200_K1", "2")          # read when the per-device handle is created
-        out = SMPL(models["sparse"], precision=precision, lbs="tc").to(dev)(*args)
-        assert torch.equal(out[0], ref[0]), precision
-    monkeypatch.delenv("SMPLB200_K1", raising=False)
 
 
 def test_cuda_graph_replay_matches_eager(dev, models):
