@@ -31,6 +31,8 @@
 //   * the skinning blend: 3-term fp16 split of BOTH operands (W_hi*A_hi + W_hi*A_lo + W_lo*A_hi, products
 //     exact in the fp32 accumulator): ~2e-7, the same fp32-class fidelity as k_lbs_tc's 3xTF32.
 //
+// The epilogue writes vertices straight from registers (lane = vertex, 12-byte stride), see the store comment.
+//
 // Schedule: persistent CTAs (one per SM) own equal contiguous ranges of the tile-major unit list.
 // Warp roles (672 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warps 1 and 20 = blend-MMA
 // issuers of T buffer 0 / 1, warp 2 = bulk-TMA producer of the A' images, warp 3 = D-MMA issuer (all issuers
@@ -43,22 +45,6 @@
 #include "common.cuh"
 #include "k_chain.cuh"
 #include "ptx.cuh"
-
-// epilogue variants (A/B-timed on one box, scripts/build_variant.sh)
-#ifndef FZ_STORE
-#define FZ_STORE 1        // 0: shared-memory transpose row  1: direct 12-byte-stride stores  2: register shuffles
-#endif
-#ifndef FZ_SPIN
-#define FZ_SPIN 0         // busy-poll (test_wait) instead of try_wait on the two accumulator hand-off waits
-#endif
-#if FZ_SPIN
-#define FZ_CHAIN_WAIT ptx::mbar_wait_spin
-#else
-#define FZ_CHAIN_WAIT ptx::mbar_wait_nohint
-#endif
-#ifndef FZ_DPREFETCH
-#define FZ_DPREFETCH 0    // fetch the D columns one sub-block ahead
-#endif
 
 namespace smplb200 {
 
@@ -75,10 +61,7 @@ constexpr uint32_t kFzPlaneLo = kFzShapeK * 128 * 2;            // 4,096
 constexpr uint32_t kFzBasisBytes = 3 * (kFzPlaneHi + kFzPlaneLo);   // 184,320 per vertex tile
 constexpr uint32_t kFzCoefLo = kFzShapeK * kFzBodies * 2;       // 2,048
 constexpr uint32_t kFzCoefBlock = kFzCoefLo + kCoefK * kFzBodies * 2;   // 30,720 per 64-body block
-#ifndef FZ_LEAD
-#define FZ_LEAD 6
-#endif
-constexpr int kFzDLead = FZ_LEAD;                                     // D groups run this many sub-blocks ahead of the pacing
+constexpr int kFzDLead = 6;                                     // D groups run this many sub-blocks ahead of the pacing
 constexpr int kFzChunks = 7;                                    // K chunks per unit: 2 k-steps each
 constexpr uint32_t kFzCoefStage = kFzCoefLo + 2 * 2048;         // 6,144 (chunk 0 carries the lo rows too)
 constexpr int kFzCoefStages = 3;
@@ -86,9 +69,8 @@ constexpr uint32_t kFzAImage = 7 * kFzNT * 16;                  // 5,376: [A_hi 
 constexpr int kFzAStages = 2;                                   // PER SLOT: each blend issuer has its own ring
 constexpr uint32_t kFzOffCoef = kFzBasisBytes;
 constexpr uint32_t kFzOffA = kFzOffCoef + kFzCoefStages * kFzCoefStage;
-constexpr uint32_t kFzOffOut = kFzOffA + 2 * kFzAStages * kFzAImage;
-constexpr uint32_t kFzOffBar = kFzOffOut + kFzEpiWarps * 96 * 4;       // per epilogue warp: one body x 96 floats
-constexpr uint32_t kFzSmemBytes = kFzOffBar + 256;              // 230,656 <= 232,448
+constexpr uint32_t kFzOffBar = kFzOffA + 2 * kFzAStages * kFzAImage;
+constexpr uint32_t kFzSmemBytes = kFzOffBar + 256;              // 224,512 <= 232,448
 constexpr uint32_t kFzTmemD = 0, kFzTmemT = 2 * 3 * kFzBodies, kFzTmemW = kFzTmemT + 2 * kFzNT;   // 0 | 384 | 480
 constexpr uint32_t kFzIdescD = ptx::make_idesc(ptx::kFmtF16, 128, kFzBodies);
 constexpr uint32_t kFzIdescT = ptx::make_idesc(ptx::kFmtF16, 128, kFzNT);
@@ -125,12 +107,11 @@ __device__ long long g_fz_time[148 * 32];
 __global__ void __launch_bounds__(kFzThreads, 1)
 k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__ w_rows,
            const uint8_t* __restrict__ coef_img, const uint8_t* __restrict__ a_img,
-           long long n, int nblk, long long total_units, int V, float* __restrict__ verts, int dbg) {
+           long long n, int nblk, long long total_units, int V, float* __restrict__ verts) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sBasis = smem;
   uint8_t* sCoef = smem + kFzOffCoef;
   uint8_t* sA = smem + kFzOffA;
-  float* sOut = reinterpret_cast<float*>(smem + kFzOffOut);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFzOffBar);
   uint64_t* bar_bfull = bars;                          // basis tile landed (tx)
   uint64_t* bar_bfree = bars + 1;                      // every MMA reading the old basis tile retired
@@ -338,17 +319,15 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
           // operand first (it has usually landed long ago), then the accumulator: when the epilogue frees the
           // T buffer nothing but the issue itself stands between that arrival and the next blend
           { FZ_T0(); ptx::mbar_wait_nohint(bar_afull + e * kFzAStages + st, a_phase); FZ_ACC(fz_a1); }
-          { FZ_T0(); FZ_CHAIN_WAIT(bar_tempty + e, te_phase); FZ_ACC(fz_a0); }
+          { FZ_T0(); ptx::mbar_wait_nohint(bar_tempty + e, te_phase); FZ_ACC(fz_a0); }
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-            if (!(dbg & 2)) {
-              ptx::mma_bf16_ts(t_tmem, tmem_w, dsc[st][0], kFzIdescT, 0u);        // W_hi * A_hi
-              ptx::mma_bf16_ts(t_tmem, tmem_w + 8, dsc[st][1], kFzIdescT, 1u);
-              ptx::mma_bf16_ts(t_tmem, tmem_w, dsc[st][2], kFzIdescT, 1u);        // W_hi * A_lo
-              ptx::mma_bf16_ts(t_tmem, tmem_w + 8, dsc[st][3], kFzIdescT, 1u);
-              ptx::mma_bf16_ts(t_tmem, tmem_w + 16, dsc[st][0], kFzIdescT, 1u);   // W_lo * A_hi
-              ptx::mma_bf16_ts(t_tmem, tmem_w + 24, dsc[st][1], kFzIdescT, 1u);
-            }
+            ptx::mma_bf16_ts(t_tmem, tmem_w, dsc[st][0], kFzIdescT, 0u);        // W_hi * A_hi
+            ptx::mma_bf16_ts(t_tmem, tmem_w + 8, dsc[st][1], kFzIdescT, 1u);
+            ptx::mma_bf16_ts(t_tmem, tmem_w, dsc[st][2], kFzIdescT, 1u);        // W_hi * A_lo
+            ptx::mma_bf16_ts(t_tmem, tmem_w + 8, dsc[st][3], kFzIdescT, 1u);
+            ptx::mma_bf16_ts(t_tmem, tmem_w + 16, dsc[st][0], kFzIdescT, 1u);   // W_lo * A_hi
+            ptx::mma_bf16_ts(t_tmem, tmem_w + 24, dsc[st][1], kFzIdescT, 1u);
             ptx::tc_commit(bar_aempty + e * kFzAStages + st);
             ptx::tc_commit(bar_tfull + e);
             if (e == 1)       // lets the D issuer release its next chunks
@@ -366,20 +345,12 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
     FZ_OUT(2 + e * 4, fz_a0); FZ_OUT(3 + e * 4, fz_a1);
   } else if (warp >= kFzEpiWarp0 && warp < kFzEpiWarp0 + kFzEpiWarps) {
     // ===== epilogue: slot e (T buffer), lane quarter q, body half h (bodies 2h, 2h+1 of each sub-block).
-    // Sixteen warps: one sub-block's transform + transpose + store is a long dependent chain (TMEM load ->
-    // FMAs -> shared-memory transpose -> stores), and with one warp per (slot, quarter) that chain, not any
-    // throughput limit, set the pace of the kernel. =====
+    // Thread = vertex: it reads its blended 3x4 transform (T) and its posed rest position (D) for two bodies from
+    // its own TMEM lane, applies the transform and stores the vertex. =====
     FZ_DECL;
     const int ew = warp - kFzEpiWarp0;
     const int q = warp & 3, e = (ew >> 2) & 1, h = ew >> 3;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* so = sOut + ew * 96;
-    (void)so;
-#if FZ_STORE == 2
-    int src_lane[3], src_comp[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { src_lane[j] = (32 * j + lane) / 3; src_comp[j] = (32 * j + lane) % 3; }
-#endif
     long long cur_tile = -1;
     int t_cnt = 0;                    // sub-blocks this warp has consumed (phase of its T buffer)
     uint32_t wf_phase = 0;            // parity of the next bar_wfree wait (slot 0 only)
@@ -420,39 +391,29 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
         cur_tile = tile;
       }
       const int warp_v0 = (int)tile * 128 + q * 32;
-      const int nf = max(0, min(32, V - warp_v0)) * 3;    // floats this warp may store per body
+      const int nv = max(0, min(32, V - warp_v0));        // vertices of this warp that exist (last tile is ragged)
       { FZ_T0(); ptx::mbar_wait_nohint(bar_dfull + a, (i >> 1) & 1); FZ_ACC(fz_a0); }
       const uint32_t d_addr0 = tmem_base + kFzTmemD + lane_addr + a * 3 * kFzBodies + 2 * h;
       uint32_t dx[2], dy[2], dz[2];
-#if FZ_DPREFETCH
-      // this warp's D values (two bodies x three planes) are fetched one sub-block ahead: the unit's D is
-      // complete (bar_dfull), so the load for sub-block sb+2 overlaps the work on sub-block sb
-      ptx::tc_fence_after();
-      ptx::tmem_ld2(d_addr0 + e * kFzSub, dx);
-      ptx::tmem_ld2(d_addr0 + e * kFzSub + kFzBodies, dy);
-      ptx::tmem_ld2(d_addr0 + e * kFzSub + 2 * kFzBodies, dz);
-#endif
       for (int sb = e; sb < kFzSubs; sb += 2) {
         const long long b0 = (long long)blk * kFzBodies + sb * kFzSub;
         SMPLB200_PROGRESS((i << 8) | sb);
-        { FZ_T0(); FZ_CHAIN_WAIT(bar_tfull + e, t_cnt & 1); FZ_ACC(fz_a1); }
+        { FZ_T0(); ptx::mbar_wait_nohint(bar_tfull + e, t_cnt & 1); FZ_ACC(fz_a1); }
         ++t_cnt;
         ptx::tc_fence_after();
         uint32_t r0[16], r1[8];
         const uint32_t t_addr = tmem_base + kFzTmemT + lane_addr + e * kFzNT + h * 24;
         ptx::tmem_ld16(t_addr, r0);
         ptx::tmem_ld8(t_addr + 16, r1);
-        ptx::tmem_ld_wait();                                   // (also completes a pending D prefetch)
+        ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(bar_tempty + e);      // T buffer free: the next blend of this slot may start
         __syncwarp();
-#if !FZ_DPREFETCH
         ptx::tmem_ld2(d_addr0 + sb * kFzSub, dx);
         ptx::tmem_ld2(d_addr0 + sb * kFzSub + kFzBodies, dy);
         ptx::tmem_ld2(d_addr0 + sb * kFzSub + 2 * kFzBodies, dz);
         ptx::tmem_ld_wait();
-#endif
         float T[24];
 #pragma unroll
         for (int k = 0; k < 16; ++k) T[k] = __uint_as_float(r0[k]);
@@ -467,26 +428,19 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
           res[3 * bb + 1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
           res[3 * bb + 2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
         }
-#if FZ_DPREFETCH
-        if (sb + 2 < kFzSubs) {                                 // prefetch the next sub-block's D columns
-          ptx::tmem_ld2(d_addr0 + (sb + 2) * kFzSub, dx);
-          ptx::tmem_ld2(d_addr0 + (sb + 2) * kFzSub + kFzBodies, dy);
-          ptx::tmem_ld2(d_addr0 + (sb + 2) * kFzSub + 2 * kFzBodies, dz);
-        } else
-#else
-        if (sb + 2 >= kFzSubs)
-#endif
-        {                                                       // this warp has read all it needs of the unit's D
+        if (sb + 2 >= kFzSubs) {                                // this warp has read all it needs of the unit's D
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(bar_dempty + a);
           __syncwarp();
         }
         const long long bh = b0 + 2 * h;                       // first of this warp's two bodies
-#if FZ_STORE == 1
-        // DIRECT stores: lane = vertex writes its own x, y, z (12-byte stride across the warp); the three store
-        // instructions of a body together cover the warp's 384 contiguous bytes
-        if (lane < nf / 3) {
+        // DIRECT stores: the lane writes its own x, y, z (12-byte stride across the warp).  The three store
+        // instructions of a body together cover the warp's 384 contiguous bytes, so every 32-byte sector is
+        // completed in L2 within a few cycles (ncu: DRAM bytes unchanged).  A/B on one box against the
+        // alternatives -- xyz interleave through a shared-memory row + coalesced 128-byte stores (round 1's k3
+        // epilogue): 143.8 us; interleave by register shuffles: 139.4 us; this: 136.7 us.
+        if (lane < nv) {
           float* d = verts + ((size_t)bh * V + warp_v0 + lane) * 3;
 #pragma unroll
           for (int bb = 0; bb < 2; ++bb) {
@@ -494,47 +448,9 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
             d += body_stride;
           }
         }
-#else
-        float* dst = verts + ((size_t)bh * V + warp_v0) * 3 + lane;
-        const bool full = bh + 2 <= n && nf == 96;             // both bodies, whole warp: unpredicated stores
-#pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-          float o0, o1, o2;
-#if FZ_STORE == 2
-          // xyz interleave IN REGISTERS: element 32j + lane of the warp's 96 output floats is component
-          // (32j + lane) % 3 of vertex (32j + lane) / 3: three shuffles (one per component) and a select each
-          float o[3];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float t0 = __shfl_sync(0xffffffffu, res[3 * bb], src_lane[j]);
-            const float t1 = __shfl_sync(0xffffffffu, res[3 * bb + 1], src_lane[j]);
-            const float t2 = __shfl_sync(0xffffffffu, res[3 * bb + 2], src_lane[j]);
-            o[j] = src_comp[j] == 0 ? t0 : (src_comp[j] == 1 ? t1 : t2);
-          }
-          o0 = o[0]; o1 = o[1]; o2 = o[2];
-#else
-          // xyz interleave through a per-warp shared-memory row (one body per pass: the shared-memory budget
-          // goes to the basis), then coalesced 128-byte stores
-          float* sbuf = so + 3 * lane;
-          sbuf[0] = res[3 * bb]; sbuf[1] = res[3 * bb + 1]; sbuf[2] = res[3 * bb + 2];
-          __syncwarp();
-          o0 = so[lane]; o1 = so[lane + 32]; o2 = so[lane + 64];
-#endif
-          float* d = dst + bb * body_stride;
-          if (full) {
-            d[0] = o0; d[32] = o1; d[64] = o2;
-          } else if (bh + bb < n) {
-            if (lane < nf) d[0] = o0;
-            if (lane + 32 < nf) d[32] = o1;
-            if (lane + 64 < nf) d[64] = o2;
-          }
-#if FZ_STORE == 0
-          __syncwarp();          // the row is reused by the next pass
-#endif
-        }
-#endif
       }
     }
+
     if (q == 0 && h == 0) { FZ_OUT(10 + 2 * e, fz_a0); FZ_OUT(11 + 2 * e, fz_a1); }
   }
   ptx::tc_fence_before();
@@ -597,9 +513,7 @@ inline cudaError_t launch_fused_tc(const DeviceModel& m, int num_sms, const uint
   const int nblk = (int)((n + kFzBodies - 1) / kFzBodies);
   const long long total = (long long)ntile * nblk;
   const unsigned grid = (unsigned)std::min<long long>(num_sms, total);
-  const char* dbg_env = std::getenv("SMPLB200_FZ_DBG");      // ablation knobs (1: no D MMAs, 2: no blend MMAs, 4: no stores)
-  k_fused_tc<<<grid, kFzThreads, kFzSmemBytes, s>>>(m.fz_basis, m.fz_w, coef_img, a_img, n, nblk, total, m.V, verts,
-                                                    dbg_env ? std::atoi(dbg_env) : 0);
+  k_fused_tc<<<grid, kFzThreads, kFzSmemBytes, s>>>(m.fz_basis, m.fz_w, coef_img, a_img, n, nblk, total, m.V, verts);
   return cudaGetLastError();
 }
 
