@@ -23,8 +23,8 @@
 // CTAs resident at one time read and write adjacent row chunks of the same bodies (DRAM pages).
 //
 // Epilogue thread = vertex: reads its 12 blended entries per body from TMEM, the planar vposed
-// coordinates (from the shared-memory ring, conflict-free), applies the 3x4 transform with FMAs,
-// transposes four bodies at a time through a per-warp shared-memory tile and emits coalesced stores.  k4 (weak-perspective projection,
+// coordinates (from the shared-memory ring, conflict-free), applies the 3x4 transform with FMAs and
+// stores its own x, y, z (direct 12-byte-stride stores, see the epilogue).  k4 (weak-perspective projection,
 // SURVEY.md A.8) rides in the epilogue of the CTAs that own vertex tile 0.
 #pragma once
 #include "common.cuh"
@@ -49,7 +49,7 @@ constexpr uint32_t kLbsVRow = kLbsTiles * 128 * 4;       // one (body, plane) ro
 constexpr uint32_t kLbsVStage = kLbsBlock * 3 * kLbsVRow;  // 24,576
 constexpr uint32_t kLbsVOff = kLbsBStages * kLbsBStage;
 constexpr uint32_t kLbsOutOff = kLbsVOff + kLbsVStages * kLbsVStage;
-constexpr uint32_t kLbsBarOff = kLbsOutOff + kLbsEpiWarps * 4 * 96 * 4;   // per warp: 4 bodies x 96 floats
+constexpr uint32_t kLbsBarOff = kLbsOutOff;
 constexpr uint32_t kLbsSmemBytes = kLbsBarOff + 256;     // ~160 KB, one CTA per SM
 constexpr uint32_t kLbsIdesc = ptx::make_idesc(ptx::kFmtTF32, 128, kLbsN);
 
@@ -61,7 +61,6 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sB = smem;
   uint8_t* sV = smem + kLbsVOff;
-  float* sOut = reinterpret_cast<float*>(smem + kLbsOutOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kLbsBarOff);
   uint64_t* bar_w = bars;                            // W' rows resident in TMEM (8 warp arrivals)
   uint64_t* bar_bfull = bars + 1;                    // [B stages] A' image landed
@@ -175,7 +174,6 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
     const int v_local = t * 128 + q * 32 + lane;       // column inside the staged tile-pair row
     const int warp_v0 = (tile0 + t) * 128 + q * 32;
     const int nf = max(0, min(32, V - warp_v0)) * 3;   // floats this warp may store per body
-    float* so = sOut + ew * (4 * 96);
     if (nblk > 0 && h == 0) {
       // W' rows of this vertex tile -> TMEM (A operand of every blend MMA of this tile)
       if (live) {
@@ -202,9 +200,7 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
       const long long b0 = (long long)(blk_begin + i) * kLbsBlock;
       const int nb = (int)min((long long)kLbsBlock, n - b0);
       const float* sv = reinterpret_cast<const float*>(sV + (size_t)s * kLbsVStage) + v_local;
-      const bool full = live && (nb == kLbsBlock) && (nf == 96);
       const size_t body_stride = (size_t)V * 3;
-      float* dst = verts + ((size_t)(b0 + 4 * h) * V + warp_v0) * 3 + lane;
       ptx::mbar_wait(bar_vfull + s, (i / kLbsVStages) & 1);
       ptx::mbar_wait(bar_tfull + a, (i / kLbsTcAcc) & 1);
       ptx::tc_fence_after();
@@ -231,42 +227,24 @@ k_lbs_tc(const uint32_t* __restrict__ w_rows, const uint8_t* __restrict__ a_img,
         for (int e = 0; e < 16; ++e) {
           T[e] = __uint_as_float(r0[e]); T[16 + e] = __uint_as_float(r1[e]); T[32 + e] = __uint_as_float(r2[e]);
         }
-        // all FMAs, then ONE shared-memory transpose (xyz interleave) and twelve independent
-        // coalesced stores: the STS -> LDS -> STG latency chain is paid once per block.
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const float* tt = T + bb * 12;
-          const float x = px[bb], y = py[bb], z = pz[bb];
-          float* sb = so + bb * 96 + 3 * lane;
-          sb[0] = fmaf(tt[2], z, fmaf(tt[1], y, fmaf(tt[0], x, tt[3])));
-          sb[1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
-          sb[2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
-        }
-        __syncwarp();
-        if (full) {                 // fast path: whole block, whole warp -> unpredicated stores
-          float o[12];
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            o[3 * bb] = so[bb * 96 + lane]; o[3 * bb + 1] = so[bb * 96 + lane + 32];
-            o[3 * bb + 2] = so[bb * 96 + lane + 64];
-          }
-#pragma unroll
-          for (int bb = 0; bb < 4; ++bb) {
-            float* d = dst + bb * body_stride;
-            d[0] = o[3 * bb]; d[32] = o[3 * bb + 1]; d[64] = o[3 * bb + 2];
-          }
-        } else if (live) {
+        // all FMAs, then DIRECT stores: the lane writes its own x, y, z (12-byte stride across the warp; the three
+        // store instructions of a body together cover the warp's 384 contiguous bytes, so every 32-byte sector is
+        // completed in L2 at once).  Round 1 interleaved xyz through a shared-memory tile for 128-byte stores;
+        // A/B-timed in the fused kernel the direct form is 5 % faster (no STS/LDS/warp barriers in the chain).
+        if (live && lane < nf / 3) {
+          float* d = verts + ((size_t)(b0 + 4 * h) * V + warp_v0 + lane) * 3;
 #pragma unroll
           for (int bb = 0; bb < 4; ++bb) {
             if (h * 4 + bb < nb) {
-              float* d = dst + bb * body_stride;
-#pragma unroll
-              for (int k = 0; k < 3; ++k)
-                if (lane + 32 * k < nf) d[32 * k] = so[bb * 96 + lane + 32 * k];
+              const float* tt = T + bb * 12;
+              const float x = px[bb], y = py[bb], z = pz[bb];
+              d[0] = fmaf(tt[2], z, fmaf(tt[1], y, fmaf(tt[0], x, tt[3])));
+              d[1] = fmaf(tt[6], z, fmaf(tt[5], y, fmaf(tt[4], x, tt[7])));
+              d[2] = fmaf(tt[10], z, fmaf(tt[9], y, fmaf(tt[8], x, tt[11])));
             }
+            d += body_stride;
           }
         }
-        __syncwarp();          // staging row is reused by the next block
       }
     }
     // k4: weak-perspective projection of this CTA's bodies (CTAs of the first tile pair only)
