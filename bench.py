@@ -293,7 +293,7 @@ def main():
     ap.add_argument("--weights", default="sparse", choices=["sparse", "dense"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip variants / configs_extra / next rows (profiling runs)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective", "off"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "dma", "collective", "off"])
     ap.add_argument("--kernel-iters", type=int, default=50)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -626,7 +626,7 @@ def main():
         dom = "fused_blend_skin" if fused else "k3_lbs"
         dom_kernel = "k_fused_tc" if fused else ("k_lbs_tc" if n >= capi.TC_LBS_MIN_BATCH else "k_lbs_fma")
         dom_bytes = BYTES_E2E if fused else BYTES_K3
-        launches_per_step = layer.launch_count(n, True, dev) + (2 if (exchange is not None and exchange.transport == "peer") else 0)
+        launches_per_step = layer.launch_count(n, True, dev) + (2 if (exchange is not None and exchange.transport == "peer") else 0)   # 'dma' exchange: no kernel
         traffic, traffic_src = ncu_traffic(dom_kernel) if n == BODIES_PER_GPU else (None, None)
         pcie_gbs = (h2d + d2h) / e2e_dt * 1e-9
         config = bench_config(n, world, args, strong)

@@ -83,6 +83,7 @@ SYMBOLS = {
     "smplb200_host_staging_layout": (_int, [_vp, _i64, _u32, C.POINTER(_sz), C.POINTER(_sz)]),
     "smplb200_push_rows": (_int, [C.c_int32, _vp, _vp, _i64, _i64, _vp, _vp, C.c_int32, C.c_int32, _u32, _vp, _vp]),
     "smplb200_wait_rows": (_int, [C.c_int32, _vp, C.c_int32, _u32, _vp]),
+    "smplb200_exchange_rows_dma": (_int, [C.c_int32, _vp, _vp, _i64, _i64, _i64, _vp, _vp, C.c_int32, C.c_int32, _u32, _vp]),
     "smplb200_probe_fp32_fma": (_int, [C.c_int32, C.c_int32, _vp, C.POINTER(C.c_double), _vp]),
     "smplb200_host_staging_bytes": (_sz, [_vp, _i64, _u32]),
     "smplb200_forward_host": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _u32, _vp]),

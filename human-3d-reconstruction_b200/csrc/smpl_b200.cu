@@ -1374,6 +1374,58 @@ int smplb200_push_rows(int32_t device, const float* joints, const float* kp2d, i
   return SMPLB200_OK;
 }
 
+// The same exchange with NO kernel at all: copy-engine (DMA) peer copies + stream memory operations.  Peer STORES
+// from SMs compete with the compute kernels' own global stores for each SM's store path (measured: the kernel push
+// adds exactly the NVLink transfer time to the step, ~1.2 us per MB pushed); DMA copies do not touch the SMs.
+int smplb200_exchange_rows_dma(int32_t device, const float* joints, const float* kp2d, int64_t n, int64_t row_offset,
+                               int64_t rows_total, void* const* peer_slots, void* const* peer_flags,
+                               int32_t world, int32_t rank, uint32_t epoch, void* stream) {
+  if (world < 1 || world > kXchgMaxRanks || rank < 0 || rank >= world || n < 0 || row_offset < 0 ||
+      rows_total < row_offset + n || !peer_slots || !peer_flags)
+    return SMPLB200_ERR_INVALID_ARG;
+  if (n > 0 && !joints) return SMPLB200_ERR_INVALID_ARG;
+  for (int r = 0; r < world; ++r)
+    if (!peer_slots[r] || !peer_flags[r]) return SMPLB200_ERR_INVALID_ARG;
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err);
+  // driver entry points for the stream memory operations, resolved through the runtime (no link-time libcuda)
+  typedef int (*WriteFn)(void*, unsigned long long, uint32_t, unsigned int);
+  typedef int (*WaitFn)(void*, unsigned long long, uint32_t, unsigned int);
+  static WriteFn write32 = nullptr;          // function pointers are process-wide constants once resolved
+  static WaitFn wait32 = nullptr;
+  if (!write32 || !wait32) {
+    void *w = nullptr, *q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CU_TRY(cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &qr));
+    CU_TRY(cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &qr));
+    if (!w || !q) return SMPLB200_ERR_UNSUPPORTED;
+    write32 = reinterpret_cast<WriteFn>(w);
+    wait32 = reinterpret_cast<WaitFn>(q);
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t jrow = kJ * 3 * sizeof(float), krow = kJ * 2 * sizeof(float);
+  for (int i = 0; i < world; ++i) {
+    const int r = (rank + 1 + i) % world;          // every rank starts with a different peer
+    uint8_t* slot = static_cast<uint8_t*>(peer_slots[r]);
+    if (n > 0) {
+      CU_TRY(cudaMemcpyAsync(slot + (size_t)row_offset * jrow, joints, (size_t)n * jrow, cudaMemcpyDeviceToDevice, s));
+      if (kp2d)
+        CU_TRY(cudaMemcpyAsync(slot + (size_t)rows_total * jrow + (size_t)row_offset * krow, kp2d, (size_t)n * krow,
+                               cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  for (int i = 0; i < world; ++i) {                // in stream order: after every copy above has completed
+    const int r = (rank + 1 + i) % world;
+    const unsigned long long addr = (unsigned long long)(uintptr_t)peer_flags[r] + (unsigned long long)rank * 4ull;
+    if (write32(s, addr, epoch, 0u /* CU_STREAM_WRITE_VALUE_DEFAULT */) != 0) return SMPLB200_ERR_CUDA;
+  }
+  for (int r = 0; r < world; ++r) {                // consumer side: all ranks' rows of this epoch have landed here
+    const unsigned long long addr = (unsigned long long)(uintptr_t)peer_flags[rank] + (unsigned long long)r * 4ull;
+    if (wait32(s, addr, epoch, 1u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) return SMPLB200_ERR_CUDA;
+  }
+  return SMPLB200_OK;
+}
+
 int smplb200_wait_rows(int32_t device, const void* my_flags, int32_t world, uint32_t epoch, void* stream) {
   if (world < 1 || world > kXchgMaxRanks || !my_flags) return SMPLB200_ERR_INVALID_ARG;
   DeviceGuard guard(device);

@@ -9,10 +9,13 @@ The forward needs NO collective.  The only optional exchange makes the small per
 body) always stay on the rank that produced them.  Two transports:
 
   * `PeerExchange` (the B200 path): each rank PUSHES its rows into every peer's copy of a
-    symmetric buffer with plain NVLink / NVSwitch peer stores from one small kernel
-    (`smplb200_push_rows`, csrc/k_exchange.cuh) and raises a per-rank flag; no NCCL launch anywhere.
-    It runs on a side stream that waits only for the forward's "joints ready" event (recorded
-    right after the ~10 us chain kernel), so it overlaps the blendshape / skinning kernels.
+    symmetric buffer over NVLink / NVSwitch and raises a per-rank flag; no NCCL launch anywhere.
+    Default ('dma'): copy-engine peer copies + stream memory operations, no kernel at all
+    (`smplb200_exchange_rows_dma`); alternative ('peer'): plain peer stores from one small kernel
+    (`smplb200_push_rows`, csrc/k_exchange.cuh) -- those stores share every SM's store path with
+    the compute kernels and cost the step exactly the NVLink transfer time (measured).
+    Either way it runs on a side stream that waits only for the forward's "joints ready" event
+    (recorded right after the ~10 us chain kernel), so it overlaps the blendshape / skinning kernels.
   * `all_gather_rows`: one fixed-size ``all_gather_into_tensor`` -- what `PeerExchange` falls back
     to (still on its side stream) when peer mapping is unavailable, and what the ``gloo`` tests
     exercise on CPU.
@@ -76,8 +79,10 @@ class PeerExchange:
     alternate: a view stays valid until the next-but-one exchange, provided its consumer runs in
     stream order before the next ``exchange`` call is enqueued (the usual pipeline).
 
-    transport 'peer': symmetric memory (``torch.distributed._symmetric_memory``: one rendezvous at
-    construction maps every rank's buffer into this process) + the library's peer-store kernels.
+    transport 'dma' ('auto' picks it): symmetric memory (``torch.distributed._symmetric_memory``: one
+    rendezvous at construction maps every rank's buffer into this process) + copy-engine peer copies and
+    stream memory operations (``smplb200_exchange_rows_dma``): nothing runs on the SMs.
+    transport 'peer': the same mapping + the library's peer-store kernels.
     transport 'collective': ``all_gather_into_tensor`` on the side stream (fallback; CPU/gloo tests).
     """
 
@@ -92,12 +97,24 @@ class PeerExchange:
         self.why_not_peer = None
         cuda = self.device.type == "cuda"
         self.stream = torch.cuda.Stream(device=self.device) if cuda else None
-        if transport in ("auto", "peer") and cuda and self.world > 1:
+        if transport in ("auto", "peer", "dma") and cuda and self.world > 1:
             try:
                 self._setup_peer()
                 self.transport = "peer"
+                if transport in ("auto", "dma"):
+                    # probe the copy-engine path once (epoch 0: writes 0 into flags that are 0, waits for >= 0);
+                    # 'auto' falls back to the peer-store kernels if the stream memory operations are unavailable
+                    st = self._lib.smplb200_exchange_rows_dma(
+                        self._dev_index, None, None, 0, 0, self.rows, self._peer_slots[0], self._peer_flags,
+                        self.world, self.rank, 0, self.stream.cuda_stream)
+                    if st == 0:
+                        self.transport = "dma"
+                    elif transport == "dma":
+                        self._check(st, "smplb200_exchange_rows_dma")
+                    else:
+                        self.why_not_peer = "stream memory operations unavailable: using the peer-store kernels"
             except Exception as e:      # no IPC between these processes / unsupported build: say so, fall back
-                if transport == "peer":
+                if transport in ("peer", "dma"):
                     raise
                 self.why_not_peer = f"{type(e).__name__}: {e}"
         if self.transport == "collective":
@@ -139,6 +156,19 @@ class PeerExchange:
                 self.stream.wait_event(ready)
             else:
                 self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if self.transport == "dma":           # copy-engine copies + stream memory ops: no kernel, one C call
+            st = self._lib.smplb200_exchange_rows_dma(
+                self._dev_index, joints.data_ptr(), None if kp2d is None else kp2d.data_ptr(), n, lo, self.rows,
+                self._peer_slots[slot], self._peer_flags, self.world, self.rank, self.epoch & 0xFFFFFFFF,
+                self.stream.cuda_stream)
+            if st:
+                self._check(st, "smplb200_exchange_rows_dma")
+            done = self._done[slot]
+            done.record(self.stream)
+            flat = self.buf[slot].view(-1)        # slot layout: joints block [rows][72] | kp2d block [rows][48]
+            j_all = flat[: self.rows * 72].view(self.rows, 24, 3)[: self.n_total]
+            k_all = flat[self.rows * 72:].view(self.rows, 24, 2)[: self.n_total]
+            return j_all, k_all, done
         if self.transport == "peer":          # two C calls on the side stream; no torch stream context needed
             idx, s, ep = self._dev_index, self.stream.cuda_stream, self.epoch & 0xFFFFFFFF
             st = self._push(idx, joints.data_ptr(), None if kp2d is None else kp2d.data_ptr(), n, lo,

@@ -180,6 +180,14 @@ int smplb200_push_rows(int32_t device, const float* joints, const float* kp2d, i
                        void* const* peer_buffers, void* const* peer_flags, int32_t world, int32_t rank,
                        uint32_t epoch, void* counter, void* stream);
 int smplb200_wait_rows(int32_t device, const void* my_flags, int32_t world, uint32_t epoch, void* stream);
+/* The same exchange with no kernel at all: copy-engine peer copies of the two contiguous row blocks, then stream
+ * memory operations (cuStreamWriteValue32 publishes `epoch` in every peer's flags[rank]; cuStreamWaitValue32 holds
+ * `stream` until all `world` local flags have reached it).  Slot layout here: joints block [rows_total][72] fp32
+ * followed by the kp2d block [rows_total][48].  Peer stores issued by SMs share each SM's store path with the
+ * compute kernels; DMA copies do not.                                                                     */
+int smplb200_exchange_rows_dma(int32_t device, const float* joints, const float* kp2d, int64_t n, int64_t row_offset,
+                               int64_t rows_total, void* const* peer_slots, void* const* peer_flags,
+                               int32_t world, int32_t rank, uint32_t epoch, void* stream);
 
 /* Measurement aid for bench.py (the fp32-FMA peak is measured in the same run): launches
  * 8 CTAs per SM of 256 threads running 8 independent FMA chains for `iters` rounds; `*flop` receives the

@@ -1,12 +1,15 @@
 #!/bin/bash
 # Weak (4096 bodies per GPU) and strong (65,536 bodies in total) scaling at 1/2/4/8 GPUs of one box.
-#   usage (on an 8-GPU box): bash scripts/scale_run.sh <tag>
+#   usage (on an 8-GPU box): bash scripts/scale_run.sh <tag> ["weak strong"] ["1 2 4 8"] [auto|dma|peer|collective|off]
 TAG=${1:-r02}
+MODES=${2:-"weak strong"}
+NS=${3:-"1 2 4 8"}
+XCHG=${4:-auto}
 mkdir -p gpurun_out
 P=29600
-for N in 1 2 4 8; do
-  for MODE in weak strong; do
-    EXTRA="--no-extras --no-cpu-baseline --steps 50 --warmup 10"
+for N in $NS; do
+  for MODE in $MODES; do
+    EXTRA="--no-extras --no-cpu-baseline --steps 100 --warmup 10 --exchange $XCHG"
     [ $MODE = strong ] && EXTRA="$EXTRA --total-bodies 65536"
     OUT=gpurun_out/${TAG}_scale_${MODE}_${N}.json
     if [ $N = 1 ]; then

@@ -66,7 +66,7 @@ def test_sharded_forward_and_gather_gloo_world2(tmp_path, n):
     assert all((tmp_path / f"ok{r}").exists() for r in range(2))
 
 
-def _gpu_worker(rank, world, port, n, tmp):
+def _gpu_worker(rank, world, port, n, tmp, transport="auto"):
     """Two processes, one GPU each, NCCL for rendezvous only: the joints | kp2d rows travel by peer stores."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -76,7 +76,7 @@ def _gpu_worker(rank, world, port, n, tmp):
     try:
         from human_3d_reconstruction_b200 import SMPL, synthetic
         layer = SMPL.synthetic(0).to(dev)
-        ex = sharding.PeerExchange(n, dev)
+        ex = sharding.PeerExchange(n, dev, transport=transport)
         sh = sharding.ShardedSMPL(layer, exchange=ex)
         with torch.no_grad():
             for step in range(5):                                   # > 2 steps: both slots are reused
@@ -94,10 +94,14 @@ def _gpu_worker(rank, world, port, n, tmp):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two visible GPUs")
+@pytest.mark.parametrize("transport", ["auto", "dma"])
 @pytest.mark.parametrize("n", [4096, 777])
-def test_peer_store_exchange_two_gpus(tmp_path, n):
-    port = 29700 + (os.getpid() % 200) + (n % 7)
-    mp.spawn(_gpu_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+def test_peer_store_exchange_two_gpus(tmp_path, n, transport):
+    """'auto' = peer stores from a kernel; 'dma' = copy-engine copies + stream memory operations."""
+    port = 29700 + (os.getpid() % 200) + (n % 7) + (13 if transport == "dma" else 0)
+    mp.spawn(_gpu_worker, args=(2, port, n, str(tmp_path), transport), nprocs=2, join=True)
     got = [(tmp_path / f"ok{r}").read_text() for r in range(2)]
     print("exchange transport:", got)
-    assert all(g.startswith("peer") or g.startswith("collective") for g in got)
+    assert all(g.startswith(("peer", "dma", "collective")) for g in got)
+    if transport == "dma":
+        assert all(g.startswith("dma") for g in got)
