@@ -1,4 +1,4 @@
-// k1 + k3 (+ the transpose/store of k3's epilogue) FUSED: blendshapes and linear blend skinning of a
+// k1 + k3 FUSED: blendshapes and linear blend skinning of a
 // (128-vertex tile, 64-body block) unit in one CTA, both contractions on tcgen05, accumulators in
 // tensor memory -- the v_posed intermediate (82,680 B per body written by k1 and read back by k3,
 // 2/3 of the unfused step's DRAM traffic) never exists.
@@ -20,7 +20,7 @@
 //     chunk feeds the MMAs of all three planes before it is released.
 //   * skinning weights W' = [W_hi | W_lo] of the tile live in TMEM (32 columns) as the A operand of the
 //     blend MMAs (TS form, N = 48 = 4 bodies x 12 entries, ~32 clk each); the joint transforms A' stream
-//     through their own 3-stage ring, one 5.3 KB image per 4-body sub-block.
+//     through two 2-stage rings (one per blend issuer), one 5.3 KB image per 4-body sub-block.
 //   * TMEM: D double-buffered (2 x 3 x 64 columns), T double-buffered (2 x 48), W' (32) = 512 columns.
 //
 // Precision (SMPLB200_PREC_F16): fp16 operands (11 significant bits), fp32 accumulation.
@@ -37,8 +37,9 @@
 // Warp roles (672 threads): warp 0 = bulk-TMA producer (basis tile, coef chunks), warps 1 and 20 = blend-MMA
 // issuers of T buffer 0 / 1, warp 2 = bulk-TMA producer of the A' images, warp 3 = D-MMA issuer (all issuers
 // warp-uniform, one elected lane), warps 4..19 = epilogue: TMEM lane quarter q = warp % 4, slot e takes the
-// sub-blocks s = e, e + 2, ... (T buffer e), body half h takes two of the sub-block's four bodies.  The D issuer runs up to one unit ahead (D is double-buffered), so
-// the tensor pipe interleaves the next unit's blendshape MMAs with this unit's blend MMAs.
+// sub-blocks s = e, e + 2, ... (T buffer e), body half h takes two of the sub-block's four bodies.  The D issuer
+// runs up to one unit ahead (D is double-buffered), so the tensor pipe interleaves the next unit's blendshape
+// MMAs with this unit's blend MMAs.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -121,10 +122,10 @@ k_fused_tc(const uint8_t* __restrict__ basis_tiles, const uint32_t* __restrict__
   uint64_t* bar_afull = bar_cempty + kFzCoefStages;    // [slot][2] A' image landed
   uint64_t* bar_aempty = bar_afull + 2 * kFzAStages;   // [slot][2]
   uint64_t* bar_dfull = bar_aempty + 2 * kFzAStages;   // [2] D accumulators of a unit complete
-  uint64_t* bar_dempty = bar_dfull + 2;                // [2] drained by the 8 epilogue warps
+  uint64_t* bar_dempty = bar_dfull + 2;                // [2] drained by the 16 epilogue warps
   uint64_t* bar_tfull = bar_dempty + 2;                // [2] blend accumulator complete
-  uint64_t* bar_tempty = bar_tfull + 2;                // [2] read by the 4 warps of its slot
-  uint64_t* bar_wfree = bar_tempty + 2;                // slot-1 epilogue warps are done with the old tile's W' (4 arrivals)
+  uint64_t* bar_tempty = bar_tfull + 2;                // [2] read by the 8 warps of its slot
+  uint64_t* bar_wfree = bar_tempty + 2;                // slot-1 epilogue warps are done with the old tile's W' (8 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_wfree + 1);
   volatile uint32_t* pace = tmem_slot + 1;             // blend groups issued so far (paces the D issuer, see below)
 
