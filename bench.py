@@ -671,6 +671,10 @@ def main():
         }
         emit(line)
     if world > 1:
+        # rank 0 is still busy with the extras while the others are done: nobody unmaps the symmetric exchange
+        # buffers (or leaves the process group) before everyone has arrived here
+        dist.barrier()
+        exchange = None
         dist.destroy_process_group()
     return 0
 
