@@ -40,3 +40,26 @@ def test_network_shape_is_the_reference_dla34():
     with torch.no_grad():
         out = net.eval()(torch.zeros(1, 3, 96, 64))[0]
     assert out["pose"].shape == (1, 72, 24, 16) and out["hm"].shape == (1, 1, 24, 16)   # down_ratio 4
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/lib"), reason="reference tree only exists in the build container")
+def test_restatement_equals_the_unmodified_reference_network():
+    """Where the reference is importable: same state_dict keys, equal seeded weights, bit-identical head maps."""
+    import contextlib
+    import io
+    sys.path.insert(0, "/root/reference/src/lib")
+    from models.model import dla_net as dla_reference
+    torch.manual_seed(SEED)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = dla_reference(dict(HEADS_HMR), num_layers=34, head_conv=256, down_ratio=4, not_use_dcn=True).eval()
+    mine = dla_net(dict(HEADS_HMR), seed=SEED).eval()
+    sd_ref, sd_mine = ref.state_dict(), mine.state_dict()
+    assert list(sd_ref.keys()) == list(sd_mine.keys())
+    assert all(torch.equal(sd_ref[k], sd_mine[k]) for k in sd_ref)
+    x = golden_input()
+    with torch.no_grad():
+        a, b = ref(x)[0], mine(x)[0]
+    assert all(torch.equal(a[h], b[h]) for h in HEADS_HMR)
