@@ -113,8 +113,9 @@ class SMPL(nn.Module):
              ``posedirs[207,3V]``, ``J_regressor[V,24]``, ``weights[V,24]``, ``parents[24]`` in the
              eager layer's layouts -- or the official SMPL file layout
              (``shapedirs[V,3,NB]``, ``J_regressor[24,V]`` dense/sparse, ``kintree_table``), see model_io.
-      precision: 'auto' | 'fp32' | 'bf16' | 'tf32' | 'bf16x3' | 'f16'  (blendshape operands; 'f16' = the
-             fused blendshapes+skinning kernel, stated vertex bound 5e-5 m)
+      precision: 'auto' | 'fp32' | 'bf16' | 'tf32' | 'bf16x3' | 'f16x3' | 'f16'  (blendshape operands;
+             'auto' = fp32 FMA below 32 bodies, 'f16x3' (split fp16, bound 4e-6 m) from there; 'f16' =
+             the fused blendshapes+skinning kernel, stated vertex bound 5e-5 m)
       joints: 'kinematic' (J_posed of the chain, default) | 'regressed' (HMR-style, from vertices)
       rotate_base: HMR's root pre-rotation by diag(1,-1,-1); default False
       lbs: 'auto' | 'fma' | 'tc' | 'dense'  (skinning kernel)
