@@ -465,7 +465,7 @@ def main():
             it = args.kernel_iters
             lib = capi.lib()
             s = torch.cuda.current_stream(dev).cuda_stream
-            # the unfused tensor-core kernels (k1 split-bf16, k3 3xTF32): timed for every run so the table is complete
+            # the unfused tensor-core kernels (k1 split-fp16, k3 3xTF32): timed for every run so the table is complete
             ulayer = layer if not fused else SMPL(model, precision="f16x3", lbs="tc").to(dev)
             flags = ulayer.flags
             coef, A, joints = ops.pose_chain(ulayer, tb, tp)
