@@ -97,7 +97,14 @@ def _gpu_worker(rank, world, port, n, tmp, transport="auto"):
 @pytest.mark.parametrize("transport", ["auto", "dma"])
 @pytest.mark.parametrize("n", [4096, 777])
 def test_peer_store_exchange_two_gpus(tmp_path, n, transport):
-    """'auto' = peer stores from a kernel; 'dma' = copy-engine copies + stream memory operations."""
+    """'auto' = peer stores from a kernel; 'dma' = copy-engine copies + stream memory operations.
+
+    The 'dma' cases passed on a 2-GPU box, but that transport's stream-memory-operation wait has no time bound and
+    its one 8-GPU run did not finish: it is opt-in in the product and opt-in here
+    (SMPLB200_TEST_DMA=1), so that an unattended suite can never sit in an unbounded wait.
+    """
+    if transport == "dma" and os.environ.get("SMPLB200_TEST_DMA") != "1":
+        pytest.skip("opt-in transport: set SMPLB200_TEST_DMA=1")
     port = 29700 + (os.getpid() % 200) + (n % 7) + (13 if transport == "dma" else 0)
     mp.spawn(_gpu_worker, args=(2, port, n, str(tmp_path), transport), nprocs=2, join=True)
     got = [(tmp_path / f"ok{r}").read_text() for r in range(2)]
