@@ -91,3 +91,26 @@ def test_product_never_imports_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("oracle/", ""), f"{fn} mentions the oracle module"
             assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_missing_library_fails_loudly_and_nothing_falls_back():
+    """The product has no CPU path: without the built .so every entry raises, it does not compute elsewhere."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch\n"
+        "from human_3d_reconstruction_b200 import SMPL, capi, synthetic\n"
+        "layer = SMPL(synthetic.make_model(3, num_verts=300))\n"
+        "b, p, c = synthetic.make_inputs(4, 1)\n"
+        "try:\n"
+        "    layer(torch.from_numpy(b), torch.from_numpy(p), torch.from_numpy(c))\n"
+        "except RuntimeError as e:\n"
+        "    print('RAISED', e)\n"
+        "try:\n"
+        "    capi.lib()\n"
+        "except RuntimeError as e:\n"
+        "    print('LOADER', e)\n")
+    env = dict(os.environ, SMPLB200_LIB="/nonexistent/libsmpl_b200.so", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "RAISED" in r.stdout and "LOADER" in r.stdout and "no cpu fallback" in r.stdout.lower()
