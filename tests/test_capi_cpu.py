@@ -114,3 +114,20 @@ def test_missing_library_fails_loudly_and_nothing_falls_back():
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-1500:]
     assert "RAISED" in r.stdout and "LOADER" in r.stdout and "no cpu fallback" in r.stdout.lower()
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 and a C program links and calls the library."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "c_abi_probe")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_abi_probe.c"), "-o", exe, "-L", libdir, "-lsmpl_b200",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "version 120" in r.stdout and "create(NULL) 1 invalid argument" in r.stdout
