@@ -131,3 +131,21 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "version 120" in r.stdout and "create(NULL) 1 invalid argument" in r.stdout
+
+
+def test_integration_md_ctypes_stub_matches_the_library():
+    """The stub INTEGRATION.md shows a reference maintainer is executable as written: it loads the library, its
+    descriptor has the header's layout, and its create() reaches the C call (which reports 'no device' here)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = next(b for b in blocks if "C.CDLL(" in b)
+    ns = {}
+    exec(stub.replace("/path/to/libsmpl_b200.so", capi.LIB_PATH), ns)
+    Desc = ns["Desc"]
+    assert ctypes.sizeof(Desc) == ctypes.sizeof(capi.ModelDesc)
+    assert [(n, getattr(Desc, n).offset) for n, _ in Desc._fields_] == \
+           [(n, getattr(capi.ModelDesc, n).offset) for n, _ in capi.ModelDesc._fields_]
+    assert ns["lib"].smplb200_strerror(1) == b"invalid argument"
+    if not torch.cuda.is_available():
+        with pytest.raises(AssertionError):          # model_create != 0 without a device: the stub's assert fires
+            ns["create"](synthetic.make_model(3, num_verts=300))
